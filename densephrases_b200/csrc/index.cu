@@ -1,0 +1,444 @@
+// index.cu -- the dph_index handle: construction, synthetic generation, search orchestration, reconstruct.
+// C ABI declared in include/dph_b200.h (each entry point cites the reference call it replaces).
+#include "index_internal.cuh"
+#include <algorithm>
+#include <mutex>
+#include <numeric>
+#include <string.h>
+
+static thread_local std::string g_err;
+void dph_set_error(const std::string& msg) { g_err = msg; }
+DPH_API const char* dph_last_error(void) { return g_err.c_str(); }
+DPH_API int dph_version(void) { return 100; }
+
+int DevBuf::ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    DPH_CUDA(cudaMalloc(&p, want));
+    cap = want;
+    return 0;
+}
+void DevBuf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+
+template <class T> static int dev_alloc(T** out, size_t count, dph_index* ix) {
+    if (*out) { cudaFree(*out); *out = nullptr; }
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    DPH_CUDA(cudaMalloc((void**)out, bytes));
+    ix->bytes += (int64_t)bytes;
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// generators (bit-identical to oracle/ivfpq_ref.c)
+// -------------------------------------------------------------------------------------------------
+__global__ void gen_normal_kernel(float* out, long long rows, int cols, uint64_t seed, uint64_t stream, float sc) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    long long r = i / cols; int t = (int)(i % cols);
+    out[i] = dph_approx_normal(dph_rnd64(seed, stream, (uint64_t)r, (uint64_t)t), sc);
+}
+
+// Block -> list lookup inside the shard: last l in [lo,hi) with blk_off[l] <= blk.
+__device__ __forceinline__ long long list_of_block(const long long* blk_off, long long lo, long long hi, long long blk) {
+    while (hi - lo > 1) { long long mid = (lo + hi) >> 1; if (blk_off[mid] <= blk) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// One thread per (block, lane, 16-byte chunk): writes the interleaved/rotated layout (common.cuh).
+// raw != nullptr: gather from list-major rows [*,96] (row index = local_row_start[l] + j); else synthesise from seed.
+__global__ void __launch_bounds__(192) fill_blocks_kernel(uint8_t* codes, long long nblocks, const long long* blk_off, const int* list_len,
+                                                          long long list_lo, long long list_hi, const uint8_t* raw,
+                                                          const long long* local_row_start, uint64_t seed) {
+    const long long blk = blockIdx.x;
+    if (blk >= nblocks) return;
+    const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;   // c in 0..5
+    __shared__ long long s_l;
+    if (threadIdx.x == 0) s_l = list_of_block(blk_off, list_lo, list_hi, blk);
+    __syncthreads();
+    const long long l = s_l;
+    const long long j = (blk - blk_off[l]) * 32 + lane;
+    const bool valid = j < (long long)list_len[l];
+    const int seg = c >> 1;
+    unsigned char bytes[16];
+    if (!valid) {
+#pragma unroll
+        for (int b = 0; b < 16; b++) bytes[b] = 0;
+    } else if (raw) {
+        const uint8_t* row = raw + (local_row_start[l - list_lo] + j) * DPH_CODE;
+#pragma unroll
+        for (int b = 0; b < 16; b++) { int t = c * 16 + b; int m = seg * 32 + ((lane + (t & 31)) & 31); bytes[b] = row[m]; }
+    } else {
+        uint64_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) w[i] = dph_rnd64(seed, DPH_STREAM_CODES, (uint64_t)l, (uint64_t)(j * 12 + seg * 4 + i));
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+            int t = c * 16 + b; int ml = (lane + (t & 31)) & 31;     // byte within the 32-byte segment
+            bytes[b] = (unsigned char)(w[ml >> 3] >> (8 * (ml & 7)));
+        }
+    }
+    uint4 v;
+    memcpy(&v, bytes, 16);
+    *reinterpret_cast<uint4*>(codes + blk * DPH_BLK_BYTES + c * 512 + lane * 16) = v;
+}
+
+__global__ void fill_ids_kernel(long long* ids, long long nblocks, const long long* blk_off, const int* list_len, long long list_lo,
+                                long long list_hi, const long long* raw_ids, const long long* local_row_start) {
+    const long long blk = blockIdx.x;
+    if (blk >= nblocks) return;
+    const long long l = list_of_block(blk_off, list_lo, list_hi, blk);
+    const long long j = (blk - blk_off[l]) * 32 + threadIdx.x;
+    ids[blk * 32 + threadIdx.x] = (j < (long long)list_len[l]) ? raw_ids[local_row_start[l - list_lo] + j] : -1;
+}
+
+// -------------------------------------------------------------------------------------------------
+// construction
+// -------------------------------------------------------------------------------------------------
+DPH_API int dph_index_create(dph_index** out, int d, int64_t nlist, int M, int nbits, int device) {
+    DPH_CHECK(out != nullptr, "null out");
+    DPH_CHECK(d == DPH_D && M == DPH_M && nbits == 8, "only d=768, M=96, nbits=8 (OPQ96/PQ96 of build_phrase_index.py:113-116) is built");
+    DPH_CHECK(nlist >= 1 && nlist < (1ll << 31), "bad nlist");
+    DPH_CUDA(cudaSetDevice(device));
+    dph_index* ix = new dph_index();
+    ix->device = device; ix->nlist = nlist; ix->list_lo = 0; ix->list_hi = nlist;
+    cudaDeviceProp prop;
+    DPH_CUDA(cudaGetDeviceProperties(&prop, device));
+    ix->num_sms = prop.multiProcessorCount;
+    if (prop.major != 10) { delete ix; dph_set_error("libdph_b200 is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor)); return 1; }
+    *out = ix;
+    return 0;
+}
+DPH_API void dph_index_free(dph_index* ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    void* ptrs[] = {ix->A, ix->C, ix->pq, ix->list_len, ix->list_start, ix->blk_off, ix->codes, ix->ids, ix->dm_ids, ix->dm_rows};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    DevBuf* bufs[] = {&ix->xdev, &ix->xr, &ix->S, &ix->key, &ix->cd, &ix->lut_scan, &ix->lut_canon, &ix->lutmax, &ix->segs, &ix->wpre, &ix->qinfo,
+                      &ix->cand, &ix->cand_off, &ix->cand_cnt, &ix->gthr, &ix->flags, &ix->work, &ix->Dp, &ix->Ip, &ix->Gp, &ix->Dh, &ix->Ih, &ix->eps};
+    for (DevBuf* b : bufs) b->release();
+    delete ix;
+}
+DPH_API int dph_index_set_stream(dph_index* ix, void* s) { ix->stream = (cudaStream_t)s; return 0; }
+
+static int upload(float** dst, const float* src, size_t count, int mem, dph_index* ix) {
+    DPH_CUDA(cudaSetDevice(ix->device));
+    DPH_TRY(dev_alloc(dst, count, ix));
+    DPH_CUDA(cudaMemcpyAsync(*dst, src, count * sizeof(float), mem == DPH_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ix->stream));
+    DPH_CUDA(cudaStreamSynchronize(ix->stream));
+    return 0;
+}
+DPH_API int dph_index_set_opq(dph_index* ix, const float* A, int mem) { return upload(&ix->A, A, (size_t)ix->d * ix->d, mem, ix); }
+DPH_API int dph_index_set_centroids(dph_index* ix, const float* C, int mem) { return upload(&ix->C, C, (size_t)ix->nlist * ix->d, mem, ix); }
+DPH_API int dph_index_set_pq(dph_index* ix, const float* pq, int mem) { return upload(&ix->pq, pq, (size_t)DPH_M * 256 * DPH_DSUB, mem, ix); }
+
+DPH_API int dph_index_gen_centroids(dph_index* ix, uint64_t seed, float sigma) {
+    DPH_CUDA(cudaSetDevice(ix->device));
+    DPH_TRY(dev_alloc(&ix->C, (size_t)ix->nlist * ix->d, ix));
+    long long tot = (long long)ix->nlist * ix->d;
+    gen_normal_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ix->stream>>>(ix->C, ix->nlist, ix->d, seed, DPH_STREAM_CENTROIDS, sigma / DPH_IH4_STD);
+    DPH_CUDA(cudaGetLastError());
+    return 0;
+}
+DPH_API int dph_index_gen_pq(dph_index* ix, uint64_t seed, float sigma) {
+    DPH_CUDA(cudaSetDevice(ix->device));
+    DPH_TRY(dev_alloc(&ix->pq, (size_t)DPH_M * 256 * DPH_DSUB, ix));
+    long long rows = DPH_M * 256;
+    gen_normal_kernel<<<(unsigned)((rows * DPH_DSUB + 255) / 256), 256, 0, ix->stream>>>(ix->pq, rows, DPH_DSUB, seed, DPH_STREAM_PQ, sigma / DPH_IH4_STD);
+    DPH_CUDA(cudaGetLastError());
+    return 0;
+}
+DPH_API int dph_index_set_shard(dph_index* ix, int64_t lo, int64_t hi) {
+    DPH_CHECK(0 <= lo && lo <= hi && hi <= ix->nlist, "bad shard range");
+    DPH_CHECK(ix->codes == nullptr, "set_shard must precede set_lists");
+    ix->list_lo = lo; ix->list_hi = hi;
+    return 0;
+}
+
+static int set_lists_common(dph_index* ix, const int64_t* list_len, const uint8_t* codes, const int64_t* ids, bool synthetic, uint64_t seed) {
+    DPH_CUDA(cudaSetDevice(ix->device));
+    const int64_t nlist = ix->nlist, lo = ix->list_lo, hi = ix->list_hi;
+    ix->h_list_len.assign(list_len, list_len + nlist);
+    ix->h_list_start.assign(nlist + 1, 0);
+    for (int64_t l = 0; l < nlist; l++) {
+        DPH_CHECK(list_len[l] >= 0 && list_len[l] < (1ll << 31), "bad list length");
+        ix->h_list_start[l + 1] = ix->h_list_start[l] + list_len[l];
+    }
+    ix->ntotal = ix->h_list_start[nlist];
+    std::vector<int32_t> len32(nlist);
+    std::vector<int64_t> blk_off(nlist, -1), local_row_start(std::max<int64_t>(hi - lo, 1), 0);
+    int64_t nb = 0, rows = 0;
+    for (int64_t l = 0; l < nlist; l++) len32[l] = (int32_t)list_len[l];
+    for (int64_t l = lo; l < hi; l++) {
+        blk_off[l] = nb; local_row_start[l - lo] = rows;
+        nb += (list_len[l] + 31) / 32; rows += list_len[l];
+    }
+    ix->nblocks_local = nb; ix->ntotal_local = rows;
+    DPH_TRY(dev_alloc(&ix->list_len, (size_t)nlist, ix));
+    DPH_TRY(dev_alloc(&ix->list_start, (size_t)nlist + 1, ix));
+    DPH_TRY(dev_alloc(&ix->blk_off, (size_t)nlist, ix));
+    DPH_CUDA(cudaMemcpy(ix->list_len, len32.data(), nlist * 4, cudaMemcpyHostToDevice));
+    DPH_CUDA(cudaMemcpy(ix->list_start, ix->h_list_start.data(), (nlist + 1) * 8, cudaMemcpyHostToDevice));
+    DPH_CUDA(cudaMemcpy(ix->blk_off, blk_off.data(), nlist * 8, cudaMemcpyHostToDevice));
+    DPH_TRY(dev_alloc(&ix->codes, (size_t)nb * DPH_BLK_BYTES, ix));
+    if (nb == 0) return 0;
+    int64_t* d_lrs = nullptr;
+    DPH_CUDA(cudaMalloc((void**)&d_lrs, local_row_start.size() * 8));
+    DPH_CUDA(cudaMemcpy(d_lrs, local_row_start.data(), local_row_start.size() * 8, cudaMemcpyHostToDevice));
+    if (synthetic) {
+        fill_blocks_kernel<<<(unsigned)nb, 192, 0, ix->stream>>>(ix->codes, nb, (const long long*)ix->blk_off, ix->list_len, lo, hi, nullptr,
+                                                              (const long long*)d_lrs, seed);
+        DPH_CUDA(cudaGetLastError());
+    } else {
+        DPH_CHECK(codes != nullptr, "codes is null");
+        uint8_t* d_raw = nullptr;
+        DPH_CUDA(cudaMalloc((void**)&d_raw, std::max<size_t>((size_t)rows * DPH_CODE, 1)));
+        DPH_CUDA(cudaMemcpy(d_raw, codes, (size_t)rows * DPH_CODE, cudaMemcpyHostToDevice));
+        fill_blocks_kernel<<<(unsigned)nb, 192, 0, ix->stream>>>(ix->codes, nb, (const long long*)ix->blk_off, ix->list_len, lo, hi, d_raw,
+                                                              (const long long*)d_lrs, 0);
+        DPH_CUDA(cudaGetLastError());
+        DPH_CUDA(cudaStreamSynchronize(ix->stream));
+        cudaFree(d_raw);
+        if (ids) {
+            int64_t* d_rawids = nullptr;
+            DPH_CUDA(cudaMalloc((void**)&d_rawids, std::max<size_t>((size_t)rows * 8, 8)));
+            DPH_CUDA(cudaMemcpy(d_rawids, ids, (size_t)rows * 8, cudaMemcpyHostToDevice));
+            DPH_TRY(dev_alloc(&ix->ids, (size_t)nb * 32, ix));
+            fill_ids_kernel<<<(unsigned)nb, 32, 0, ix->stream>>>((long long*)ix->ids, nb, (const long long*)ix->blk_off, ix->list_len, lo, hi,
+                                                               (const long long*)d_rawids, (const long long*)d_lrs);
+            DPH_CUDA(cudaGetLastError());
+            DPH_CUDA(cudaStreamSynchronize(ix->stream));
+            cudaFree(d_rawids);
+            // direct map (faiss DirectMap::Hashtable, build_phrase_index.py:139-141): sorted labels -> padded local row
+            std::vector<int64_t> order(rows);
+            std::iota(order.begin(), order.end(), 0);
+            std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return ids[a] < ids[b]; });
+            std::vector<int64_t> sid(rows), srow(rows);
+            std::vector<int64_t> prow(rows);
+            for (int64_t l = lo; l < hi; l++)
+                for (int64_t j = 0; j < list_len[l]; j++) prow[local_row_start[l - lo] + j] = (blk_off[l] + j / 32) * 32 + (j % 32);
+            for (int64_t i = 0; i < rows; i++) { sid[i] = ids[order[i]]; srow[i] = prow[order[i]]; }
+            DPH_TRY(dev_alloc(&ix->dm_ids, (size_t)rows, ix));
+            DPH_TRY(dev_alloc(&ix->dm_rows, (size_t)rows, ix));
+            DPH_CUDA(cudaMemcpy(ix->dm_ids, sid.data(), rows * 8, cudaMemcpyHostToDevice));
+            DPH_CUDA(cudaMemcpy(ix->dm_rows, srow.data(), rows * 8, cudaMemcpyHostToDevice));
+            ix->dm_n = rows;
+        }
+    }
+    DPH_CUDA(cudaStreamSynchronize(ix->stream));
+    cudaFree(d_lrs);
+    return 0;
+}
+DPH_API int dph_index_set_lists(dph_index* ix, const int64_t* list_len, const uint8_t* codes, const int64_t* ids) {
+    return set_lists_common(ix, list_len, codes, ids, false, 0);
+}
+DPH_API int dph_index_set_lists_synthetic(dph_index* ix, const int64_t* list_len, uint64_t seed) {
+    return set_lists_common(ix, list_len, nullptr, nullptr, true, seed);
+}
+
+// -------------------------------------------------------------------------------------------------
+// getters
+// -------------------------------------------------------------------------------------------------
+DPH_API int64_t dph_index_ntotal(const dph_index* ix) { return ix->ntotal; }
+DPH_API int64_t dph_index_ntotal_local(const dph_index* ix) { return ix->ntotal_local; }
+DPH_API int dph_index_d(const dph_index* ix) { return ix->d; }
+DPH_API int64_t dph_index_nlist(const dph_index* ix) { return ix->nlist; }
+DPH_API int dph_index_nprobe(const dph_index* ix) { return ix->nprobe; }
+DPH_API int dph_index_set_nprobe(dph_index* ix, int nprobe) {
+    DPH_CHECK(nprobe >= 1 && nprobe <= DPH_MAX_NPROBE, "nprobe must be in [1,1024]");
+    ix->nprobe = nprobe;
+    return 0;
+}
+DPH_API int dph_index_set_scan_mode(dph_index* ix, int mode) {
+    DPH_CHECK(mode == DPH_SCAN_FAST || mode == DPH_SCAN_EXACT, "bad scan mode");
+    ix->scan_mode = mode;
+    return 0;
+}
+DPH_API int dph_index_get_opq(const dph_index* ix, float* A_out, int mem) {
+    DPH_CHECK(ix->A != nullptr, "OPQ matrix not set");
+    DPH_CUDA(cudaMemcpy(A_out, ix->A, (size_t)ix->d * ix->d * 4, mem == DPH_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice));
+    return 0;
+}
+DPH_API int64_t dph_index_device_bytes(const dph_index* ix) { return ix->bytes; }
+DPH_API const int32_t* dph_index_last_flags(const dph_index* ix) { return ix->flags.as<int32_t>(); }
+DPH_API const int32_t* dph_index_last_probes(const dph_index* ix) { return ix->key.as<int32_t>(); }
+DPH_API const float* dph_index_last_coarse(const dph_index* ix) { return ix->cd.as<float>(); }
+DPH_API const float* dph_index_last_xr(const dph_index* ix) { return ix->xr.as<float>(); }
+DPH_API int dph_index_copy_last(dph_index* ix, int which, void* dst_host, int64_t bytes) {
+    const void* src = which == 0 ? ix->flags.p : which == 1 ? ix->key.p : which == 2 ? ix->cd.p : which == 3 ? ix->xr.p : nullptr;
+    DPH_CHECK(src != nullptr, "copy_last: nothing to copy");
+    DPH_CUDA(cudaStreamSynchronize(ix->stream));
+    DPH_CUDA(cudaMemcpy(dst_host, src, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// search
+// -------------------------------------------------------------------------------------------------
+static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, float* D, int64_t* I, uint32_t* G) {
+    cudaStream_t st = ix->stream;
+    const int nprobe = ix->nprobe;
+    const int grid = ix->num_sms;
+    const int keep_fast = k + DPH_KEEP_SLACK;
+    const int keep_max = keep_fast;
+    DPH_TRY(ix->xr.ensure((size_t)n * ix->d * 4));
+    DPH_TRY(ix->S.ensure((size_t)n * ix->nlist * 4));
+    DPH_TRY(ix->key.ensure((size_t)n * nprobe * 4));
+    DPH_TRY(ix->cd.ensure((size_t)n * nprobe * 4));
+    DPH_TRY(ix->lut_scan.ensure((size_t)n * DPH_LUT_SCAN_FLOATS * 4));
+    DPH_TRY(ix->lut_canon.ensure((size_t)n * DPH_LUT_CANON_FLOATS * 4));
+    DPH_TRY(ix->lutmax.ensure((size_t)n * DPH_M * 4));
+    DPH_TRY(ix->segs.ensure((size_t)n * nprobe * sizeof(DphSeg)));
+    DPH_TRY(ix->wpre.ensure((size_t)(n + 1) * 8));
+    DPH_TRY(ix->qinfo.ensure((size_t)n * 4));
+    DPH_TRY(ix->eps.ensure((size_t)n * 4));
+    DPH_TRY(ix->cand.ensure((size_t)(2 * grid + 2 * n + 2) * keep_max * 8));
+    DPH_TRY(ix->cand_off.ensure((size_t)(n + 1) * 8));
+    DPH_TRY(ix->cand_cnt.ensure((size_t)n * 4));
+    DPH_TRY(ix->gthr.ensure((size_t)n * 4));
+    DPH_TRY(ix->flags.ensure((size_t)n * 4));
+    DPH_TRY(ix->work.ensure(sizeof(DphWork)));
+    ix->last_n = n;
+
+    DPH_TRY(dph_launch_sgemm_nt_seq(x_dev, n, ix->A, ix->d, ix->d, ix->xr.as<float>(), st));                       // OPQ rotation
+    DPH_TRY(dph_launch_sgemm_nt_seq(ix->xr.as<float>(), n, ix->C, ix->nlist, ix->d, ix->S.as<float>(), st));       // coarse scores
+    DPH_TRY(dph_launch_coarse_select(ix->S.as<float>(), n, ix->nlist, nprobe, ix->key.as<int32_t>(), ix->cd.as<float>(), st));
+    DPH_TRY(dph_launch_lut(ix->xr.as<float>(), n, ix->pq, ix->lut_scan.as<float>(), ix->lut_canon.as<float>(), ix->lutmax.as<float>(), st));
+    if (ix->scan_mode == DPH_SCAN_FAST) {
+        DPH_TRY(dph_launch_plan(ix, n, k, keep_fast, grid, nullptr, st));
+        DPH_TRY(dph_launch_scan(ix, n, k, keep_fast, DPH_SCAN_FAST, grid, st));
+        DPH_TRY(dph_launch_merge(ix, n, k, DPH_SCAN_FAST, nullptr, D, I, G, st));
+        // fallback for queries whose filter could not be proven exact (no-op launches when no flag is set)
+        DPH_TRY(dph_launch_plan(ix, n, k, k, grid, ix->flags.as<int32_t>(), st));
+        DPH_TRY(dph_launch_scan(ix, n, k, k, DPH_SCAN_EXACT, grid, st));
+        DPH_TRY(dph_launch_merge(ix, n, k, DPH_SCAN_EXACT, ix->flags.as<int32_t>(), D, I, G, st));
+    } else {
+        DPH_CUDA(cudaMemsetAsync(ix->flags.p, 0, (size_t)n * 4, st));
+        DPH_TRY(dph_launch_plan(ix, n, k, k, grid, nullptr, st));
+        DPH_TRY(dph_launch_scan(ix, n, k, k, DPH_SCAN_EXACT, grid, st));
+        DPH_TRY(dph_launch_merge(ix, n, k, DPH_SCAN_EXACT, nullptr, D, I, G, st));
+    }
+    return 0;
+}
+
+static int check_ready(dph_index* ix, int k) {
+    DPH_CHECK(ix && ix->A && ix->C && ix->pq && ix->list_len, "index is not fully constructed (opq/centroids/pq/lists)");
+    DPH_CHECK(k >= 1 && k <= DPH_MAX_K, "k must be in [1,1024]");
+    return 0;
+}
+static int64_t chunk_size(const dph_index* ix, int64_t n) {
+    int64_t c = (1ll << 28) / std::max<int64_t>(ix->nlist, 1);   // S chunk <= 1 GiB
+    c = std::max<int64_t>(1, std::min<int64_t>(c, 4096));
+    return std::min(c, n);
+}
+
+DPH_API int dph_index_search_partial(dph_index* ix, const float* x_dev, int64_t n, int k, float* D, int64_t* I, uint32_t* G) {
+    DPH_TRY(check_ready(ix, k));
+    DPH_CUDA(cudaSetDevice(ix->device));
+    const int64_t cs = chunk_size(ix, n);
+    for (int64_t o = 0; o < n; o += cs) {
+        int64_t m = std::min(cs, n - o);
+        DPH_TRY(search_chunk(ix, x_dev + o * ix->d, m, k, D + o * k, I + o * k, G + o * k));
+    }
+    return 0;
+}
+
+DPH_API int dph_index_search(dph_index* ix, const float* x, int64_t n, int k, float* D, int64_t* I, int mem) {
+    DPH_TRY(check_ready(ix, k));
+    DPH_CUDA(cudaSetDevice(ix->device));
+    if (n == 0) return 0;
+    DPH_TRY(ix->Gp.ensure((size_t)n * k * 4));
+    if (mem == DPH_MEM_DEVICE) return dph_index_search_partial(ix, x, n, k, D, I, ix->Gp.as<uint32_t>());
+    DPH_TRY(ix->xdev.ensure((size_t)n * ix->d * 4));
+    DPH_TRY(ix->Dp.ensure((size_t)n * k * 4));
+    DPH_TRY(ix->Ip.ensure((size_t)n * k * 8));
+    DPH_CUDA(cudaMemcpyAsync(ix->xdev.p, x, (size_t)n * ix->d * 4, cudaMemcpyHostToDevice, ix->stream));
+    DPH_TRY(dph_index_search_partial(ix, ix->xdev.as<float>(), n, k, ix->Dp.as<float>(), ix->Ip.as<int64_t>(), ix->Gp.as<uint32_t>()));
+    DPH_CUDA(cudaMemcpyAsync(D, ix->Dp.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost, ix->stream));
+    DPH_CUDA(cudaMemcpyAsync(I, ix->Ip.p, (size_t)n * k * 8, cudaMemcpyDeviceToHost, ix->stream));
+    DPH_CUDA(cudaStreamSynchronize(ix->stream));
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// reconstruct: label -> (list, offset) -> centroid + PQ decode (rotated space)
+// -------------------------------------------------------------------------------------------------
+struct LocateArgs {
+    const long long* list_start; long long nlist; long long list_lo, list_hi; const long long* blk_off; const int* list_len;
+    const long long* dm_ids; const long long* dm_rows; long long dm_n; bool explicit_ids;
+};
+__device__ __forceinline__ bool locate_label(const LocateArgs& a, long long id, long long& l, long long& prow) {
+    if (!a.explicit_ids) {
+        if (id < 0 || id >= a.list_start[a.nlist]) return false;
+        long long lo = 0, hi = a.nlist;      // last l with list_start[l] <= id
+        while (hi - lo > 1) { long long mid = (lo + hi) >> 1; if (a.list_start[mid] <= id) lo = mid; else hi = mid; }
+        l = lo;
+        if (l < a.list_lo || l >= a.list_hi) return false;
+        long long j = id - a.list_start[l];
+        prow = (a.blk_off[l] + (j >> 5)) * 32 + (j & 31);
+        return true;
+    }
+    long long lo = 0, hi = a.dm_n;
+    if (hi == 0) return false;
+    while (hi - lo > 1) { long long mid = (lo + hi) >> 1; if (a.dm_ids[mid] <= id) lo = mid; else hi = mid; }
+    if (a.dm_ids[lo] != id) return false;
+    prow = a.dm_rows[lo];
+    l = list_of_block(a.blk_off, a.list_lo, a.list_hi, prow >> 5);
+    return true;
+}
+
+__global__ void __launch_bounds__(96) reconstruct_kernel(LocateArgs la, const long long* ids, long long m, const uint8_t* codes, const float* C,
+                                                          const float* pq, float* out, unsigned char* found) {
+    const long long i = blockIdx.x;
+    const int t = threadIdx.x;      // sub-quantizer
+    __shared__ long long s_l, s_prow; __shared__ int s_ok;
+    if (t == 0) { long long l = 0, pr = 0; s_ok = locate_label(la, ids[i], l, pr) ? 1 : 0; s_l = l; s_prow = pr; }
+    __syncthreads();
+    float4* o = reinterpret_cast<float4*>(out + i * DPH_D + t * 8);
+    if (!s_ok) { o[0] = make_float4(0, 0, 0, 0); o[1] = make_float4(0, 0, 0, 0); if (t == 0 && found) found[i] = 0; return; }
+    const long long blk = s_prow >> 5; const int lane = (int)(s_prow & 31);
+    const unsigned char code = codes[blk * DPH_BLK_BYTES + dph_blk_addr(lane, t)];
+    const float4* cb = reinterpret_cast<const float4*>(pq + ((size_t)t * 256 + code) * 8);
+    const float4* ce = reinterpret_cast<const float4*>(C + s_l * DPH_D + t * 8);
+    float4 a0 = cb[0], a1 = cb[1], c0 = ce[0], c1 = ce[1];
+    o[0] = make_float4(a0.x + c0.x, a0.y + c0.y, a0.z + c0.z, a0.w + c0.w);
+    o[1] = make_float4(a1.x + c1.x, a1.y + c1.y, a1.z + c1.z, a1.w + c1.w);
+    if (t == 0 && found) found[i] = 1;
+}
+
+static LocateArgs make_locate(const dph_index* ix) {
+    LocateArgs la;
+    la.list_start = (const long long*)ix->list_start; la.nlist = ix->nlist; la.list_lo = ix->list_lo; la.list_hi = ix->list_hi;
+    la.blk_off = (const long long*)ix->blk_off; la.list_len = ix->list_len; la.dm_ids = (const long long*)ix->dm_ids;
+    la.dm_rows = (const long long*)ix->dm_rows; la.dm_n = ix->dm_n; la.explicit_ids = ix->ids != nullptr;
+    return la;
+}
+
+DPH_API int dph_index_reconstruct_batch(dph_index* ix, const int64_t* ids, int64_t m, float* out, uint8_t* found, int mem) {
+    DPH_TRY(check_ready(ix, 1));
+    DPH_CUDA(cudaSetDevice(ix->device));
+    if (m == 0) return 0;
+    const int64_t* d_ids = ids; float* d_out = out; uint8_t* d_found = found;
+    DevBuf tmp_ids, tmp_out, tmp_found;
+    if (mem == DPH_MEM_HOST) {
+        DPH_TRY(tmp_ids.ensure((size_t)m * 8)); DPH_TRY(tmp_out.ensure((size_t)m * ix->d * 4)); DPH_TRY(tmp_found.ensure((size_t)m));
+        DPH_CUDA(cudaMemcpyAsync(tmp_ids.p, ids, (size_t)m * 8, cudaMemcpyHostToDevice, ix->stream));
+        d_ids = tmp_ids.as<int64_t>(); d_out = tmp_out.as<float>(); d_found = tmp_found.as<uint8_t>();
+    }
+    reconstruct_kernel<<<(unsigned)m, 96, 0, ix->stream>>>(make_locate(ix), (const long long*)d_ids, m, ix->codes, ix->C, ix->pq, d_out, d_found);
+    DPH_CUDA(cudaGetLastError());
+    if (mem == DPH_MEM_HOST) {
+        DPH_CUDA(cudaMemcpyAsync(out, d_out, (size_t)m * ix->d * 4, cudaMemcpyDeviceToHost, ix->stream));
+        if (found) DPH_CUDA(cudaMemcpyAsync(found, d_found, (size_t)m, cudaMemcpyDeviceToHost, ix->stream));
+        DPH_CUDA(cudaStreamSynchronize(ix->stream));
+        tmp_ids.release(); tmp_out.release(); tmp_found.release();
+    }
+    return 0;
+}
+
+DPH_API int dph_index_window_scores(dph_index* ix, const float* q, const int64_t* first_id, int64_t m, int L, float* out_scores, int mem) {
+    (void)ix; (void)q; (void)first_id; (void)m; (void)L; (void)out_scores; (void)mem;
+    dph_set_error("dph_index_window_scores: not built yet (SURVEY 8f #1)");
+    return 1;
+}

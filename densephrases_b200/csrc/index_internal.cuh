@@ -1,0 +1,69 @@
+// index_internal.cuh -- the dph_index handle and the internal kernel-launch prototypes.
+#pragma once
+#include "common.cuh"
+#include "../../include/dph_b200.h"
+#include <vector>
+
+#define DPH_SCAN_THREADS 512
+#define DPH_SCAN_WARPS (DPH_SCAN_THREADS / 32)
+#define DPH_CAND_CAP 3072          // shared-memory candidate buffer (u64 keys) per scan CTA
+#define DPH_KEEP_SLACK 32          // fast mode keeps k + slack candidates per CTA
+#define DPH_MAX_K 1024
+#define DPH_MAX_NPROBE 1024
+#define DPH_SURV_CAP 2048          // merge kernel: survivors re-scored exactly per query
+#define DPH_LUT_SCAN_FLOATS (3 * 256 * 64)   // per query: 3 segments x 256 codes x (32 + 31 dup + 1 pad)
+#define DPH_LUT_CANON_FLOATS (96 * 256)
+
+struct DevBuf {            // grow-only device buffer
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes);
+    void release();
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct dph_index {
+    int device = 0;
+    int d = DPH_D, M = DPH_M;
+    int64_t nlist = 0;
+    int nprobe = 256;
+    int scan_mode = DPH_SCAN_FAST;
+    cudaStream_t stream = 0;
+    int num_sms = 148;
+
+    // model
+    float* A = nullptr;         // [d,d]
+    float* C = nullptr;         // [nlist,d]
+    float* pq = nullptr;        // [M,256,dsub]
+    // lists
+    int64_t list_lo = 0, list_hi = 0;   // shard range
+    int64_t ntotal = 0, ntotal_local = 0, nblocks_local = 0;
+    int32_t* list_len = nullptr;        // [nlist]   (all lists)
+    int64_t* list_start = nullptr;      // [nlist+1] global list-major row of each list's first vector
+    int64_t* blk_off = nullptr;         // [nlist]   first code block in `codes` (-1 when not in shard)
+    uint8_t* codes = nullptr;           // [nblocks_local * 3072] interleaved blocks
+    int64_t* ids = nullptr;             // [nblocks_local * 32] labels (or nullptr: sequential)
+    // direct map for explicit ids (sorted labels -> local padded row); built at set_lists
+    int64_t* dm_ids = nullptr;
+    int64_t* dm_rows = nullptr;
+    int64_t dm_n = 0;
+    std::vector<int64_t> h_list_len;    // host copies
+    std::vector<int64_t> h_list_start;
+    int64_t bytes = 0;
+
+    // per-batch workspace
+    DevBuf xdev, xr, S, key, cd, lut_scan, lut_canon, lutmax, segs, wpre, qinfo, cand, cand_off, cand_cnt, gthr, flags,
+        work, Dp, Ip, Gp, Dh, Ih, eps;
+    int64_t last_n = 0;
+};
+
+// ---- prep.cu ----
+int dph_launch_sgemm_nt_seq(const float* X, int64_t n, const float* W, int64_t m, int K, float* out, cudaStream_t st);
+int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprobe, int32_t* key, float* cd, cudaStream_t st);
+int dph_launch_lut(const float* xr, int64_t n, const float* pq, float* lut_scan, float* lut_canon, float* lutmax, cudaStream_t st);
+int dph_launch_plan(dph_index* ix, int64_t n, int k, int keep, int grid, const int32_t* only_flagged, cudaStream_t st);
+// ---- scan.cu ----
+int dph_launch_scan(dph_index* ix, int64_t n, int k, int keep, int mode, int grid, cudaStream_t st);
+int dph_launch_merge(dph_index* ix, int64_t n, int k, int mode, const int32_t* only_flagged, float* D, int64_t* I,
+                     uint32_t* G, cudaStream_t st);
+int dph_scan_setup_attrs();

@@ -1,0 +1,343 @@
+// prep.cu -- query preparation kernels of the IVF-PQ search (everything before the code scan):
+//   * sgemm_nt_seq : out = X W^T with ONE sequential fp32 FMA chain per output (k ascending) -- used for the
+//                    OPQ rotation (faiss LinearTransform::apply) and the coarse scores (IndexFlatIP::search),
+//                    replacing the sgemm faiss calls at /root/reference/densephrases/index.py:200.
+//   * coarse_select: top-nprobe lists per query, (score desc, list asc).
+//   * lut          : PQ inner-product tables (faiss ProductQuantizer::compute_inner_prod_table) in two layouts.
+//   * plan         : per (query, probe) segment descriptors + work partition for the scan kernel.
+#include "index_internal.cuh"
+#include "select.cuh"
+
+// =================================================================================================
+// sgemm_nt_seq: X [n,K] row-major, W [m,K] row-major, out [n,m].  128x128 tile, 256 threads, 8x8 micro-tile,
+// BK = 8, double-buffered smem.  Each accumulator is updated by exactly one FFMA per k, k ascending, starting
+// from +0 -> bit-identical to `acc = fmaf(x[t], w[t], acc)` on the host (oracle/ivfpq_ref.c:dot_seq).
+// =================================================================================================
+#define GBM 128
+#define GBN 128
+#define GBK 8
+__global__ void __launch_bounds__(256) sgemm_nt_seq_kernel(const float* __restrict__ X, long long n, const float* __restrict__ W,
+                                                            long long m, int K, float* __restrict__ out) {
+    __shared__ __align__(16) float As[2][GBK][GBM];
+    __shared__ __align__(16) float Bs[2][GBK][GBN];
+    const int tid = threadIdx.x;
+    const long long row0 = (long long)blockIdx.y * GBM, col0 = (long long)blockIdx.x * GBN;
+    const int lr = tid & 127, lk4 = tid >> 7;          // tile row, which float4 along K (0..1)
+    const long long arow = row0 + lr, brow = col0 + lr;
+    const bool aok = arow < n, bok = brow < m;
+    const float4* ap = reinterpret_cast<const float4*>(X + (aok ? arow : 0) * K) + lk4;
+    const float4* bp = reinterpret_cast<const float4*>(W + (bok ? brow : 0) * K) + lk4;
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = 0.0f;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 ra = aok ? __ldg(ap) : z4, rb = bok ? __ldg(bp) : z4;
+    const int ktiles = K / GBK;
+    int buf = 0;
+    As[0][lk4 * 4 + 0][lr] = ra.x; As[0][lk4 * 4 + 1][lr] = ra.y; As[0][lk4 * 4 + 2][lr] = ra.z; As[0][lk4 * 4 + 3][lr] = ra.w;
+    Bs[0][lk4 * 4 + 0][lr] = rb.x; Bs[0][lk4 * 4 + 1][lr] = rb.y; Bs[0][lk4 * 4 + 2][lr] = rb.z; Bs[0][lk4 * 4 + 3][lr] = rb.w;
+    __syncthreads();
+    for (int kt = 0; kt < ktiles; kt++) {
+        if (kt + 1 < ktiles) {
+            ra = aok ? __ldg(ap + (kt + 1) * 2) : z4;
+            rb = bok ? __ldg(bp + (kt + 1) * 2) : z4;
+        }
+#pragma unroll
+        for (int k = 0; k < GBK; k++) {
+            float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+            float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+            float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+            float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (kt + 1 < ktiles) {
+            int nb = buf ^ 1;
+            As[nb][lk4 * 4 + 0][lr] = ra.x; As[nb][lk4 * 4 + 1][lr] = ra.y; As[nb][lk4 * 4 + 2][lr] = ra.z; As[nb][lk4 * 4 + 3][lr] = ra.w;
+            Bs[nb][lk4 * 4 + 0][lr] = rb.x; Bs[nb][lk4 * 4 + 1][lr] = rb.y; Bs[nb][lk4 * 4 + 2][lr] = rb.z; Bs[nb][lk4 * 4 + 3][lr] = rb.w;
+            __syncthreads();
+            buf = nb;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        long long r = row0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (r >= n) continue;
+#pragma unroll
+        for (int jh = 0; jh < 2; jh++) {
+            long long c = col0 + jh * 64 + tx * 4;
+            float* o = out + r * m + c;
+            if (c + 3 < m && ((m & 3) == 0)) {
+                *reinterpret_cast<float4*>(o) = make_float4(acc[i][jh * 4 + 0], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (c + j < m) o[j] = acc[i][jh * 4 + j];
+            }
+        }
+    }
+}
+
+int dph_launch_sgemm_nt_seq(const float* X, int64_t n, const float* W, int64_t m, int K, float* out, cudaStream_t st) {
+    DPH_CHECK(K % GBK == 0 && K % 4 == 0, "sgemm_nt_seq: K must be a multiple of 8");
+    if (n == 0 || m == 0) return 0;
+    dim3 grid((unsigned)((m + GBN - 1) / GBN), (unsigned)((n + GBM - 1) / GBM));
+    sgemm_nt_seq_kernel<<<grid, 256, 0, st>>>(X, n, W, m, K, out);
+    DPH_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =================================================================================================
+// coarse_select: one CTA per query.  key = (fkey(score) << 32) | (~list)  -> distinct, order = score desc,
+// list asc.  Radix-select the nprobe-th key over the S row, gather, bitonic sort, write.
+// (faiss IndexFlatIP::search keeps the same SET unless scores tie exactly at the boundary; order among exact
+//  ties is heap-dependent in faiss and canonicalised here.)
+// =================================================================================================
+__global__ void __launch_bounds__(256) coarse_select_kernel(const float* __restrict__ S, long long nlist, int nprobe,
+                                                             int* __restrict__ key, float* __restrict__ cd) {
+    __shared__ SelectScratch sc;
+    __shared__ unsigned long long sel[DPH_MAX_NPROBE];
+    __shared__ int cnt;
+    const long long q = blockIdx.x;
+    const float* row = S + q * nlist;
+    const int tid = threadIdx.x;
+    const int take = (int)(nlist < nprobe ? nlist : nprobe);
+    auto get = [&](int i) { return ((unsigned long long)dph_fkey(__ldg(row + i)) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i); };
+    unsigned long long pivot = 0;
+    if (nlist > nprobe) pivot = block_radix_select(get, (int)nlist, take, &sc);
+    if (tid == 0) cnt = 0;
+    const int p2 = dph_next_pow2(take);
+    for (int i = tid; i < p2; i += blockDim.x) sel[i] = 0ull;
+    __syncthreads();
+    for (int i = tid; i < nlist; i += blockDim.x) {
+        unsigned long long k = get(i);
+        if (k >= pivot) { int p = atomicAdd(&cnt, 1); if (p < DPH_MAX_NPROBE) sel[p] = k; }
+    }
+    __syncthreads();
+    block_bitonic_sort_desc(sel, p2);
+    for (int r = tid; r < nprobe; r += blockDim.x) {
+        if (r < take) {
+            unsigned long long k = sel[r];
+            key[q * nprobe + r] = (int)(0xFFFFFFFFu - (unsigned)k);
+            cd[q * nprobe + r] = dph_fkey_inv((unsigned)(k >> 32));
+        } else {
+            key[q * nprobe + r] = -1;
+            cd[q * nprobe + r] = DPH_NEUTRAL;
+        }
+    }
+}
+
+int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprobe, int32_t* key, float* cd, cudaStream_t st) {
+    DPH_CHECK(nprobe >= 1 && nprobe <= DPH_MAX_NPROBE, "nprobe out of range [1,1024]");
+    DPH_CHECK(nlist < (1ll << 31), "nlist too large");
+    if (n == 0) return 0;
+    coarse_select_kernel<<<(unsigned)n, 256, 0, st>>>(S, nlist, nprobe, key, cd);
+    DPH_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =================================================================================================
+// lut: grid (n, 3), 256 threads.  Block (q, seg) computes LUT[m][j] for m in [32 seg, 32 seg + 32), j = tid:
+//   canonical  lut_canon[q][m][j]                      (exact re-scoring, canonical-order scan)
+//   scan       lut_scan[q][seg][j][w], w in 0..63:  w<32 -> m=32seg+w ; 32<=w<63 -> m=32seg+w-32 (wrap copy)
+// so that lane l reading word (l + s) at step s never has to wrap (scan.cu).  lutmax[q][m] = max_j |LUT[m][j]|.
+// Each entry is the sequential FMA chain over the 8 sub-dimensions (compute_inner_prod_table).
+// =================================================================================================
+__global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ xr, const float* __restrict__ pq,
+                                                   float* __restrict__ lut_scan, float* __restrict__ lut_canon,
+                                                   float* __restrict__ lutmax) {
+    __shared__ float tile[256 * 33];
+    __shared__ float xs[32 * 8];
+    __shared__ float wmax[8][32];
+    const long long q = blockIdx.x;
+    const int seg = blockIdx.y, j = threadIdx.x, lane = j & 31, warp = j >> 5;
+    xs[j] = xr[q * DPH_D + seg * 256 + j];
+    __syncthreads();
+#pragma unroll 4
+    for (int ml = 0; ml < 32; ml++) {
+        const int m = seg * 32 + ml;
+        const float4* cb = reinterpret_cast<const float4*>(pq + ((size_t)m * 256 + j) * 8);
+        float4 c0 = __ldg(cb), c1 = __ldg(cb + 1);
+        const float* x = xs + ml * 8;
+        float acc = 0.0f;
+        acc = fmaf(x[0], c0.x, acc); acc = fmaf(x[1], c0.y, acc); acc = fmaf(x[2], c0.z, acc); acc = fmaf(x[3], c0.w, acc);
+        acc = fmaf(x[4], c1.x, acc); acc = fmaf(x[5], c1.y, acc); acc = fmaf(x[6], c1.z, acc); acc = fmaf(x[7], c1.w, acc);
+        tile[j * 33 + ml] = acc;
+        lut_canon[(q * DPH_M + m) * 256 + j] = acc;
+        float a = fabsf(acc);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, off));
+        if (lane == 0) wmax[warp][ml] = a;
+    }
+    __syncthreads();
+    if (j < 32) {
+        float a = wmax[0][j];
+#pragma unroll
+        for (int w = 1; w < 8; w++) a = fmaxf(a, wmax[w][j]);
+        lutmax[q * DPH_M + seg * 32 + j] = a;
+    }
+    float* dst = lut_scan + ((size_t)q * 3 + seg) * (256 * 64);
+    for (int idx = j; idx < 256 * 64; idx += 256) {
+        int row = idx >> 6, w = idx & 63;
+        float v = (w < 63) ? tile[row * 33 + (w & 31)] : 0.0f;
+        dst[idx] = v;
+    }
+}
+
+int dph_launch_lut(const float* xr, int64_t n, const float* pq, float* lut_scan, float* lut_canon, float* lutmax, cudaStream_t st) {
+    if (n == 0) return 0;
+    lut_kernel<<<dim3((unsigned)n, 3), 256, 0, st>>>(xr, pq, lut_scan, lut_canon, lutmax);
+    DPH_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =================================================================================================
+// plan: (1) plan_segs -- one warp per query: segment descriptors, canonical scan positions, per-query block
+// count and the fast filter's error bound eps;  (2) plan_scan -- one CTA: prefix over queries -> qpre[n+1],
+// candidate-region offsets, total work; resets the per-batch counters.
+// =================================================================================================
+struct PlanArgs {
+    const int* key; const float* cd; const int* list_len; const long long* blk_off;
+    long long list_lo, list_hi; int nprobe; long long n;
+    const int* only_flagged;       // nullable: plan work only for queries with flag != 0
+    const float* lutmax;
+    DphSeg* segs; unsigned* qblocks; float* eps;
+};
+__global__ void __launch_bounds__(256) plan_segs_kernel(PlanArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long q = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (q >= a.n) return;
+    const bool active = a.only_flagged ? (a.only_flagged[q] != 0) : true;
+    unsigned gacc = 0, wacc = 0;
+    float dmax = 0.0f;
+    for (int r0 = 0; r0 < a.nprobe; r0 += 32) {
+        const int r = r0 + lane;
+        int l = -1, len = 0; float d0 = 0.0f; unsigned nb = 0; long long blk = -1;
+        if (r < a.nprobe) {
+            l = a.key[q * a.nprobe + r];
+            d0 = a.cd[q * a.nprobe + r];
+            if (l >= 0) {
+                len = a.list_len[l];
+                dmax = fmaxf(dmax, fabsf(d0));
+                if (active && len > 0 && l >= a.list_lo && l < a.list_hi) { nb = (unsigned)((len + 31) >> 5); blk = a.blk_off[l]; }
+            }
+        }
+        // warp exclusive scans of len and nb
+        unsigned gl = (unsigned)len, wl = nb;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            unsigned g2 = __shfl_up_sync(0xffffffffu, gl, off), w2 = __shfl_up_sync(0xffffffffu, wl, off);
+            if (lane >= off) { gl += g2; wl += w2; }
+        }
+        if (r < a.nprobe) {
+            DphSeg s;
+            s.blk = blk; s.len = len; s.gstart = gacc + gl - (unsigned)len; s.dis0 = d0;
+            s.wrel = wacc + wl - nb; s.wend = wacc + wl; s.list = l;
+            a.segs[q * a.nprobe + r] = s;
+        }
+        gacc += __shfl_sync(0xffffffffu, gl, 31);
+        wacc += __shfl_sync(0xffffffffu, wl, 31);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, off));
+    float lsum = 0.0f;
+    for (int m = lane; m < DPH_M; m += 32) lsum += a.lutmax[q * DPH_M + m];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+    if (lane == 0) {
+        a.qblocks[q] = wacc;
+        // |approx - canonical| <= 2 * gamma_96 * sum|terms|,  gamma_96 = 96u/(1-96u), u = 2^-24  (Higham 2002, eq. 4.4);
+        // inflated by 1.01 for the fp32 evaluation of the bound itself.
+        const float gamma96 = 5.7221e-6f;
+        a.eps[q] = 2.0f * gamma96 * (dmax + lsum) * 1.01f;
+    }
+}
+
+struct PlanScanArgs {
+    const unsigned* qblocks; long long n; int keep; int grid;
+    long long* qpre; long long* cand_off; int* cand_cnt; unsigned* gthr; DphWork* work;
+};
+__global__ void __launch_bounds__(1024) plan_scan_kernel(PlanScanArgs a) {
+    __shared__ long long wsum[32];
+    __shared__ long long carry, total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // pass 1: qpre = exclusive prefix of qblocks
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (long long base = 0; base < a.n; base += 1024) {
+        long long q = base + tid;
+        long long v = q < a.n ? (long long)a.qblocks[q] : 0, incl = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { long long t = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += t; }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = wsum[lane], wi = w;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { long long t = __shfl_up_sync(0xffffffffu, wi, off); if (lane >= off) wi += t; }
+            wsum[lane] = wi - w;
+        }
+        __syncthreads();
+        long long excl = carry + wsum[warp] + incl - v;
+        if (q < a.n) { a.qpre[q] = excl; a.cand_cnt[q] = 0; a.gthr[q] = 0u; }
+        __syncthreads();
+        if (tid == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) { total = carry; a.qpre[a.n] = carry; a.work->total_blocks = carry; carry = 0; }
+    __syncthreads();
+    // pass 2: candidate-region offsets; a query spanning `parts` scan CTAs may receive parts*keep entries
+    const long long T = total;
+    const long long per = T / a.grid > 0 ? T / a.grid : 1;
+    for (long long base = 0; base < a.n; base += 1024) {
+        long long q = base + tid;
+        long long v = 0;
+        if (q < a.n) {
+            long long qb = (long long)a.qblocks[q];
+            if (qb > 0) { long long parts = qb / per + 2; if (parts > a.grid) parts = a.grid; v = parts * a.keep; }
+        }
+        long long incl = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { long long t = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += t; }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = wsum[lane], wi = w;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { long long t = __shfl_up_sync(0xffffffffu, wi, off); if (lane >= off) wi += t; }
+            wsum[lane] = wi - w;
+        }
+        __syncthreads();
+        long long excl = carry + wsum[warp] + incl - v;
+        if (q < a.n) a.cand_off[q] = excl;
+        __syncthreads();
+        if (tid == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) a.cand_off[a.n] = carry;
+}
+
+int dph_launch_plan(dph_index* ix, int64_t n, int k, int keep, int grid, const int32_t* only_flagged, cudaStream_t st) {
+    (void)k;
+    if (n == 0) return 0;
+    PlanArgs a;
+    a.key = ix->key.as<int>(); a.cd = ix->cd.as<float>(); a.list_len = ix->list_len; a.blk_off = (const long long*)ix->blk_off;
+    a.list_lo = ix->list_lo; a.list_hi = ix->list_hi; a.nprobe = ix->nprobe; a.n = n; a.only_flagged = only_flagged;
+    a.lutmax = ix->lutmax.as<float>(); a.segs = ix->segs.as<DphSeg>(); a.qblocks = ix->qinfo.as<unsigned>(); a.eps = ix->eps.as<float>();
+    plan_segs_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(a);
+    DPH_CUDA(cudaGetLastError());
+    PlanScanArgs b;
+    b.qblocks = ix->qinfo.as<unsigned>(); b.n = n; b.keep = keep; b.grid = grid; b.qpre = ix->wpre.as<long long>();
+    b.cand_off = ix->cand_off.as<long long>(); b.cand_cnt = ix->cand_cnt.as<int>(); b.gthr = ix->gthr.as<unsigned>();
+    b.work = ix->work.as<DphWork>();
+    plan_scan_kernel<<<1, 1024, 0, st>>>(b);
+    DPH_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,442 @@
+// scan.cu -- the PQ asymmetric-distance scan over the probed inverted lists and the top-k merge.
+//
+// Replaces faiss IVFPQScanner::scan_codes + the result heap behind self.index.search(...) at
+// /root/reference/densephrases/index.py:200.
+//
+// Work decomposition: the plan kernel linearises all in-shard (query, probe, 32-vector block) triples in
+// canonical scan order; scan CTA c of G takes the contiguous range [T c/G, T (c+1)/G).  One persistent CTA
+// per SM (the per-query LUT fills shared memory); inside a CTA each warp owns one 32-vector block per round,
+// lane l <-> vector l.
+//
+// FAST mode (the product path).  Shared-memory gathers, not HBM, co-limit this scan (one 4-byte LUT gather
+// per code byte).  The code blocks are stored lane-rotated (common.cuh: dph_blk_addr) and the LUT is stored as
+// three [256][64] tables (32 sub-quantizers + 31 wrap copies per row), so that at step t lane l reads word
+// (l + t%32) of row `code byte` of table t/32: the 32 lanes always hit 32 different banks -> every LDS is one
+// conflict-free wavefront regardless of the code values.  One PRMT builds the address (code<<8 | lane*4), so a
+// lookup is PRMT + LDS + FADD.  The rotated summation order differs from faiss' m-ascending order by at most
+// eps (plan kernel), so the scores are used as a FILTER: each CTA keeps its best k+32 by filter score, the merge
+// kernel re-scores the survivors in canonical order (bit-exact with the oracle) and PROVES that nothing that
+// was dropped could have been in the top-k (T_k - max drop threshold > 2 eps); otherwise the query is flagged
+// and re-run through EXACT mode.
+//
+// EXACT mode: canonical m-ascending fp32 sum for every code (bank conflicts and all) -- fallback/cross-check.
+#include "index_internal.cuh"
+#include "select.cuh"
+
+struct ScanArgs {
+    const uint8_t* codes; const long long* qpre; const DphSeg* segs; const DphWork* work;
+    const float* lut_scan; const float* lut_canon;
+    unsigned* gthr; unsigned long long* cand; const long long* cand_off; int* cand_cnt;
+    long long n; int nprobe; int keep;
+};
+
+#define NT DPH_SCAN_THREADS
+#define NW DPH_SCAN_WARPS
+#define SMEM_LUT_FAST (DPH_LUT_SCAN_FLOATS * 4)                 // 196608
+#define SMEM_LUT_EXACT (DPH_LUT_CANON_FLOATS * 4 + NW * DPH_BLK_BYTES)   // 98304 + 49152
+#define SMEM_TAIL (DPH_CAND_CAP * 8 + (int)sizeof(SelectScratch) + 64)
+
+struct ScanShared {   // tail of the dynamic shared memory
+    unsigned long long cbuf[DPH_CAND_CAP];
+    SelectScratch sc;
+    int cnt; unsigned thr; int base; int pad;
+};
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+struct BlockMeta { const uint4* ptr; int j0; int len; unsigned gstart; float dis0; };
+
+extern __shared__ __align__(1024) unsigned char dph_smem[];
+// The dynamic shared memory window of a kernel without static shared memory starts at this shared-space address on
+// sm_100 (1 KB is reserved by the system); probed once at library init (dph_scan_setup_attrs), a mismatch is fatal.
+#define DPH_DYN_SMEM_BASE 0x400
+
+// One FAST lookup: PRMT builds (cta window bits | code << 8 | lane*4); the table base, the step offset and the window
+// base are folded into the LDS immediate -> PRMT + LDS + FADD per code byte.
+template <int IMM> __device__ __forceinline__ float lds_imm(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
+template <int T0> __device__ __forceinline__ void fast_word(unsigned wv, unsigned y, float& a0, float& a1, float& a2, float& a3) {
+    constexpr int TB = DPH_DYN_SMEM_BASE + (T0 >> 5) * 65536 + (T0 & 31) * 4;   // T0 % 4 == 0: the 4 bytes share a table
+    a0 += lds_imm<TB + 0>(__byte_perm(wv, y, 0x7504));
+    a1 += lds_imm<TB + 4>(__byte_perm(wv, y, 0x7514));
+    a2 += lds_imm<TB + 8>(__byte_perm(wv, y, 0x7524));
+    a3 += lds_imm<TB + 12>(__byte_perm(wv, y, 0x7534));
+}
+template <int C> __device__ __forceinline__ void fast_chunk(const uint4& v, unsigned y, float& a0, float& a1, float& a2, float& a3) {
+    fast_word<C * 16 + 0>(v.x, y, a0, a1, a2, a3);
+    fast_word<C * 16 + 4>(v.y, y, a0, a1, a2, a3);
+    fast_word<C * 16 + 8>(v.z, y, a0, a1, a2, a3);
+    fast_word<C * 16 + 12>(v.w, y, a0, a1, a2, a3);
+}
+
+// Warp-cooperative lookup of the segment containing work block b (relative to the query's first block).
+// Each lane caches one descriptor of a 32-wide window; windows only move forward.
+__device__ __forceinline__ BlockMeta resolve_block(unsigned b, const DphSeg* __restrict__ segs, int nprobe, int& base,
+                                                    DphSeg& mine, const uint8_t* codes, int lane) {
+    BlockMeta m;
+    while (true) {
+        bool hit = (mine.wrel <= b) && (b < mine.wend);
+        unsigned mask = __ballot_sync(0xffffffffu, hit);
+        if (mask) {
+            int src = __ffs(mask) - 1;
+            unsigned blo = __shfl_sync(0xffffffffu, (unsigned)(mine.blk & 0xffffffffll), src);
+            unsigned bhi = __shfl_sync(0xffffffffu, (unsigned)((unsigned long long)mine.blk >> 32), src);
+            unsigned wrel = __shfl_sync(0xffffffffu, mine.wrel, src);
+            m.len = __shfl_sync(0xffffffffu, mine.len, src);
+            m.gstart = __shfl_sync(0xffffffffu, mine.gstart, src);
+            m.dis0 = __shfl_sync(0xffffffffu, mine.dis0, src);
+            long long blk = (long long)(((unsigned long long)bhi << 32) | blo) + (long long)(b - wrel);
+            m.ptr = reinterpret_cast<const uint4*>(codes + blk * DPH_BLK_BYTES);
+            m.j0 = (int)(b - wrel) * 32;
+            return m;
+        }
+        base += 32;
+        if (base >= nprobe) { m.ptr = nullptr; m.j0 = 0; m.len = 0; m.gstart = 0; m.dis0 = 0.f; return m; }   // unreachable by construction
+        int r = base + lane;
+        if (r < nprobe) {
+            const uint4* sp = reinterpret_cast<const uint4*>(segs + r);
+            uint4 u0 = __ldg(sp), u1 = __ldg(sp + 1);
+            mine.blk = (long long)(((unsigned long long)u0.y << 32) | u0.x);
+            mine.len = (int)u0.z; mine.gstart = u0.w;
+            mine.dis0 = __uint_as_float(u1.x); mine.wrel = u1.y; mine.wend = u1.z; mine.list = (int)u1.w;
+        } else { mine.wrel = 0xFFFFFFFFu; mine.wend = 0u; }
+    }
+}
+
+__device__ __forceinline__ void block_compact(ScanShared* sh, int keep, unsigned* gthr_q) {
+    const int tid = threadIdx.x;
+    const int n = sh->cnt;
+    unsigned long long* cb = sh->cbuf;
+    unsigned long long pivot = block_radix_select([&](int i) { return cb[i]; }, n, keep, &sh->sc);
+    unsigned long long mine[DPH_CAND_CAP / NT];
+#pragma unroll
+    for (int e = 0; e < DPH_CAND_CAP / NT; e++) { int i = tid + e * NT; mine[e] = (i < n) ? cb[i] : 0ull; }
+    __syncthreads();
+    if (tid == 0) sh->cnt = 0;
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < DPH_CAND_CAP / NT; e++)
+        if (mine[e] >= pivot && mine[e] != 0ull) { int p = atomicAdd(&sh->cnt, 1); cb[p] = mine[e]; }
+    if (tid == 0) {
+        unsigned t = (unsigned)(pivot >> 32);
+        unsigned old = atomicMax(gthr_q, t);
+        sh->thr = t > old ? t : old;
+    }
+    __syncthreads();
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NT, 1) scan_kernel(ScanArgs a) {
+    unsigned char* const smem = dph_smem;
+    constexpr int LUT_BYTES = (MODE == DPH_SCAN_FAST) ? SMEM_LUT_FAST : SMEM_LUT_EXACT;
+    ScanShared* sh = reinterpret_cast<ScanShared*>(smem + LUT_BYTES);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long T = a.work->total_blocks;
+    const long long G = gridDim.x, c = blockIdx.x;
+    const long long g0 = T * c / G, g1 = T * (c + 1) / G;
+    if (g0 >= g1) return;
+    long long lo = 0, hi = a.n;
+    while (hi - lo > 1) { long long mid = (lo + hi) >> 1; if (a.qpre[mid] <= g0) lo = mid; else hi = mid; }
+    long long q = lo, g = g0;
+    const int RB = (DPH_CAND_CAP - a.keep) / NT;     // rounds between compaction checks (>= 3 for keep <= 1056)
+    const unsigned ywin = (((unsigned)__cvta_generic_to_shared(dph_smem)) & 0xFF000000u) | ((unsigned)lane * 4u);
+
+    while (g < g1) {
+        while (a.qpre[q + 1] <= g) q++;
+        const long long qstart = a.qpre[q];
+        const long long gend = (a.qpre[q + 1] < g1) ? a.qpre[q + 1] : g1;
+        const unsigned b0 = (unsigned)(g - qstart), b1 = (unsigned)(gend - qstart);
+        __syncthreads();
+        // ---- stage this query's LUT into shared memory ----
+        {
+            const float4* src = reinterpret_cast<const float4*>(MODE == DPH_SCAN_FAST ? a.lut_scan + (size_t)q * DPH_LUT_SCAN_FLOATS
+                                                                                      : a.lut_canon + (size_t)q * DPH_LUT_CANON_FLOATS);
+            constexpr int NF4 = ((MODE == DPH_SCAN_FAST) ? DPH_LUT_SCAN_FLOATS : DPH_LUT_CANON_FLOATS) / 4;
+            float4* dst = reinterpret_cast<float4*>(smem);
+#pragma unroll 8
+            for (int i = tid; i < NF4; i += NT) dst[i] = __ldg(src + i);
+        }
+        if (tid == 0) { sh->cnt = 0; sh->thr = *((volatile unsigned*)(a.gthr + q)); }
+        __syncthreads();
+
+        const DphSeg* segs = a.segs + q * a.nprobe;
+        int wbase = -32;
+        DphSeg mine; mine.wrel = 0xFFFFFFFFu; mine.wend = 0u; mine.blk = 0; mine.len = 0; mine.gstart = 0; mine.dis0 = 0.f; mine.list = -1;
+        const int nrounds = (int)((b1 - b0 + NW - 1) / NW);
+        uint4 nxt[6];
+        BlockMeta mn; mn.ptr = nullptr; mn.j0 = 0; mn.len = 0; mn.gstart = 0; mn.dis0 = 0.f;
+        {
+            unsigned b = b0 + warp;
+            if (b < b1) {
+                mn = resolve_block(b, segs, a.nprobe, wbase, mine, a.codes, lane);
+#pragma unroll
+                for (int cc = 0; cc < 6; cc++) nxt[cc] = ldg_stream(mn.ptr + cc * 32 + lane);
+            }
+        }
+        for (int round = 0; round < nrounds; round++) {
+            const unsigned b = b0 + (unsigned)round * NW + warp;
+            const bool active = b < b1;
+            uint4 cur[6];
+            BlockMeta mc = mn;
+#pragma unroll
+            for (int cc = 0; cc < 6; cc++) cur[cc] = nxt[cc];
+            {
+                unsigned bn = b + NW;
+                if (bn < b1) {
+                    mn = resolve_block(bn, segs, a.nprobe, wbase, mine, a.codes, lane);
+#pragma unroll
+                    for (int cc = 0; cc < 6; cc++) nxt[cc] = ldg_stream(mn.ptr + cc * 32 + lane);
+                }
+            }
+            if (active) {
+                float score;
+                if (MODE == DPH_SCAN_FAST) {
+                    float acc0 = mc.dis0, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+                    fast_chunk<0>(cur[0], ywin, acc0, acc1, acc2, acc3);
+                    fast_chunk<1>(cur[1], ywin, acc0, acc1, acc2, acc3);
+                    fast_chunk<2>(cur[2], ywin, acc0, acc1, acc2, acc3);
+                    fast_chunk<3>(cur[3], ywin, acc0, acc1, acc2, acc3);
+                    fast_chunk<4>(cur[4], ywin, acc0, acc1, acc2, acc3);
+                    fast_chunk<5>(cur[5], ywin, acc0, acc1, acc2, acc3);
+                    score = (acc0 + acc1) + (acc2 + acc3);
+                } else {
+                    unsigned char* stage = smem + DPH_LUT_CANON_FLOATS * 4 + warp * DPH_BLK_BYTES;
+                    const float* lutc = reinterpret_cast<const float*>(smem);
+#pragma unroll
+                    for (int cc = 0; cc < 6; cc++) *reinterpret_cast<uint4*>(stage + cc * 512 + lane * 16) = cur[cc];
+                    __syncwarp();
+                    float dis = mc.dis0;
+#pragma unroll 8
+                    for (int m = 0; m < DPH_M; m++) dis += lutc[m * 256 + stage[dph_blk_addr(lane, m)]];
+                    score = dis;
+                    __syncwarp();
+                }
+                const int j = mc.j0 + lane;
+                const unsigned sk = dph_fkey(score);
+                const bool pass = (j < mc.len) && (sk >= sh->thr);
+                const unsigned pm = __ballot_sync(0xffffffffu, pass);
+                if (pm) {
+                    int basep = 0;
+                    if (lane == 0) basep = atomicAdd(&sh->cnt, __popc(pm));
+                    basep = __shfl_sync(0xffffffffu, basep, 0);
+                    if (pass) {
+                        int p = basep + __popc(pm & ((1u << lane) - 1u));
+                        if (p < DPH_CAND_CAP) sh->cbuf[p] = ((unsigned long long)sk << 32) | (unsigned long long)(0xFFFFFFFFu - (mc.gstart + (unsigned)j));
+                    }
+                }
+            }
+            if (((round + 1) % RB) == 0 || round == nrounds - 1) {
+                __syncthreads();
+                if (sh->cnt > a.keep) block_compact(sh, a.keep, a.gthr + q);
+                else {
+                    if (tid == 0) { unsigned gt = *((volatile unsigned*)(a.gthr + q)); if (gt > sh->thr) sh->thr = gt; }
+                    __syncthreads();
+                }
+            }
+        }
+        // ---- publish this CTA's candidates for query q ----
+        __syncthreads();
+        const int cnt = sh->cnt;
+        if (tid == 0) sh->base = atomicAdd(a.cand_cnt + q, cnt);
+        __syncthreads();
+        {
+            const long long off = a.cand_off[q], cap = a.cand_off[q + 1] - off;
+            const int basep = sh->base;
+            for (int i = tid; i < cnt; i += NT)
+                if (basep + i < cap) a.cand[off + basep + i] = sh->cbuf[i];
+        }
+        g = gend;
+        q++;
+    }
+}
+
+__global__ void smem_base_probe_kernel(unsigned* out) { *out = (unsigned)__cvta_generic_to_shared(dph_smem) & 0x00FFFFFFu; }
+
+static bool g_attrs_set = false;
+int dph_scan_setup_attrs() {
+    if (g_attrs_set) return 0;
+    {
+        unsigned* d = nullptr; unsigned h = 0;
+        DPH_CUDA(cudaMalloc((void**)&d, 4));
+        smem_base_probe_kernel<<<1, 32, 1024>>>(d);
+        DPH_CUDA(cudaMemcpy(&h, d, 4, cudaMemcpyDeviceToHost));
+        cudaFree(d);
+        DPH_CHECK(h == DPH_DYN_SMEM_BASE, "dynamic shared memory window does not start at 0x400 on this driver; rebuild with the probed value");
+    }
+    DPH_CUDA(cudaFuncSetAttribute(scan_kernel<DPH_SCAN_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LUT_FAST + (int)sizeof(ScanShared)));
+    DPH_CUDA(cudaFuncSetAttribute(scan_kernel<DPH_SCAN_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LUT_EXACT + (int)sizeof(ScanShared)));
+    g_attrs_set = true;
+    return 0;
+}
+
+int dph_launch_scan(dph_index* ix, int64_t n, int k, int keep, int mode, int grid, cudaStream_t st) {
+    (void)k;
+    if (n == 0) return 0;
+    DPH_TRY(dph_scan_setup_attrs());
+    ScanArgs a;
+    a.codes = ix->codes; a.qpre = ix->wpre.as<long long>(); a.segs = ix->segs.as<DphSeg>(); a.work = ix->work.as<DphWork>();
+    a.lut_scan = ix->lut_scan.as<float>(); a.lut_canon = ix->lut_canon.as<float>(); a.gthr = ix->gthr.as<unsigned>();
+    a.cand = ix->cand.as<unsigned long long>(); a.cand_off = ix->cand_off.as<long long>(); a.cand_cnt = ix->cand_cnt.as<int>();
+    a.n = n; a.nprobe = ix->nprobe; a.keep = keep;
+    if (mode == DPH_SCAN_FAST)
+        scan_kernel<DPH_SCAN_FAST><<<grid, NT, SMEM_LUT_FAST + sizeof(ScanShared), st>>>(a);
+    else
+        scan_kernel<DPH_SCAN_EXACT><<<grid, NT, SMEM_LUT_EXACT + sizeof(ScanShared), st>>>(a);
+    DPH_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =================================================================================================
+// merge: one CTA per query.  FAST: prove the filter, re-score survivors in canonical order, sort.
+// EXACT: candidates already carry canonical scores.  Output: D (score desc), I (labels), G (scan position).
+// =================================================================================================
+struct MergeArgs {
+    const unsigned long long* cand; const long long* cand_off; const int* cand_cnt; const unsigned* gthr; const float* eps;
+    const DphSeg* segs; int nprobe; int k; int mode;
+    const uint8_t* codes; const float* lut_canon; const long long* ids; const long long* list_start;
+    float* D; long long* I; unsigned* G; int* flags; const int* only_flagged;
+};
+
+__device__ __forceinline__ int find_seg(const DphSeg* segs, int nprobe, unsigned gidx) {
+    int lo = 0, hi = nprobe;   // last r with gstart <= gidx
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (segs[mid].gstart <= gidx) lo = mid; else hi = mid; }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) merge_kernel(MergeArgs a) {
+    __shared__ SelectScratch sc;
+    __shared__ unsigned long long surv[DPH_SURV_CAP];
+    __shared__ int scnt, sflag;
+    const long long q = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (a.only_flagged && a.only_flagged[q] == 0) return;
+    const unsigned long long* E = a.cand + a.cand_off[q];
+    long long cap = a.cand_off[q + 1] - a.cand_off[q];
+    int n = a.cand_cnt[q];
+    if (n > cap) n = (int)cap;
+    const DphSeg* segs = a.segs + q * a.nprobe;
+    const int k = a.k;
+    if (tid == 0) { scnt = 0; sflag = 0; }
+    __syncthreads();
+    auto get = [&](int i) { return E[i]; };
+    unsigned long long pivot = 0ull;   // gather keys >= pivot
+    int flag = 0;
+    if (a.mode == DPH_SCAN_FAST) {
+        const float eps2 = 2.0f * a.eps[q];
+        const unsigned gt = a.gthr[q];
+        if (n > k) {
+            unsigned long long pk = block_radix_select(get, n, k, &sc);
+            const float Tk = dph_ckey_score(pk);
+            if (gt != 0u && !(Tk - dph_fkey_inv(gt) > eps2)) flag = 1;
+            pivot = (unsigned long long)dph_fkey(Tk - eps2) << 32;       // every entry with filter score >= Tk - 2eps
+        } else if (gt != 0u) flag = 1;
+    } else {
+        if (n > DPH_SURV_CAP) pivot = block_radix_select(get, n, k, &sc);
+    }
+    for (int i = tid; i < n; i += blockDim.x) {
+        unsigned long long e = E[i];
+        if (e >= pivot) { int p = atomicAdd(&scnt, 1); if (p < DPH_SURV_CAP) surv[p] = e; else sflag = 1; }
+    }
+    __syncthreads();
+    int ns = scnt < DPH_SURV_CAP ? scnt : DPH_SURV_CAP;
+    if (sflag) flag = 1;
+    if (a.mode == DPH_SCAN_FAST) {
+        const float* lutc = a.lut_canon + (size_t)q * DPH_LUT_CANON_FLOATS;
+        for (int i = tid; i < ns; i += blockDim.x) {
+            const unsigned gidx = dph_ckey_gidx(surv[i]);
+            const DphSeg s = segs[find_seg(segs, a.nprobe, gidx)];
+            const unsigned j = gidx - s.gstart;
+            const uint8_t* blk = a.codes + (s.blk + (long long)(j >> 5)) * DPH_BLK_BYTES;
+            const int ln = (int)(j & 31u);
+            float dis = s.dis0;
+            for (int m = 0; m < DPH_M; m++) dis += __ldg(lutc + m * 256 + blk[dph_blk_addr(ln, m)]);   // canonical order
+            surv[i] = dph_ckey(dis, gidx);
+        }
+    }
+    const int p2 = dph_next_pow2(ns > 1 ? ns : 1);
+    for (int i = ns + tid; i < p2; i += blockDim.x) surv[i] = 0ull;
+    __syncthreads();
+    block_bitonic_sort_desc(surv, p2);
+    for (int i = tid; i < k; i += blockDim.x) {
+        float d = DPH_NEUTRAL; long long id = -1; unsigned gi = 0xFFFFFFFFu;
+        if (i < ns) {
+            const unsigned long long e = surv[i];
+            gi = dph_ckey_gidx(e); d = dph_ckey_score(e);
+            const DphSeg s = segs[find_seg(segs, a.nprobe, gi)];
+            const unsigned j = gi - s.gstart;
+            id = a.ids ? a.ids[s.blk * 32 + j] : a.list_start[s.list] + (long long)j;
+        }
+        a.D[q * k + i] = d; a.I[q * k + i] = id; a.G[q * k + i] = gi;
+    }
+    if (a.mode == DPH_SCAN_FAST && tid == 0) a.flags[q] = flag;
+}
+
+int dph_launch_merge(dph_index* ix, int64_t n, int k, int mode, const int32_t* only_flagged, float* D, int64_t* I, uint32_t* G,
+                     cudaStream_t st) {
+    if (n == 0) return 0;
+    MergeArgs a;
+    a.cand = ix->cand.as<unsigned long long>(); a.cand_off = ix->cand_off.as<long long>(); a.cand_cnt = ix->cand_cnt.as<int>();
+    a.gthr = ix->gthr.as<unsigned>(); a.eps = ix->eps.as<float>(); a.segs = ix->segs.as<DphSeg>(); a.nprobe = ix->nprobe; a.k = k; a.mode = mode;
+    a.codes = ix->codes; a.lut_canon = ix->lut_canon.as<float>(); a.ids = (const long long*)ix->ids; a.list_start = (const long long*)ix->list_start;
+    a.D = D; a.I = (long long*)I; a.G = G; a.flags = ix->flags.as<int>(); a.only_flagged = only_flagged;
+    merge_kernel<<<(unsigned)n, 256, 0, st>>>(a);
+    DPH_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =================================================================================================
+// merge_shards: all-gathered per-shard top-k -> global top-k, order (score desc, scan position asc).
+// =================================================================================================
+__global__ void __launch_bounds__(256) merge_shards_kernel(const float* Dg, const long long* Ig, const unsigned* Gg, int nshards, long long n,
+                                                            int k, float* D, long long* I) {
+    extern __shared__ unsigned long long ms[];     // keys [p2] then payload index is recovered from a parallel array
+    const long long q = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int tot = nshards * k;
+    const int p2 = dph_next_pow2(tot);
+    unsigned long long* keys = ms;
+    // key = (fkey(score), ~gidx); payload looked up afterwards by matching (shard, slot) stored in a side table:
+    // gidx is unique per real entry, so re-find the source by scanning the <= nshards*k inputs (tiny).
+    for (int i = tid; i < p2; i += blockDim.x) {
+        unsigned long long key = 0ull;
+        if (i < tot) {
+            int s = i / k, r = i % k;
+            long long id = Ig[((long long)s * n + q) * k + r];
+            if (id >= 0) key = dph_ckey(Dg[((long long)s * n + q) * k + r], Gg[((long long)s * n + q) * k + r]);
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    block_bitonic_sort_desc(keys, p2);
+    for (int i = tid; i < k; i += blockDim.x) {
+        float d = DPH_NEUTRAL; long long id = -1;
+        unsigned long long key = keys[i];
+        if (key != 0ull) {
+            unsigned gi = dph_ckey_gidx(key);
+            d = dph_ckey_score(key);
+            for (int s = 0; s < nshards && id < 0; s++)
+                for (int r = 0; r < k; r++) {
+                    long long o = ((long long)s * n + q) * k + r;
+                    if (Gg[o] == gi && Ig[o] >= 0) { id = Ig[o]; break; }
+                }
+        }
+        D[q * k + i] = d; I[q * k + i] = id;
+    }
+}
+
+DPH_API int dph_merge_shards(const float* Dg, const int64_t* Ig, const uint32_t* Gg, int nshards, int64_t n, int k, float* D, int64_t* I,
+                                void* cuda_stream) {
+    if (n == 0) return 0;
+    DPH_CHECK(nshards >= 1 && k >= 1 && (long long)nshards * k <= 8192, "merge_shards: nshards*k must be <= 8192");
+    int p2 = 1; while (p2 < nshards * k) p2 <<= 1;
+    merge_shards_kernel<<<(unsigned)n, 256, p2 * 8, (cudaStream_t)cuda_stream>>>(Dg, (const long long*)Ig, Gg, nshards, n, k, D, (long long*)I);
+    DPH_CUDA(cudaGetLastError());
+    return 0;
+}

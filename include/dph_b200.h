@@ -1,0 +1,109 @@
+/*
+ * dph_b200.h -- C ABI of libdph_b200.so: the B200-native replacement for the FAISS calls on the
+ * DensePhrases retrieval hot path.  Plain pointers and sizes only (no torch / faiss types).
+ *
+ * Every entry point names the reference interface it replaces (paths relative to /root/reference):
+ *
+ *   dph_index_search            <- faiss.IndexPreTransform.search(x, k)      densephrases/index.py:200
+ *   dph_index_reconstruct_batch <- faiss IndexIVFPQ.reconstruct(id) per id   densephrases/index.py:31,282-300
+ *   dph_index_get_opq           <- faiss.vector_to_array(OPQMatrix.A)        densephrases/index.py:32
+ *   dph_index_ntotal/d/nlist    <- index.ntotal / index.d / index_ivf.nlist  densephrases/index.py:33,128-133
+ *   dph_index_set_nprobe        <- index_ivf.nprobe = 256                    densephrases/index.py:53,62
+ *   dph_index_create/set_*      <- faiss.read_index(...) / IndexPreTransform(OPQMatrix, IndexIVFPQ(...))
+ *                                  densephrases/index.py:30 ; build_phrase_index.py:113-116,149-150
+ *
+ * Conventions: every function returns 0 on success, non-zero on error (dph_last_error() gives the
+ * message; the Python layer raises RuntimeError like faiss' SWIG layer does).  `mem` arguments say
+ * where caller buffers live.  All device work is issued on the stream passed to dph_index_set_stream
+ * (default: the legacy default stream).  Calls with host buffers are synchronous; calls with device
+ * buffers are asynchronous on that stream.  Inputs are never modified.
+ */
+#ifndef DPH_B200_H
+#define DPH_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPH_MEM_HOST 0
+#define DPH_MEM_DEVICE 1
+
+/* scan kernel selection (dph_index_set_scan_mode) */
+#define DPH_SCAN_FAST 0  /* conflict-free diagonal ADC filter + exact fp32 re-scoring (default) */
+#define DPH_SCAN_EXACT 1 /* canonical-order fp32 ADC for every code (slow; fallback + cross-check) */
+
+typedef struct dph_index dph_index;
+
+const char* dph_last_error(void);
+int dph_version(void);
+
+/* ---- construction (replaces faiss.read_index / index build; build_phrase_index.py:113-116) ---- */
+/* d = M*dsub, nbits must be 8 (ksub 256), M must be 96 (PQ96: code row = 96 bytes). */
+int dph_index_create(dph_index** out, int d, int64_t nlist, int M, int nbits, int device);
+void dph_index_free(dph_index* ix);
+int dph_index_set_stream(dph_index* ix, void* cuda_stream);
+/* OPQ matrix A [d,d] row-major (d_out rows), centroids [nlist,d], PQ codebooks [M,256,dsub]; fp32. */
+int dph_index_set_opq(dph_index* ix, const float* A, int mem);
+int dph_index_set_centroids(dph_index* ix, const float* C, int mem);
+int dph_index_set_pq(dph_index* ix, const float* pq, int mem);
+/* Synthetic centroids/PQ (bit-identical to oracle ref_gen_centroids / ref_gen_pq), generated on device. */
+int dph_index_gen_centroids(dph_index* ix, uint64_t seed, float sigma);
+int dph_index_gen_pq(dph_index* ix, uint64_t seed, float sigma);
+/* This process holds only inverted lists [list_lo, list_hi) (list-range shard). Call before set_lists. */
+int dph_index_set_shard(dph_index* ix, int64_t list_lo, int64_t list_hi);
+/* list_len [nlist] (ALL lists, host). codes: [ntotal,96] list-major rows of the lists in the shard only
+ * (host), ids likewise [ntotal_shard] or NULL for sequential labels (label = global list-major row,
+ * build_phrase_index.py:149-150). */
+int dph_index_set_lists(dph_index* ix, const int64_t* list_len, const uint8_t* codes, const int64_t* ids);
+/* Same but codes are generated on device from `seed` (bit-identical to oracle ref_gen_codes); ids sequential. */
+int dph_index_set_lists_synthetic(dph_index* ix, const int64_t* list_len, uint64_t seed);
+
+/* ---- getters ---- */
+int64_t dph_index_ntotal(const dph_index* ix);       /* all shards */
+int64_t dph_index_ntotal_local(const dph_index* ix); /* this shard */
+int dph_index_d(const dph_index* ix);
+int64_t dph_index_nlist(const dph_index* ix);
+int dph_index_nprobe(const dph_index* ix);
+int dph_index_set_nprobe(dph_index* ix, int nprobe);
+int dph_index_set_scan_mode(dph_index* ix, int mode);
+int dph_index_get_opq(const dph_index* ix, float* A_out, int mem);
+int64_t dph_index_device_bytes(const dph_index* ix);
+
+/* ---- search (replaces index.search at index.py:200) ----
+ * x [n,d] fp32; D [n,k] fp32, I [n,k] int64 labels; sorted by descending score; unfilled slots are
+ * (-FLT_MAX, -1) like faiss' CMin heap.  Uses the index's nprobe (default 256, index.py:53,62). */
+int dph_index_search(dph_index* ix, const float* x, int64_t n, int k, float* D, int64_t* I, int mem);
+/* Sharded search: per-shard partial top-k.  G [n,k] uint32 = canonical scan position (tie-break key,
+ * global over all shards).  Buffers on device.  After an all-gather over shards feed dph_merge_shards. */
+int dph_index_search_partial(dph_index* ix, const float* x_dev, int64_t n, int k, float* D_dev, int64_t* I_dev,
+                             uint32_t* G_dev);
+/* Dg/Ig/Gg [nshards,n,k] (all-gathered, device) -> D/I [n,k] (device).  Order: score desc, scan position asc. */
+int dph_merge_shards(const float* Dg, const int64_t* Ig, const uint32_t* Gg, int nshards, int64_t n, int k, float* D,
+                     int64_t* I, void* cuda_stream);
+/* Per-query flags of the last search (device pointer, int32 [n]): bit0 = fast filter could not prove
+ * exactness and the query was re-run through the exact kernel. */
+const int32_t* dph_index_last_flags(const dph_index* ix);
+/* Intermediate results of the last search, for tests (device pointers): probed lists [n,nprobe] int32,
+ * coarse scores [n,nprobe] fp32, rotated queries [n,d]. */
+const int32_t* dph_index_last_probes(const dph_index* ix);
+const float* dph_index_last_coarse(const dph_index* ix);
+const float* dph_index_last_xr(const dph_index* ix);
+/* Copy one of them to the host (synchronises): which = 0 flags, 1 probes, 2 coarse scores, 3 rotated queries. */
+int dph_index_copy_last(dph_index* ix, int which, void* dst_host, int64_t bytes);
+
+/* ---- reconstruct (replaces reconst_fn loop, index.py:282-300) ----
+ * out [m,d] fp32 in ROTATED space (caller un-rotates with R = OPQ matrix, index.py:340,365);
+ * found [m] u8: 0 -> label not in this shard / not in the index, row is zeros (index.py:287-288). */
+int dph_index_reconstruct_batch(dph_index* ix, const int64_t* ids, int64_t m, float* out, uint8_t* found, int mem);
+
+/* ---- phrase re-scoring (replaces index.py:323-371: end.matmul(R); (q*end).sum; argmax with mask) ----
+ * For each of m hits: window of L consecutive labels starting at first_id[i]; score[i,l] =
+ * <q[i], R^T-unrotated reconstruct(first_id[i]+l)> computed as <A q[i] , reconstruct> (A orthonormal);
+ * out_scores [m,L] fp32 (missing label -> 0, like the zero vector at index.py:287-288). */
+int dph_index_window_scores(dph_index* ix, const float* q /*[m,d]*/, const int64_t* first_id /*[m]*/, int64_t m, int L,
+                            float* out_scores, int mem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

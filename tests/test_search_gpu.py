@@ -1,0 +1,131 @@
+"""GPU parity tests proper: CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs.
+Integer/index outputs bit-exact; fp32 scores bit-identical (stricter than the 1e-3 the north star allows)."""
+import numpy as np
+import pytest
+
+from tests.helpers import assert_topk_equal, near_queries, opq_matrix, uniform_lens
+
+pytestmark = pytest.mark.gpu
+SEED = 1234
+
+
+def make_pair(oracle, nlist, lens, seed=SEED, explicit=False, shard=None, perm_ids=False):
+    from densephrases_b200 import IvfPqIndex
+    A = opq_matrix(seed)
+    pq = oracle.gen_pq(seed)
+    codes = ids = None
+    if explicit:
+        codes = np.concatenate([oracle.gen_codes(seed + 7, l, 0, int(lens[l])) for l in range(nlist)] + [np.zeros((0, 96), np.uint8)])
+        if perm_ids:
+            ids = np.random.default_rng(seed).permutation(int(np.sum(lens))).astype(np.int64) * 3 + 11
+    ref = oracle.RefIndex(A, pq, lens, centroids=oracle.gen_centroids(seed, 0, nlist), codes=codes, ids=ids, seed=seed)
+    gpu = IvfPqIndex(nlist)
+    gpu.set_opq(A)
+    gpu.gen_pq(seed)
+    gpu.gen_centroids(seed)
+    if shard is not None:
+        gpu.set_shard(*shard)
+    if explicit:
+        lo, hi = shard if shard is not None else (0, nlist)
+        r0, r1 = ref.list_off[lo], ref.list_off[hi - 1] + lens[hi - 1]
+        gpu.set_lists(lens, codes[r0:r1], None if ids is None else ids[r0:r1])
+    else:
+        gpu.set_lists_synthetic(lens, seed)
+    return ref, gpu
+
+
+def test_generators_match_oracle(oracle):
+    lens = np.array([40, 0, 33, 1, 64], dtype=np.int64)
+    ref, gpu = make_pair(oracle, 5, lens)
+    ids = np.arange(ref.ntotal, dtype=np.int64)
+    v, f = gpu.reconstruct_batch(ids)
+    vr, fr = ref.reconstruct(ids)
+    assert f.all() and fr.all()
+    assert np.array_equal(v.view(np.int32), vr.view(np.int32))      # centroids + pq + codes + layout all bit-identical
+    v2, f2 = gpu.reconstruct_batch(np.array([-1, ref.ntotal, 10**12], dtype=np.int64))
+    assert not f2.any() and not v2.any()                              # missing label -> zeros (index.py:287-288)
+    assert np.array_equal(gpu.opq_matrix(), ref.A)
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("nlist,N,nprobe,k,nq", [(16, 5000, 4, 10, 9), (64, 40000, 16, 10, 33), (1, 3000, 256, 10, 5),
+                                                  (40, 2000, 256, 100, 7), (8, 100, 8, 200, 3)])
+def test_search_matches_oracle(oracle, mode, nlist, N, nprobe, k, nq):
+    lens = uniform_lens(N, nlist)
+    ref, gpu = make_pair(oracle, nlist, lens)
+    gpu.nprobe = nprobe
+    gpu.set_scan_mode(mode)
+    x = np.concatenate([near_queries(ref, nq - 2, 4321), 0.5 * np.random.default_rng(1).standard_normal((2, 768)).astype(np.float32)])
+    D, I = gpu.search(x, k)
+    Dr, Ir, keyr = ref.search(x, k, nprobe, return_key=True)
+    assert np.array_equal(gpu.last_xr(nq).view(np.int32), ref.rotate(x).view(np.int32))
+    assert np.array_equal(gpu.last_probes(nq), keyr.astype(np.int32))
+    assert_topk_equal(D, I, Dr, Ir, f"mode={mode}")
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+def test_ragged_empty_lists_and_explicit_ids(oracle, mode):
+    rng = np.random.default_rng(5)
+    nlist = 48
+    lens = rng.integers(0, 700, nlist).astype(np.int64)
+    lens[[0, 7, 47]] = 0
+    lens[3] = 1
+    lens[4] = 32
+    lens[5] = 33
+    ref, gpu = make_pair(oracle, nlist, lens, explicit=True, perm_ids=True)
+    gpu.nprobe = 12
+    gpu.set_scan_mode(mode)
+    x = near_queries(ref, 17, 99)
+    D, I = gpu.search(x, 10)
+    Dr, Ir = ref.search(x, 10, 12)
+    assert_topk_equal(D, I, Dr, Ir)
+    v, f = gpu.reconstruct_batch(Ir[0])
+    vr, fr = ref.reconstruct(Ir[0])
+    assert np.array_equal(v.view(np.int32), vr.view(np.int32)) and f.all()
+    # search score == <xr, reconstruct(id)> identity
+    xr = ref.rotate(x)
+    assert np.abs(v @ xr[0] - D[0]).max() < 1e-3
+
+
+def test_duplicate_codes_ties(oracle):
+    """Identical codes => exactly equal scores (duplicate Wikipedia text): canonical tie order."""
+    nlist = 4
+    lens = np.array([50, 60, 70, 80], dtype=np.int64)
+    from densephrases_b200 import IvfPqIndex
+    A = opq_matrix(3)
+    pq = oracle.gen_pq(3)
+    Cm = oracle.gen_centroids(3, 0, nlist)
+    base = oracle.gen_codes(3, 0, 0, 8)
+    codes = base[np.random.default_rng(0).integers(0, 8, int(lens.sum()))]      # only 8 distinct code rows
+    ref = oracle.RefIndex(A, pq, lens, centroids=Cm, codes=codes)
+    for mode in (1, 0):
+        gpu = IvfPqIndex(nlist)
+        gpu.set_opq(A); gpu.set_pq(pq); gpu.set_centroids(Cm); gpu.set_lists(lens, codes)
+        gpu.nprobe = 4
+        gpu.set_scan_mode(mode)
+        x = near_queries(ref, 6, 1)
+        D, I = gpu.search(x, 20)
+        Dr, Ir = ref.search(x, 20, 4)
+        assert_topk_equal(D, I, Dr, Ir, f"ties mode={mode}")
+        # canonical order inside a tie group: scan order (probe rank, offset) ascending == label ascending within a list
+        if mode == 0:
+            flags = gpu.last_flags(6)
+            assert flags.any(), "heavy ties must trip the exactness proof and take the exact fallback"
+
+
+def test_device_tensor_api_and_fast_equals_exact(oracle):
+    import torch
+    lens = uniform_lens(200000, 128)
+    ref, gpu = make_pair(oracle, 128, lens)
+    gpu.nprobe = 32
+    x = near_queries(ref, 64, 7)
+    xt = torch.from_numpy(x).cuda()
+    gpu.set_scan_mode(0)
+    D0, I0 = gpu.search(xt, 10)
+    flags = gpu.last_flags(64)
+    gpu.set_scan_mode(1)
+    D1, I1 = gpu.search(xt, 10)
+    assert torch.equal(D0, D1) and torch.equal(I0, I1)
+    assert flags.sum() == 0, "fast filter should prove exactness on generic data"
+    Dr, Ir = ref.search(x, 10, 32)
+    assert_topk_equal(D0.cpu().numpy(), I0.cpu().numpy(), Dr, Ir)
