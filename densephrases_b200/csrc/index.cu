@@ -260,6 +260,18 @@ DPH_API int dph_index_get_opq(const dph_index* ix, float* A_out, int mem) {
     DPH_CUDA(cudaMemcpy(A_out, ix->A, (size_t)ix->d * ix->d * 4, mem == DPH_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice));
     return 0;
 }
+DPH_API int dph_index_set_profile(dph_index* ix, int on) {
+    DPH_CUDA(cudaSetDevice(ix->device));
+    if (on && !ix->ev0) { DPH_CUDA(cudaEventCreate(&ix->ev0)); DPH_CUDA(cudaEventCreate(&ix->ev1)); }
+    ix->profile = on != 0;
+    return 0;
+}
+DPH_API int dph_index_last_scan_ms(dph_index* ix, float* ms) {
+    DPH_CHECK(ix->profile && ix->ev0, "profiling is off");
+    DPH_CUDA(cudaEventSynchronize(ix->ev1));
+    DPH_CUDA(cudaEventElapsedTime(ms, ix->ev0, ix->ev1));
+    return 0;
+}
 DPH_API int64_t dph_index_device_bytes(const dph_index* ix) { return ix->bytes; }
 DPH_API const int32_t* dph_index_last_flags(const dph_index* ix) { return ix->flags.as<int32_t>(); }
 DPH_API const int32_t* dph_index_last_probes(const dph_index* ix) { return ix->key.as<int32_t>(); }
@@ -307,7 +319,9 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
     DPH_TRY(dph_launch_lut(ix->xr.as<float>(), n, ix->pq, ix->lut_scan.as<float>(), ix->lut_canon.as<float>(), ix->lutmax.as<float>(), st));
     if (ix->scan_mode == DPH_SCAN_FAST) {
         DPH_TRY(dph_launch_plan(ix, n, k, keep_fast, grid, nullptr, st));
+        if (ix->profile) DPH_CUDA(cudaEventRecord(ix->ev0, st));
         DPH_TRY(dph_launch_scan(ix, n, k, keep_fast, DPH_SCAN_FAST, grid, st));
+        if (ix->profile) DPH_CUDA(cudaEventRecord(ix->ev1, st));
         DPH_TRY(dph_launch_merge(ix, n, k, DPH_SCAN_FAST, nullptr, D, I, G, st));
         // fallback for queries whose filter could not be proven exact (no-op launches when no flag is set)
         DPH_TRY(dph_launch_plan(ix, n, k, k, grid, ix->flags.as<int32_t>(), st));
@@ -316,7 +330,9 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
     } else {
         DPH_CUDA(cudaMemsetAsync(ix->flags.p, 0, (size_t)n * 4, st));
         DPH_TRY(dph_launch_plan(ix, n, k, k, grid, nullptr, st));
+        if (ix->profile) DPH_CUDA(cudaEventRecord(ix->ev0, st));
         DPH_TRY(dph_launch_scan(ix, n, k, k, DPH_SCAN_EXACT, grid, st));
+        if (ix->profile) DPH_CUDA(cudaEventRecord(ix->ev1, st));
         DPH_TRY(dph_launch_merge(ix, n, k, DPH_SCAN_EXACT, nullptr, D, I, G, st));
     }
     return 0;

@@ -55,6 +55,8 @@ struct dph_index {
     DevBuf xdev, xr, S, key, cd, lut_scan, lut_canon, lutmax, segs, wpre, qinfo, cand, cand_off, cand_cnt, gthr, flags,
         work, Dp, Ip, Gp, Dh, Ih, eps;
     int64_t last_n = 0;
+    bool profile = false;              // CUDA events around the scan kernel of the last search chunk
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
 // ---- prep.cu ----

@@ -98,6 +98,14 @@ class IvfPqIndex:
         L.check(L.lib().dph_index_get_opq(self._h, _np_ptr(A), L.MEM_HOST))
         return A
 
+    def set_profile(self, on):
+        L.check(L.lib().dph_index_set_profile(self._h, int(bool(on))))
+
+    def last_scan_ms(self):
+        ms = C.c_float(0)
+        L.check(L.lib().dph_index_last_scan_ms(self._h, C.byref(ms)))
+        return ms.value
+
     @property
     def device_bytes(self):
         return L.lib().dph_index_device_bytes(self._h)

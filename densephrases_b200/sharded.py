@@ -1,0 +1,81 @@
+"""ShardedIvfPq: the phrase index sharded by inverted-list range over the ranks of one torch.distributed job
+(SURVEY.md 8e): every rank holds lists [lo, hi), replicated coarse quantizer / OPQ / PQ codebooks; a search is
+  per-rank partial top-k  ->  ONE all-gather of (score, label, scan position) per shard  ->  identical k-way merge.
+With world_size 1 it degenerates to IvfPqIndex.  This is the call a user (MIPS.search_dense) makes."""
+import numpy as np
+import torch
+
+from .ivfpq import IvfPqIndex, merge_shards
+
+
+def shard_ranges(list_len, world):
+    """Contiguous list ranges cut by cumulative code bytes (not by list count), SURVEY.md 8e."""
+    list_len = np.asarray(list_len, dtype=np.int64)
+    cum = np.concatenate([[0], np.cumsum(list_len)])
+    total = cum[-1]
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(cum, total * r / world, side="left")))
+    cuts.append(len(list_len))
+    cuts = np.maximum.accumulate(np.array(cuts))
+    return [(int(cuts[r]), int(cuts[r + 1])) for r in range(world)]
+
+
+class ShardedIvfPq:
+    def __init__(self, nlist, rank=0, world=1, device=0, group=None):
+        self.rank, self.world, self.device, self.group = rank, world, device, group
+        self.local = IvfPqIndex(nlist, device=device)
+        self._pinned_in = None
+        self._pinned_out = None
+
+    def build_synthetic(self, A, list_len, seed, centroid_sigma=0.5, pq_sigma=0.25):
+        lo, hi = shard_ranges(list_len, self.world)[self.rank]
+        self.range = (lo, hi)
+        ix = self.local
+        ix.set_opq(A)
+        ix.gen_centroids(seed, centroid_sigma)
+        ix.gen_pq(seed, pq_sigma)
+        if self.world > 1:
+            ix.set_shard(lo, hi)
+        ix.set_lists_synthetic(list_len, seed)
+        return self
+
+    @property
+    def nprobe(self):
+        return self.local.nprobe
+
+    @nprobe.setter
+    def nprobe(self, v):
+        self.local.nprobe = v
+
+    def search_device(self, x, k):
+        """x torch cuda [n,d] (same on every rank) -> (D, I) torch cuda [n,k] (same on every rank)."""
+        if self.world == 1:
+            return self.local.search(x, k)
+        import torch.distributed as dist
+        D, I, G = self.local.search_partial(x, k)
+        n = x.shape[0]
+        Dg = torch.empty((self.world, n, k), dtype=torch.float32, device=x.device)
+        Ig = torch.empty((self.world, n, k), dtype=torch.int64, device=x.device)
+        Gg = torch.empty((self.world, n, k), dtype=torch.int32, device=x.device)
+        dist.all_gather_into_tensor(Dg, D, group=self.group)
+        dist.all_gather_into_tensor(Ig, I, group=self.group)
+        dist.all_gather_into_tensor(Gg, G, group=self.group)
+        return merge_shards(Dg, Ig, Gg, k)
+
+    def search(self, x, k):
+        """Host API == faiss index.search (index.py:200): numpy / pinned CPU tensor [n,d] -> numpy (D, I)."""
+        if self.world == 1 and isinstance(x, np.ndarray):
+            return self.local.search(x, k)
+        xt = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)) if isinstance(x, np.ndarray) else x
+        n = xt.shape[0]
+        dev = torch.device("cuda", self.device)
+        xd = xt.to(dev, non_blocking=True)
+        D, I = self.search_device(xd, k)
+        if self._pinned_out is None or self._pinned_out[0].shape != (n, k):
+            self._pinned_out = (torch.empty((n, k), dtype=torch.float32).pin_memory(), torch.empty((n, k), dtype=torch.int64).pin_memory())
+        Dh, Ih = self._pinned_out
+        Dh.copy_(D, non_blocking=True)
+        Ih.copy_(I, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return Dh.numpy(), Ih.numpy()

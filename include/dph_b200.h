@@ -68,6 +68,10 @@ int dph_index_set_nprobe(dph_index* ix, int nprobe);
 int dph_index_set_scan_mode(dph_index* ix, int mode);
 int dph_index_get_opq(const dph_index* ix, float* A_out, int mem);
 int64_t dph_index_device_bytes(const dph_index* ix);
+/* Measurement hook: when on, CUDA events bracket the scan kernel of each search (last chunk); last_scan_ms waits
+ * for it and returns the kernel's duration in milliseconds (bench.py roofline). */
+int dph_index_set_profile(dph_index* ix, int on);
+int dph_index_last_scan_ms(dph_index* ix, float* ms);
 
 /* ---- search (replaces index.search at index.py:200) ----
  * x [n,d] fp32; D [n,k] fp32, I [n,k] int64 labels; sorted by descending score; unfilled slots are

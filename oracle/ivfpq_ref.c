@@ -72,6 +72,12 @@ REF_API void ref_gen_codes(uint64_t seed, int64_t list_no, int64_t j0, int64_t n
             memcpy(out + j * code_size + 8 * w, &u, 8); /* little endian */
         }
 }
+/* codes of several whole lists, list i written at row offs[i] of out (OpenMP over lists) */
+REF_API void ref_gen_codes_lists(uint64_t seed, const int64_t* lists, int64_t nl, const int64_t* lens, const int64_t* offs,
+                                 int code_size, uint8_t* out) {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t i = 0; i < nl; i++) ref_gen_codes(seed, lists[i], 0, lens[i], code_size, out + (size_t)offs[i] * code_size);
+}
 REF_API void ref_gen_centroids(uint64_t seed, int64_t l0, int64_t n, int d, float sigma, float* out) {
     float sc = sigma / IH4_STD;
     for (int64_t l = 0; l < n; l++)
@@ -213,11 +219,13 @@ typedef struct {
     const int64_t* ids;      /* [ntotal] list-major, or NULL -> id = list_off[l] + j */
     uint64_t seed;           /* synthetic seed */
     float centroid_sigma;    /* synthetic centroids when C == NULL */
+    const int64_t* code_off; /* optional: row offset of each list inside `codes` when only some lists are resident
+                                (bench cpu_baseline keeps just the probed lists in RAM); NULL -> list_off */
 } ref_index;
 
 static const uint8_t* list_codes(const ref_index* ix, int64_t l, uint8_t** scratch, size_t* cap) {
     int64_t len = ix->list_len[l];
-    if (ix->codes) return ix->codes + (size_t)ix->list_off[l] * ix->code_size;
+    if (ix->codes) return ix->codes + (size_t)(ix->code_off ? ix->code_off[l] : ix->list_off[l]) * ix->code_size;
     size_t need = (size_t)len * ix->code_size;
     if (need > *cap) { free(*scratch); *scratch = (uint8_t*)malloc(need ? need : 1); *cap = need; }
     ref_gen_codes(ix->seed, l, 0, len, ix->code_size, *scratch);
@@ -300,7 +308,7 @@ REF_API void ref_reconstruct_at(const ref_index* ix, const int64_t* list_no, con
         if (l < 0 || l >= ix->nlist || j < 0 || j >= ix->list_len[l]) {
             memset(v, 0, sizeof(float) * ix->d); if (found) found[i] = 0; continue;
         }
-        if (ix->codes) memcpy(row, ix->codes + (size_t)(ix->list_off[l] + j) * ix->code_size, ix->code_size);
+        if (ix->codes) memcpy(row, ix->codes + (size_t)((ix->code_off ? ix->code_off[l] : ix->list_off[l]) + j) * ix->code_size, ix->code_size);
         else ref_gen_codes(ix->seed, l, j, 1, ix->code_size, row);
         centroid_row(ix, l, v);
         for (int mm = 0; mm < ix->M; mm++) {

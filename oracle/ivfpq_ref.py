@@ -40,7 +40,7 @@ class _RefIndexStruct(C.Structure):
     _fields_ = [("d", C.c_int), ("M", C.c_int), ("ksub", C.c_int), ("dsub", C.c_int), ("code_size", C.c_int),
                 ("nlist", C.c_int64), ("A", C.c_void_p), ("C", C.c_void_p), ("pq", C.c_void_p),
                 ("list_len", C.c_void_p), ("list_off", C.c_void_p), ("codes", C.c_void_p), ("ids", C.c_void_p),
-                ("seed", C.c_uint64), ("centroid_sigma", C.c_float)]
+                ("seed", C.c_uint64), ("centroid_sigma", C.c_float), ("code_off", C.c_void_p)]
 
 
 _lib = None
@@ -89,7 +89,7 @@ def gen_pq(seed, M=96, ksub=256, dsub=8, sigma=0.25):
 class RefIndex:
     """Explicit (codes/ids arrays) or synthetic (codes, optionally centroids, regenerated from `seed`)."""
 
-    def __init__(self, A, pq, list_len, centroids=None, codes=None, ids=None, seed=0, centroid_sigma=0.5):
+    def __init__(self, A, pq, list_len, centroids=None, codes=None, ids=None, seed=0, centroid_sigma=0.5, code_off=None):
         self.A = _f32(A)
         self.pq = _f32(pq)
         self.M, self.ksub, self.dsub = self.pq.shape
@@ -105,11 +105,30 @@ class RefIndex:
         self.codes = None if codes is None else np.ascontiguousarray(codes, dtype=np.uint8)
         self.ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.int64)
         self.seed, self.centroid_sigma = int(seed), float(centroid_sigma)
+        self.code_off = None if code_off is None else np.ascontiguousarray(code_off, dtype=np.int64)
         self.s = _RefIndexStruct(self.d, self.M, self.ksub, self.dsub, self.code_size, self.nlist, _p(self.A).value,
                                  None if self.C is None else _p(self.C).value, _p(self.pq).value,
                                  _p(self.list_len).value, _p(self.list_off).value,
                                  None if self.codes is None else _p(self.codes).value,
-                                 None if self.ids is None else _p(self.ids).value, self.seed, self.centroid_sigma)
+                                 None if self.ids is None else _p(self.ids).value, self.seed, self.centroid_sigma,
+                                 None if self.code_off is None else _p(self.code_off).value)
+
+    def with_resident_lists(self, lists):
+        """Copy of a synthetic index whose `lists` are materialised in RAM (like faiss' inverted lists); every other
+        list stays virtual and must not be probed. Used by bench.py's CPU baseline so the timed scan reads resident codes."""
+        assert self.codes is None
+        lists = np.unique(np.asarray(lists, dtype=np.int64))
+        lists = lists[lists >= 0]
+        lens = self.list_len[lists]
+        offs = np.zeros(len(lists), dtype=np.int64)
+        np.cumsum(lens[:-1], out=offs[1:])
+        codes = np.empty((int(lens.sum()), self.code_size), dtype=np.uint8)
+        lib().ref_gen_codes_lists(C.c_uint64(self.seed), _p(lists), C.c_int64(len(lists)), _p(np.ascontiguousarray(lens)), _p(offs),
+                                  C.c_int(self.code_size), _p(codes))
+        code_off = np.full(self.nlist, -1, dtype=np.int64)
+        code_off[lists] = offs
+        return RefIndex(self.A, self.pq, self.list_len, centroids=self.C, codes=codes, ids=None, seed=self.seed,
+                        centroid_sigma=self.centroid_sigma, code_off=code_off)
 
     # --- C restatement -------------------------------------------------------------------------
     def rotate(self, x):
@@ -181,7 +200,7 @@ class RefIndex:
 
     def list_codes(self, l):
         if self.codes is not None:
-            o = self.list_off[l]
+            o = self.list_off[l] if self.code_off is None else self.code_off[l]
             return self.codes[o:o + self.list_len[l]]
         return gen_codes(self.seed, l, 0, int(self.list_len[l]), self.code_size)
 

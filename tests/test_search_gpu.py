@@ -90,7 +90,7 @@ def test_ragged_empty_lists_and_explicit_ids(oracle, mode):
 def test_duplicate_codes_ties(oracle):
     """Identical codes => exactly equal scores (duplicate Wikipedia text): canonical tie order."""
     nlist = 4
-    lens = np.array([50, 60, 70, 80], dtype=np.int64)
+    lens = np.array([50000, 60000, 70000, 80000], dtype=np.int64)
     from densephrases_b200 import IvfPqIndex
     A = opq_matrix(3)
     pq = oracle.gen_pq(3)
