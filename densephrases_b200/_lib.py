@@ -38,6 +38,8 @@ _SIGS = {
     "dph_index_device_bytes": (_i64, [_vp]),
     "dph_index_set_profile": (_i32, [_vp, _i32]),
     "dph_index_last_scan_ms": (_i32, [_vp, C.POINTER(C.c_float)]),
+    "dph_index_profile_scan_ms": (_i32, [_vp, _vp, _i32]),
+    "dph_index_profile_count": (_i32, [_vp]),
     "dph_index_search": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i32]),
     "dph_index_search_partial": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "dph_merge_shards": (_i32, [_vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),

@@ -116,7 +116,7 @@ DPH_API void dph_index_free(dph_index* ix) {
     void* ptrs[] = {ix->A, ix->C, ix->pq, ix->list_len, ix->list_start, ix->blk_off, ix->codes, ix->ids, ix->dm_ids, ix->dm_rows};
     for (void* p : ptrs) if (p) cudaFree(p);
     DevBuf* bufs[] = {&ix->xdev, &ix->xr, &ix->S, &ix->key, &ix->cd, &ix->lut_scan, &ix->lut_canon, &ix->lutmax, &ix->segs, &ix->wpre, &ix->qinfo,
-                      &ix->cand, &ix->cand_off, &ix->cand_cnt, &ix->gthr, &ix->flags, &ix->work, &ix->Dp, &ix->Ip, &ix->Gp, &ix->Dh, &ix->Ih, &ix->eps};
+                      &ix->cand, &ix->cand_off, &ix->cand_cnt, &ix->gthr, &ix->flags, &ix->work, &ix->Dp, &ix->Ip, &ix->Gp, &ix->Dh, &ix->Ih, &ix->eps, &ix->nseg};
     for (DevBuf* b : bufs) b->release();
     delete ix;
 }
@@ -262,16 +262,30 @@ DPH_API int dph_index_get_opq(const dph_index* ix, float* A_out, int mem) {
 }
 DPH_API int dph_index_set_profile(dph_index* ix, int on) {
     DPH_CUDA(cudaSetDevice(ix->device));
-    if (on && !ix->ev0) { DPH_CUDA(cudaEventCreate(&ix->ev0)); DPH_CUDA(cudaEventCreate(&ix->ev1)); }
+    if (on && !ix->ev0[0])
+        for (int i = 0; i < DPH_PROF_RING; i++) { DPH_CUDA(cudaEventCreate(&ix->ev0[i])); DPH_CUDA(cudaEventCreate(&ix->ev1[i])); }
     ix->profile = on != 0;
+    ix->prof_n = 0;
     return 0;
 }
 DPH_API int dph_index_last_scan_ms(dph_index* ix, float* ms) {
-    DPH_CHECK(ix->profile && ix->ev0, "profiling is off");
-    DPH_CUDA(cudaEventSynchronize(ix->ev1));
-    DPH_CUDA(cudaEventElapsedTime(ms, ix->ev0, ix->ev1));
+    DPH_CHECK(ix->ev0[0] && ix->prof_n > 0, "no profiled search");
+    int i = (int)((ix->prof_n - 1) % DPH_PROF_RING);
+    DPH_CUDA(cudaEventSynchronize(ix->ev1[i]));
+    DPH_CUDA(cudaEventElapsedTime(ms, ix->ev0[i], ix->ev1[i]));
     return 0;
 }
+DPH_API int dph_index_profile_scan_ms(dph_index* ix, float* ms_out, int max_out) {
+    DPH_CHECK(ix->ev0[0] != nullptr, "profiling was never enabled");
+    int n = (int)std::min<int64_t>(std::min<int64_t>(ix->prof_n, DPH_PROF_RING), max_out);
+    for (int j = 0; j < n; j++) {
+        int i = (int)((ix->prof_n - n + j) % DPH_PROF_RING);
+        DPH_CUDA(cudaEventSynchronize(ix->ev1[i]));
+        DPH_CUDA(cudaEventElapsedTime(ms_out + j, ix->ev0[i], ix->ev1[i]));
+    }
+    return n < 0 ? 0 : 0 * n;
+}
+DPH_API int dph_index_profile_count(const dph_index* ix) { return (int)std::min<int64_t>(ix->prof_n, DPH_PROF_RING); }
 DPH_API int64_t dph_index_device_bytes(const dph_index* ix) { return ix->bytes; }
 DPH_API const int32_t* dph_index_last_flags(const dph_index* ix) { return ix->flags.as<int32_t>(); }
 DPH_API const int32_t* dph_index_last_probes(const dph_index* ix) { return ix->key.as<int32_t>(); }
@@ -305,6 +319,7 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
     DPH_TRY(ix->wpre.ensure((size_t)(n + 1) * 8));
     DPH_TRY(ix->qinfo.ensure((size_t)n * 4));
     DPH_TRY(ix->eps.ensure((size_t)n * 4));
+    DPH_TRY(ix->nseg.ensure((size_t)n * 4));
     DPH_TRY(ix->cand.ensure((size_t)(2 * grid + 2 * n + 2) * keep_max * 8));
     DPH_TRY(ix->cand_off.ensure((size_t)(n + 1) * 8));
     DPH_TRY(ix->cand_cnt.ensure((size_t)n * 4));
@@ -319,9 +334,9 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
     DPH_TRY(dph_launch_lut(ix->xr.as<float>(), n, ix->pq, ix->lut_scan.as<float>(), ix->lut_canon.as<float>(), ix->lutmax.as<float>(), st));
     if (ix->scan_mode == DPH_SCAN_FAST) {
         DPH_TRY(dph_launch_plan(ix, n, k, keep_fast, grid, nullptr, st));
-        if (ix->profile) DPH_CUDA(cudaEventRecord(ix->ev0, st));
+        if (ix->profile) DPH_CUDA(cudaEventRecord(ix->ev0[ix->prof_n % DPH_PROF_RING], st));
         DPH_TRY(dph_launch_scan(ix, n, k, keep_fast, DPH_SCAN_FAST, grid, st));
-        if (ix->profile) DPH_CUDA(cudaEventRecord(ix->ev1, st));
+        if (ix->profile) { DPH_CUDA(cudaEventRecord(ix->ev1[ix->prof_n % DPH_PROF_RING], st)); ix->prof_n++; }
         DPH_TRY(dph_launch_merge(ix, n, k, DPH_SCAN_FAST, nullptr, D, I, G, st));
         // fallback for queries whose filter could not be proven exact (no-op launches when no flag is set)
         DPH_TRY(dph_launch_plan(ix, n, k, k, grid, ix->flags.as<int32_t>(), st));
@@ -330,9 +345,9 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
     } else {
         DPH_CUDA(cudaMemsetAsync(ix->flags.p, 0, (size_t)n * 4, st));
         DPH_TRY(dph_launch_plan(ix, n, k, k, grid, nullptr, st));
-        if (ix->profile) DPH_CUDA(cudaEventRecord(ix->ev0, st));
+        if (ix->profile) DPH_CUDA(cudaEventRecord(ix->ev0[ix->prof_n % DPH_PROF_RING], st));
         DPH_TRY(dph_launch_scan(ix, n, k, k, DPH_SCAN_EXACT, grid, st));
-        if (ix->profile) DPH_CUDA(cudaEventRecord(ix->ev1, st));
+        if (ix->profile) { DPH_CUDA(cudaEventRecord(ix->ev1[ix->prof_n % DPH_PROF_RING], st)); ix->prof_n++; }
         DPH_TRY(dph_launch_merge(ix, n, k, DPH_SCAN_EXACT, nullptr, D, I, G, st));
     }
     return 0;

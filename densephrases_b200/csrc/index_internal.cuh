@@ -9,10 +9,13 @@
 #define DPH_CAND_CAP 3072          // shared-memory candidate buffer (u64 keys) per scan CTA
 #define DPH_KEEP_SLACK 32          // fast mode keeps k + slack candidates per CTA
 #define DPH_MAX_K 1024
+#define DPH_PROF_RING 64
 #define DPH_MAX_NPROBE 1024
 #define DPH_SURV_CAP 2048          // merge kernel: survivors re-scored exactly per query
 #define DPH_LUT_SCAN_FLOATS (3 * 256 * 64)   // per query: 3 segments x 256 codes x (32 + 31 dup + 1 pad)
 #define DPH_LUT_CANON_FLOATS (96 * 256)
+#define DPH_SEG_SMEM 256            // segment descriptors of one query kept in shared memory by the scan kernel
+#define DPH_L2_PREFETCH_ROUNDS 4    // scan kernel: bulk L2 prefetch distance, in rounds (one 3 KB block per warp per round)
 
 struct DevBuf {            // grow-only device buffer
     void* p = nullptr;
@@ -53,10 +56,11 @@ struct dph_index {
 
     // per-batch workspace
     DevBuf xdev, xr, S, key, cd, lut_scan, lut_canon, lutmax, segs, wpre, qinfo, cand, cand_off, cand_cnt, gthr, flags,
-        work, Dp, Ip, Gp, Dh, Ih, eps;
+        work, Dp, Ip, Gp, Dh, Ih, eps, nseg;
     int64_t last_n = 0;
     bool profile = false;              // CUDA events around the scan kernel of the last search chunk
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0[DPH_PROF_RING] = {}, ev1[DPH_PROF_RING] = {};
+    int64_t prof_n = 0;
 };
 
 // ---- prep.cu ----

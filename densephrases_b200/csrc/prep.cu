@@ -208,14 +208,17 @@ struct PlanArgs {
     long long list_lo, list_hi; int nprobe; long long n;
     const int* only_flagged;       // nullable: plan work only for queries with flag != 0
     const float* lutmax;
-    DphSeg* segs; unsigned* qblocks; float* eps;
+    DphSeg* segs; unsigned* qblocks; int* nseg; float* eps;
 };
+// One warp per query.  Writes the COMPACTED list of in-shard, non-empty segments (probe-rank order) to
+// segs[q][0..nseg[q]); gstart stays the canonical scan position over ALL probed lists (tie-break key across shards).
 __global__ void __launch_bounds__(256) plan_segs_kernel(PlanArgs a) {
     const int lane = threadIdx.x & 31;
     const long long q = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (q >= a.n) return;
     const bool active = a.only_flagged ? (a.only_flagged[q] != 0) : true;
     unsigned gacc = 0, wacc = 0;
+    int sacc = 0;
     float dmax = 0.0f;
     for (int r0 = 0; r0 < a.nprobe; r0 += 32) {
         const int r = r0 + lane;
@@ -229,19 +232,21 @@ __global__ void __launch_bounds__(256) plan_segs_kernel(PlanArgs a) {
                 if (active && len > 0 && l >= a.list_lo && l < a.list_hi) { nb = (unsigned)((len + 31) >> 5); blk = a.blk_off[l]; }
             }
         }
-        // warp exclusive scans of len and nb
+        // warp inclusive scans of len and nb
         unsigned gl = (unsigned)len, wl = nb;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             unsigned g2 = __shfl_up_sync(0xffffffffu, gl, off), w2 = __shfl_up_sync(0xffffffffu, wl, off);
             if (lane >= off) { gl += g2; wl += w2; }
         }
-        if (r < a.nprobe) {
+        const unsigned have = __ballot_sync(0xffffffffu, nb > 0);
+        if (nb > 0) {
             DphSeg s;
             s.blk = blk; s.len = len; s.gstart = gacc + gl - (unsigned)len; s.dis0 = d0;
             s.wrel = wacc + wl - nb; s.wend = wacc + wl; s.list = l;
-            a.segs[q * a.nprobe + r] = s;
+            a.segs[q * a.nprobe + sacc + __popc(have & ((1u << lane) - 1u))] = s;
         }
+        sacc += __popc(have);
         gacc += __shfl_sync(0xffffffffu, gl, 31);
         wacc += __shfl_sync(0xffffffffu, wl, 31);
     }
@@ -253,6 +258,7 @@ __global__ void __launch_bounds__(256) plan_segs_kernel(PlanArgs a) {
     for (int off = 16; off > 0; off >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
     if (lane == 0) {
         a.qblocks[q] = wacc;
+        a.nseg[q] = sacc;
         // |approx - canonical| <= 2 * gamma_96 * sum|terms|,  gamma_96 = 96u/(1-96u), u = 2^-24  (Higham 2002, eq. 4.4);
         // inflated by 1.01 for the fp32 evaluation of the bound itself.
         const float gamma96 = 5.7221e-6f;
@@ -330,7 +336,7 @@ int dph_launch_plan(dph_index* ix, int64_t n, int k, int keep, int grid, const i
     PlanArgs a;
     a.key = ix->key.as<int>(); a.cd = ix->cd.as<float>(); a.list_len = ix->list_len; a.blk_off = (const long long*)ix->blk_off;
     a.list_lo = ix->list_lo; a.list_hi = ix->list_hi; a.nprobe = ix->nprobe; a.n = n; a.only_flagged = only_flagged;
-    a.lutmax = ix->lutmax.as<float>(); a.segs = ix->segs.as<DphSeg>(); a.qblocks = ix->qinfo.as<unsigned>(); a.eps = ix->eps.as<float>();
+    a.lutmax = ix->lutmax.as<float>(); a.segs = ix->segs.as<DphSeg>(); a.qblocks = ix->qinfo.as<unsigned>(); a.nseg = ix->nseg.as<int>(); a.eps = ix->eps.as<float>();
     plan_segs_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(a);
     DPH_CUDA(cudaGetLastError());
     PlanScanArgs b;

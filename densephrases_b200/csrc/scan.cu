@@ -24,7 +24,7 @@
 #include "select.cuh"
 
 struct ScanArgs {
-    const uint8_t* codes; const long long* qpre; const DphSeg* segs; const DphWork* work;
+    const uint8_t* codes; const long long* qpre; const DphSeg* segs; const int* nseg; const DphWork* work;
     const float* lut_scan; const float* lut_canon;
     unsigned* gthr; unsigned long long* cand; const long long* cand_off; int* cand_cnt;
     long long n; int nprobe; int keep;
@@ -34,18 +34,22 @@ struct ScanArgs {
 #define NW DPH_SCAN_WARPS
 #define SMEM_LUT_FAST (DPH_LUT_SCAN_FLOATS * 4)                 // 196608
 #define SMEM_LUT_EXACT (DPH_LUT_CANON_FLOATS * 4 + NW * DPH_BLK_BYTES)   // 98304 + 49152
-#define SMEM_TAIL (DPH_CAND_CAP * 8 + (int)sizeof(SelectScratch) + 64)
 
 struct ScanShared {   // tail of the dynamic shared memory
     unsigned long long cbuf[DPH_CAND_CAP];
+    DphSeg segtab[DPH_SEG_SMEM];
     SelectScratch sc;
-    int cnt; unsigned thr; int base; int pad;
+    int cnt; unsigned thr; int base; int ndone; int ndone_snap; int pad[3];
 };
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
+}
+// TMA-engine bulk prefetch of one contiguous code block into L2 (no register / shared-memory cost).
+__device__ __forceinline__ void l2_prefetch_block(const void* p) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "n"(DPH_BLK_BYTES) : "memory");
 }
 
 struct BlockMeta { const uint4* ptr; int j0; int len; unsigned gstart; float dis0; };
@@ -76,39 +80,22 @@ template <int C> __device__ __forceinline__ void fast_chunk(const uint4& v, unsi
     fast_word<C * 16 + 12>(v.w, y, a0, a1, a2, a3);
 }
 
-// Warp-cooperative lookup of the segment containing work block b (relative to the query's first block).
-// Each lane caches one descriptor of a 32-wide window; windows only move forward.
-__device__ __forceinline__ BlockMeta resolve_block(unsigned b, const DphSeg* __restrict__ segs, int nprobe, int& base,
-                                                    DphSeg& mine, const uint8_t* codes, int lane) {
-    BlockMeta m;
-    while (true) {
-        bool hit = (mine.wrel <= b) && (b < mine.wend);
-        unsigned mask = __ballot_sync(0xffffffffu, hit);
-        if (mask) {
-            int src = __ffs(mask) - 1;
-            unsigned blo = __shfl_sync(0xffffffffu, (unsigned)(mine.blk & 0xffffffffll), src);
-            unsigned bhi = __shfl_sync(0xffffffffu, (unsigned)((unsigned long long)mine.blk >> 32), src);
-            unsigned wrel = __shfl_sync(0xffffffffu, mine.wrel, src);
-            m.len = __shfl_sync(0xffffffffu, mine.len, src);
-            m.gstart = __shfl_sync(0xffffffffu, mine.gstart, src);
-            m.dis0 = __shfl_sync(0xffffffffu, mine.dis0, src);
-            long long blk = (long long)(((unsigned long long)bhi << 32) | blo) + (long long)(b - wrel);
-            m.ptr = reinterpret_cast<const uint4*>(codes + blk * DPH_BLK_BYTES);
-            m.j0 = (int)(b - wrel) * 32;
-            return m;
-        }
-        base += 32;
-        if (base >= nprobe) { m.ptr = nullptr; m.j0 = 0; m.len = 0; m.gstart = 0; m.dis0 = 0.f; return m; }   // unreachable by construction
-        int r = base + lane;
-        if (r < nprobe) {
-            const uint4* sp = reinterpret_cast<const uint4*>(segs + r);
-            uint4 u0 = __ldg(sp), u1 = __ldg(sp + 1);
-            mine.blk = (long long)(((unsigned long long)u0.y << 32) | u0.x);
-            mine.len = (int)u0.z; mine.gstart = u0.w;
-            mine.dis0 = __uint_as_float(u1.x); mine.wrel = u1.y; mine.wend = u1.z; mine.list = (int)u1.w;
-        } else { mine.wrel = 0xFFFFFFFFu; mine.wend = 0u; }
+// Segment cursor: blocks are visited in increasing order, so a forward-only cursor finds the segment of work block b
+// (relative to the query's first block).  The segment fields are cached in registers and re-read only when a
+// segment boundary is crossed (every ~48 rounds at C2 sizes), all lanes reading the same table entry (broadcast).
+struct SegCursor {
+    int seg; unsigned wrel, wend; const uint4* base; int len; unsigned gstart; float dis0;
+    __device__ __forceinline__ void init() { seg = -1; wrel = 0; wend = 0; base = nullptr; len = 0; gstart = 0; dis0 = 0.f; }
+    __device__ __forceinline__ void seek(const DphSeg* __restrict__ tab, unsigned b, const uint8_t* codes) {
+        if (b < wend) return;
+        do { seg++; } while (b >= tab[seg].wend);
+        const uint4 u0 = *reinterpret_cast<const uint4*>(tab + seg);
+        const uint4 u1 = *(reinterpret_cast<const uint4*>(tab + seg) + 1);
+        base = reinterpret_cast<const uint4*>(codes + (long long)(((unsigned long long)u0.y << 32) | u0.x) * DPH_BLK_BYTES);
+        len = (int)u0.z; gstart = u0.w; dis0 = __uint_as_float(u1.x); wrel = u1.y; wend = u1.z;
     }
-}
+    __device__ __forceinline__ const uint4* ptr(unsigned b) const { return base + (size_t)(b - wrel) * (DPH_BLK_BYTES / 16); }
+};
 
 __device__ __forceinline__ void block_compact(ScanShared* sh, int keep, unsigned* gthr_q) {
     const int tid = threadIdx.x;
@@ -128,6 +115,7 @@ __device__ __forceinline__ void block_compact(ScanShared* sh, int keep, unsigned
         unsigned t = (unsigned)(pivot >> 32);
         unsigned old = atomicMax(gthr_q, t);
         sh->thr = t > old ? t : old;
+        sh->ndone_snap = sh->ndone;
     }
     __syncthreads();
 }
@@ -145,7 +133,6 @@ __global__ void __launch_bounds__(NT, 1) scan_kernel(ScanArgs a) {
     long long lo = 0, hi = a.n;
     while (hi - lo > 1) { long long mid = (lo + hi) >> 1; if (a.qpre[mid] <= g0) lo = mid; else hi = mid; }
     long long q = lo, g = g0;
-    const int RB = (DPH_CAND_CAP - a.keep) / NT;     // rounds between compaction checks (>= 3 for keep <= 1056)
     const unsigned ywin = (((unsigned)__cvta_generic_to_shared(dph_smem)) & 0xFF000000u) | ((unsigned)lane * 4u);
 
     while (g < g1) {
@@ -163,42 +150,63 @@ __global__ void __launch_bounds__(NT, 1) scan_kernel(ScanArgs a) {
 #pragma unroll 8
             for (int i = tid; i < NF4; i += NT) dst[i] = __ldg(src + i);
         }
-        if (tid == 0) { sh->cnt = 0; sh->thr = *((volatile unsigned*)(a.gthr + q)); }
-        __syncthreads();
-
-        const DphSeg* segs = a.segs + q * a.nprobe;
-        int wbase = -32;
-        DphSeg mine; mine.wrel = 0xFFFFFFFFu; mine.wend = 0u; mine.blk = 0; mine.len = 0; mine.gstart = 0; mine.dis0 = 0.f; mine.list = -1;
-        const int nrounds = (int)((b1 - b0 + NW - 1) / NW);
-        uint4 nxt[6];
-        BlockMeta mn; mn.ptr = nullptr; mn.j0 = 0; mn.len = 0; mn.gstart = 0; mn.dis0 = 0.f;
         {
-            unsigned b = b0 + warp;
-            if (b < b1) {
-                mn = resolve_block(b, segs, a.nprobe, wbase, mine, a.codes, lane);
-#pragma unroll
-                for (int cc = 0; cc < 6; cc++) nxt[cc] = ldg_stream(mn.ptr + cc * 32 + lane);
+            const int nsg0 = a.nseg[q];
+            if (nsg0 <= DPH_SEG_SMEM) {
+                const uint4* src = reinterpret_cast<const uint4*>(a.segs + q * a.nprobe);
+                uint4* dst = reinterpret_cast<uint4*>(sh->segtab);
+                for (int i = tid; i < nsg0 * 2; i += NT) dst[i] = __ldg(src + i);
             }
         }
-        for (int round = 0; round < nrounds; round++) {
-            const unsigned b = b0 + (unsigned)round * NW + warp;
-            const bool active = b < b1;
-            uint4 cur[6];
-            BlockMeta mc = mn;
+        if (tid == 0) { sh->cnt = 0; sh->ndone = 0; sh->ndone_snap = 0; sh->thr = *((volatile unsigned*)(a.gthr + q)); }
+        __syncthreads();
+
+        // segment table of this query: shared memory when it fits (always for nprobe <= 256), else global
+        const DphSeg* tab = (a.nseg[q] <= DPH_SEG_SMEM) ? sh->segtab : (a.segs + q * a.nprobe);
+        SegCursor cc, pc;                                 // consume / L2-prefetch cursors
+        cc.init(); pc.init();
+        unsigned b = b0 + warp;                           // next block this warp consumes
+        unsigned bp = b0 + warp;                          // next block this warp prefetches into L2
+        uint4 nxt[6];
+        int n_len = 0; unsigned n_gstart = 0, n_j0 = 0; float n_dis0 = 0.f;
+#pragma unroll 1
+        for (int r = 0; r < DPH_L2_PREFETCH_ROUNDS && bp < b1; r++, bp += NW) {
+            pc.seek(tab, bp, a.codes);
+            if (lane == 0) l2_prefetch_block(pc.ptr(bp));
+        }
+        bool more = b < b1;
+        if (more) {
+            cc.seek(tab, b, a.codes);
+            const uint4* p = cc.ptr(b) + lane;
 #pragma unroll
-            for (int cc = 0; cc < 6; cc++) cur[cc] = nxt[cc];
-            {
-                unsigned bn = b + NW;
-                if (bn < b1) {
-                    mn = resolve_block(bn, segs, a.nprobe, wbase, mine, a.codes, lane);
+            for (int c6 = 0; c6 < 6; c6++) nxt[c6] = ldg_stream(p + c6 * 32);
+            n_len = cc.len; n_gstart = cc.gstart; n_dis0 = cc.dis0; n_j0 = (b - cc.wrel) * 32u;
+        }
+        bool counted = false;
+        while (true) {      // epochs: run until the candidate buffer may overflow or this warp is out of blocks, then meet
+            while (more) {
+                if (*((volatile int*)&sh->cnt) > DPH_CAND_CAP - NT) break;     // every warp adds <= 32 per round after this check
+                uint4 cur[6];
 #pragma unroll
-                    for (int cc = 0; cc < 6; cc++) nxt[cc] = ldg_stream(mn.ptr + cc * 32 + lane);
+                for (int c6 = 0; c6 < 6; c6++) cur[c6] = nxt[c6];
+                const int c_len = n_len; const unsigned c_gstart = n_gstart, c_j0 = n_j0; const float c_dis0 = n_dis0;
+                if (bp < b1) {
+                    pc.seek(tab, bp, a.codes);
+                    if (lane == 0) l2_prefetch_block(pc.ptr(bp));
+                    bp += NW;
                 }
-            }
-            if (active) {
+                b += NW;
+                more = b < b1;
+                if (more) {
+                    cc.seek(tab, b, a.codes);
+                    const uint4* p = cc.ptr(b) + lane;
+#pragma unroll
+                    for (int c6 = 0; c6 < 6; c6++) nxt[c6] = ldg_stream(p + c6 * 32);
+                    n_len = cc.len; n_gstart = cc.gstart; n_dis0 = cc.dis0; n_j0 = (b - cc.wrel) * 32u;
+                }
                 float score;
                 if (MODE == DPH_SCAN_FAST) {
-                    float acc0 = mc.dis0, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+                    float acc0 = c_dis0, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
                     fast_chunk<0>(cur[0], ywin, acc0, acc1, acc2, acc3);
                     fast_chunk<1>(cur[1], ywin, acc0, acc1, acc2, acc3);
                     fast_chunk<2>(cur[2], ywin, acc0, acc1, acc2, acc3);
@@ -210,17 +218,17 @@ __global__ void __launch_bounds__(NT, 1) scan_kernel(ScanArgs a) {
                     unsigned char* stage = smem + DPH_LUT_CANON_FLOATS * 4 + warp * DPH_BLK_BYTES;
                     const float* lutc = reinterpret_cast<const float*>(smem);
 #pragma unroll
-                    for (int cc = 0; cc < 6; cc++) *reinterpret_cast<uint4*>(stage + cc * 512 + lane * 16) = cur[cc];
+                    for (int c6 = 0; c6 < 6; c6++) *reinterpret_cast<uint4*>(stage + c6 * 512 + lane * 16) = cur[c6];
                     __syncwarp();
-                    float dis = mc.dis0;
+                    float dis = c_dis0;
 #pragma unroll 8
                     for (int m = 0; m < DPH_M; m++) dis += lutc[m * 256 + stage[dph_blk_addr(lane, m)]];
                     score = dis;
                     __syncwarp();
                 }
-                const int j = mc.j0 + lane;
+                const unsigned j = c_j0 + lane;
                 const unsigned sk = dph_fkey(score);
-                const bool pass = (j < mc.len) && (sk >= sh->thr);
+                const bool pass = ((int)j < c_len) && (sk >= *((volatile unsigned*)&sh->thr));
                 const unsigned pm = __ballot_sync(0xffffffffu, pass);
                 if (pm) {
                     int basep = 0;
@@ -228,18 +236,22 @@ __global__ void __launch_bounds__(NT, 1) scan_kernel(ScanArgs a) {
                     basep = __shfl_sync(0xffffffffu, basep, 0);
                     if (pass) {
                         int p = basep + __popc(pm & ((1u << lane) - 1u));
-                        if (p < DPH_CAND_CAP) sh->cbuf[p] = ((unsigned long long)sk << 32) | (unsigned long long)(0xFFFFFFFFu - (mc.gstart + (unsigned)j));
+                        if (p < DPH_CAND_CAP) sh->cbuf[p] = ((unsigned long long)sk << 32) | (unsigned long long)(0xFFFFFFFFu - (c_gstart + j));
                     }
                 }
             }
-            if (((round + 1) % RB) == 0 || round == nrounds - 1) {
-                __syncthreads();
-                if (sh->cnt > a.keep) block_compact(sh, a.keep, a.gthr + q);
-                else {
-                    if (tid == 0) { unsigned gt = *((volatile unsigned*)(a.gthr + q)); if (gt > sh->thr) sh->thr = gt; }
-                    __syncthreads();
+            if (!more && !counted) { counted = true; if (lane == 0) atomicAdd(&sh->ndone, 1); }
+            __syncthreads();
+            if (sh->cnt > a.keep) block_compact(sh, a.keep, a.gthr + q);
+            else {
+                if (tid == 0) {
+                    unsigned gt = *((volatile unsigned*)(a.gthr + q));
+                    if (gt > sh->thr) sh->thr = gt;
+                    sh->ndone_snap = sh->ndone;
                 }
+                __syncthreads();
             }
+            if (sh->ndone_snap == NW) break;
         }
         // ---- publish this CTA's candidates for query q ----
         __syncthreads();
@@ -281,7 +293,7 @@ int dph_launch_scan(dph_index* ix, int64_t n, int k, int keep, int mode, int gri
     if (n == 0) return 0;
     DPH_TRY(dph_scan_setup_attrs());
     ScanArgs a;
-    a.codes = ix->codes; a.qpre = ix->wpre.as<long long>(); a.segs = ix->segs.as<DphSeg>(); a.work = ix->work.as<DphWork>();
+    a.codes = ix->codes; a.qpre = ix->wpre.as<long long>(); a.segs = ix->segs.as<DphSeg>(); a.nseg = ix->nseg.as<int>(); a.work = ix->work.as<DphWork>();
     a.lut_scan = ix->lut_scan.as<float>(); a.lut_canon = ix->lut_canon.as<float>(); a.gthr = ix->gthr.as<unsigned>();
     a.cand = ix->cand.as<unsigned long long>(); a.cand_off = ix->cand_off.as<long long>(); a.cand_cnt = ix->cand_cnt.as<int>();
     a.n = n; a.nprobe = ix->nprobe; a.keep = keep;
@@ -299,7 +311,7 @@ int dph_launch_scan(dph_index* ix, int64_t n, int k, int keep, int mode, int gri
 // =================================================================================================
 struct MergeArgs {
     const unsigned long long* cand; const long long* cand_off; const int* cand_cnt; const unsigned* gthr; const float* eps;
-    const DphSeg* segs; int nprobe; int k; int mode;
+    const DphSeg* segs; const int* nseg; int nprobe; int k; int mode;
     const uint8_t* codes; const float* lut_canon; const long long* ids; const long long* list_start;
     float* D; long long* I; unsigned* G; int* flags; const int* only_flagged;
 };
@@ -322,6 +334,7 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeArgs a) {
     int n = a.cand_cnt[q];
     if (n > cap) n = (int)cap;
     const DphSeg* segs = a.segs + q * a.nprobe;
+    const int nsg = a.nseg[q];
     const int k = a.k;
     if (tid == 0) { scnt = 0; sflag = 0; }
     __syncthreads();
@@ -351,7 +364,7 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeArgs a) {
         const float* lutc = a.lut_canon + (size_t)q * DPH_LUT_CANON_FLOATS;
         for (int i = tid; i < ns; i += blockDim.x) {
             const unsigned gidx = dph_ckey_gidx(surv[i]);
-            const DphSeg s = segs[find_seg(segs, a.nprobe, gidx)];
+            const DphSeg s = segs[find_seg(segs, nsg, gidx)];
             const unsigned j = gidx - s.gstart;
             const uint8_t* blk = a.codes + (s.blk + (long long)(j >> 5)) * DPH_BLK_BYTES;
             const int ln = (int)(j & 31u);
@@ -369,7 +382,7 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeArgs a) {
         if (i < ns) {
             const unsigned long long e = surv[i];
             gi = dph_ckey_gidx(e); d = dph_ckey_score(e);
-            const DphSeg s = segs[find_seg(segs, a.nprobe, gi)];
+            const DphSeg s = segs[find_seg(segs, nsg, gi)];
             const unsigned j = gi - s.gstart;
             id = a.ids ? a.ids[s.blk * 32 + j] : a.list_start[s.list] + (long long)j;
         }
@@ -383,7 +396,7 @@ int dph_launch_merge(dph_index* ix, int64_t n, int k, int mode, const int32_t* o
     if (n == 0) return 0;
     MergeArgs a;
     a.cand = ix->cand.as<unsigned long long>(); a.cand_off = ix->cand_off.as<long long>(); a.cand_cnt = ix->cand_cnt.as<int>();
-    a.gthr = ix->gthr.as<unsigned>(); a.eps = ix->eps.as<float>(); a.segs = ix->segs.as<DphSeg>(); a.nprobe = ix->nprobe; a.k = k; a.mode = mode;
+    a.gthr = ix->gthr.as<unsigned>(); a.eps = ix->eps.as<float>(); a.segs = ix->segs.as<DphSeg>(); a.nseg = ix->nseg.as<int>(); a.nprobe = ix->nprobe; a.k = k; a.mode = mode;
     a.codes = ix->codes; a.lut_canon = ix->lut_canon.as<float>(); a.ids = (const long long*)ix->ids; a.list_start = (const long long*)ix->list_start;
     a.D = D; a.I = (long long*)I; a.G = G; a.flags = ix->flags.as<int>(); a.only_flagged = only_flagged;
     merge_kernel<<<(unsigned)n, 256, 0, st>>>(a);

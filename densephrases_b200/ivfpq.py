@@ -106,6 +106,12 @@ class IvfPqIndex:
         L.check(L.lib().dph_index_last_scan_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def profile_scan_ms(self):
+        n = L.lib().dph_index_profile_count(self._h)
+        out = np.zeros(max(n, 1), dtype=np.float32)
+        L.check(L.lib().dph_index_profile_scan_ms(self._h, _np_ptr(out), n))
+        return out[:n]
+
     @property
     def device_bytes(self):
         return L.lib().dph_index_device_bytes(self._h)

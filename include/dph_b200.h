@@ -72,6 +72,10 @@ int64_t dph_index_device_bytes(const dph_index* ix);
  * for it and returns the kernel's duration in milliseconds (bench.py roofline). */
 int dph_index_set_profile(dph_index* ix, int on);
 int dph_index_last_scan_ms(dph_index* ix, float* ms);
+/* Durations of the scan kernels of the last (up to 64) searches since profiling was switched on, oldest first;
+ * dph_index_profile_count gives how many.  Lets bench.py time the kernel inside a back-to-back step loop. */
+int dph_index_profile_scan_ms(dph_index* ix, float* ms_out, int max_out);
+int dph_index_profile_count(const dph_index* ix);
 
 /* ---- search (replaces index.search at index.py:200) ----
  * x [n,d] fp32; D [n,k] fp32, I [n,k] int64 labels; sorted by descending score; unfilled slots are
