@@ -15,10 +15,29 @@ def shard_ranges(list_len, world):
     total = cum[-1]
     cuts = [0]
     for r in range(1, world):
-        cuts.append(int(np.searchsorted(cum, total * r / world, side="left")))
+        t = total * r / world
+        i = int(np.searchsorted(cum, t, side="left"))
+        if i > 0 and abs(cum[i - 1] - t) <= abs(cum[min(i, len(cum) - 1)] - t):
+            i -= 1
+        cuts.append(i)
     cuts.append(len(list_len))
     cuts = np.maximum.accumulate(np.array(cuts))
     return [(int(cuts[r]), int(cuts[r + 1])) for r in range(world)]
+
+
+def gather_and_merge(D, I, G, k, world, group=None, merge_fn=merge_shards):
+    """The single exchange step of the sharded search: all-gather every shard's [n,k] partial top-k
+    (score f32, label i64, canonical scan position i32) and merge identically on every rank.
+    Backend-agnostic (nccl on GPUs; the gloo CPU test passes a numpy merge_fn)."""
+    import torch.distributed as dist
+    n = D.shape[0]
+    Dg = torch.empty((world * n, k), dtype=D.dtype, device=D.device)      # concatenated along dim 0 (gloo and nccl both accept it)
+    Ig = torch.empty((world * n, k), dtype=I.dtype, device=I.device)
+    Gg = torch.empty((world * n, k), dtype=G.dtype, device=G.device)
+    dist.all_gather_into_tensor(Dg, D.contiguous(), group=group)
+    dist.all_gather_into_tensor(Ig, I.contiguous(), group=group)
+    dist.all_gather_into_tensor(Gg, G.contiguous(), group=group)
+    return merge_fn(Dg.view(world, n, k), Ig.view(world, n, k), Gg.view(world, n, k), k)
 
 
 class ShardedIvfPq:
@@ -52,16 +71,8 @@ class ShardedIvfPq:
         """x torch cuda [n,d] (same on every rank) -> (D, I) torch cuda [n,k] (same on every rank)."""
         if self.world == 1:
             return self.local.search(x, k)
-        import torch.distributed as dist
         D, I, G = self.local.search_partial(x, k)
-        n = x.shape[0]
-        Dg = torch.empty((self.world, n, k), dtype=torch.float32, device=x.device)
-        Ig = torch.empty((self.world, n, k), dtype=torch.int64, device=x.device)
-        Gg = torch.empty((self.world, n, k), dtype=torch.int32, device=x.device)
-        dist.all_gather_into_tensor(Dg, D, group=self.group)
-        dist.all_gather_into_tensor(Ig, I, group=self.group)
-        dist.all_gather_into_tensor(Gg, G, group=self.group)
-        return merge_shards(Dg, Ig, Gg, k)
+        return gather_and_merge(D, I, G, k, self.world, self.group)
 
     def search(self, x, k):
         """Host API == faiss index.search (index.py:200): numpy / pinned CPU tensor [n,d] -> numpy (D, I)."""

@@ -1,0 +1,78 @@
+"""CPU (gloo, world_size 2): host-side logic of the list-range sharded search -- shard_ranges cuts, the one
+all-gather exchange (gather_and_merge) and the canonical (score desc, scan position asc) merge -- checked against the
+unsharded oracle.  Per-shard partial results are produced by the oracle restricted to the shard's lists."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests.helpers import assert_topk_equal, near_queries, opq_matrix
+
+
+def test_shard_ranges_balance_by_bytes():
+    from densephrases_b200.sharded import shard_ranges
+    rng = np.random.default_rng(0)
+    lens = np.exp(rng.normal(0, 0.5, 4096))
+    lens = (lens / lens.sum() * 1e7).astype(np.int64)
+    for world in (1, 2, 4, 8):
+        rs = shard_ranges(lens, world)
+        assert rs[0][0] == 0 and rs[-1][1] == len(lens) and all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
+        loads = np.array([lens[a:b].sum() for a, b in rs], dtype=np.float64)
+        assert loads.max() / loads.mean() < 1.01
+    (a0, a1), (b0, b1) = shard_ranges(np.array([5, 0, 0, 7]), 2)
+    assert a0 == 0 and a1 == b0 and b1 == 4 and 1 <= a1 <= 3
+
+
+def numpy_merge(Dg, Ig, Gg, k):
+    Dg, Ig, Gg = Dg.numpy(), Ig.numpy(), Gg.numpy().astype(np.int64) & 0xFFFFFFFF
+    nsh, n, _ = Dg.shape
+    D = np.full((n, k), np.float32(-3.4028234663852886e38), dtype=np.float32)
+    I = np.full((n, k), -1, dtype=np.int64)
+    for q in range(n):
+        ent = [(-float(Dg[s, q, r]), int(Gg[s, q, r]), int(Ig[s, q, r]), Dg[s, q, r]) for s in range(nsh) for r in range(k) if Ig[s, q, r] >= 0]
+        ent.sort(key=lambda e: (e[0], e[1]))
+        for i, e in enumerate(ent[:k]):
+            D[q, i], I[q, i] = e[3], e[2]
+    return torch.from_numpy(D), torch.from_numpy(I)
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from densephrases_b200.sharded import gather_and_merge, shard_ranges
+    from oracle import ivfpq_ref as R
+    seed, nlist, nprobe, k = 5, 32, 12, 10
+    lens = np.random.default_rng(seed).integers(0, 300, nlist).astype(np.int64)
+    ix = R.RefIndex(opq_matrix(seed), R.gen_pq(seed), lens, centroids=R.gen_centroids(seed, 0, nlist), seed=seed)
+    x = near_queries(ix, 9, 3)
+    Dfull, Ifull, key = ix.search(x, k, nprobe, return_key=True)
+    lo, hi = shard_ranges(lens, world)[rank]
+    xr = ix.rotate(x)
+    key_local = np.where((key >= lo) & (key < hi), key, -1)
+    D, I = ix.search_preassigned(xr, key_local, k)
+    # canonical scan position of each hit: prefix of the probed list lengths (ALL probes, global) + offset
+    G = np.zeros_like(I)
+    for q in range(len(x)):
+        starts = np.concatenate([[0], np.cumsum([lens[l] if l >= 0 else 0 for l in key[q]])])
+        for r in range(k):
+            if I[q, r] >= 0:
+                l, off = ix.locate(np.array([I[q, r]]))
+                G[q, r] = starts[list(key[q]).index(int(l[0]))] + int(off[0])
+    Dm, Im = gather_and_merge(torch.from_numpy(D), torch.from_numpy(I), torch.from_numpy(G.astype(np.int32)), k, world, merge_fn=numpy_merge)
+    if rank == 0:
+        np.savez(out, D=Dm.numpy(), I=Im.numpy(), Dfull=Dfull, Ifull=Ifull)
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_sharded_merge_equals_unsharded(tmp_path, oracle):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "merged.npz")
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    g = np.load(out)
+    assert_topk_equal(g["D"], g["I"], g["Dfull"], g["Ifull"], "sharded vs unsharded")
