@@ -26,6 +26,18 @@ class IvfPqIndex:
         if h:
             L.lib().dph_index_free(h)
 
+    @classmethod
+    def from_arrays(cls, A, centroids, pq, list_len, codes, ids=None, device=0, shard=None):
+        """Build from the arrays a faiss IndexPreTransform(OPQ)->IndexIVFPQ file holds (index.py:30)."""
+        ix = cls(len(list_len), device=device)
+        ix.set_opq(A)
+        ix.set_centroids(centroids)
+        ix.set_pq(pq)
+        if shard is not None:
+            ix.set_shard(*shard)
+        ix.set_lists(list_len, codes, ids)
+        return ix
+
     # ---- construction -----------------------------------------------------------------------
     def set_opq(self, A):
         A = np.ascontiguousarray(A, dtype=np.float32)
