@@ -1,0 +1,109 @@
+"""MIPS API mirror (densephrases_b200/mips.py) vs the item-by-item restatement of the reference's phrase stage
+(oracle/mips_ref.py).  CPU: host logic over an adapter around the oracle index (the CUDA index cannot run here);
+GPU: the same comparison end to end through libdph_b200."""
+import numpy as np
+import pytest
+
+from tests.helpers import opq_matrix
+
+NLIST, SEED = 24, 3
+
+
+class OracleIndexAdapter:
+    """Test-only: gives the oracle RefIndex the IvfPqIndex surface MIPS uses (search / reconstruct_batch / ...)."""
+
+    def __init__(self, ref):
+        self.ref, self.nprobe, self.d, self.ntotal = ref, 256, ref.d, ref.ntotal
+
+    def search(self, x, k):
+        return self.ref.search(x, k, self.nprobe)
+
+    def reconstruct_batch(self, ids):
+        return self.ref.reconstruct(np.asarray(ids, dtype=np.int64))
+
+    def opq_matrix(self):
+        return self.ref.A
+
+
+def build(oracle, n_docs=12):
+    from densephrases_b200.synthetic import make_corpus, make_phrase_index_arrays
+    doc_groups, idx_f, ntotal = make_corpus(n_docs, SEED)
+    list_len, codes, ids = make_phrase_index_arrays(ntotal, NLIST, SEED)
+    A, pq, Cm = opq_matrix(SEED), oracle.gen_pq(SEED), oracle.gen_centroids(SEED, 0, NLIST)
+    ref = oracle.RefIndex(A, pq, list_len, centroids=Cm, codes=codes, ids=ids)
+    rng = np.random.default_rng(9)
+    pick = rng.integers(0, ntotal, (6, 2))
+    vs, _ = ref.reconstruct(pick[:, 0])
+    ve, _ = ref.reconstruct(np.minimum(pick[:, 0] + rng.integers(0, 4, 6), ntotal - 1))
+    query = np.concatenate([vs @ A, ve @ A], 1).astype(np.float64) + 0.05 * rng.standard_normal((6, 1536))
+    return doc_groups, idx_f, (A, pq, Cm, list_len, codes, ids), ref, query
+
+
+def compare(outs, refs, vec_tol=None):
+    assert len(outs) == len(refs)
+    for got, want in zip(outs, refs):
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            for key in ('context', 'title', 'doc_idx', 'start_pos', 'end_pos', 'start_idx', 'end_idx', 'answer'):
+                assert g[key] == w[key], (key, g[key], w[key])
+            assert abs(g['score'] - w['score']) <= 1e-3 * max(1.0, abs(w['score']))        # fp32 matmul order differs (torch vs numpy)
+            if vec_tol is not None:
+                assert np.abs(np.asarray(g['start_vec']) - w['start_vec']).max() < vec_tol
+                assert np.abs(np.asarray(g['end_vec']) - w['end_vec']).max() < vec_tol
+
+
+@pytest.mark.parametrize("aggregate,agg", [(False, 'opt1'), (True, 'opt1'), (True, 'opt2'), (True, 'opt3'), (True, 'opt4')])
+def test_mips_host_logic_matches_reference_restatement_cpu(oracle, aggregate, agg):
+    from densephrases_b200.mips import MIPS, normalize_answer
+    from oracle.mips_ref import ref_search
+    doc_groups, idx_f, _, ref, query = build(oracle)
+    mips = MIPS.from_components(OracleIndexAdapter(ref), idx_f, doc_groups, cuda=False)
+    mips.index.nprobe = 8
+    outs = mips.search(query, q_texts=['q'] * len(query), top_k=5, aggregate=aggregate, agg_strat=agg, return_idxs=True)
+    refs = ref_search(ref, idx_f, doc_groups, query, top_k=5, nprobe=8, aggregate=aggregate, agg_strat=agg, return_idxs=True,
+                      normalize_answer=normalize_answer)
+    compare(outs, refs, vec_tol=1e-3)
+    assert len(mips.num_docs_list) == 1
+
+
+def test_get_idxs_clips_out_of_range(oracle):
+    from densephrases_b200.mips import MIPS
+    doc_groups, idx_f, _, ref, _ = build(oracle)
+    mips = MIPS.from_components(OracleIndexAdapter(ref), idx_f, doc_groups, cuda=False)
+    doc, word = mips.get_idxs(np.array([[-1, 0, ref.ntotal + 5]]))
+    assert doc[0, 0] == idx_f['0']['doc'][0] and doc[0, 2] == idx_f['0']['doc'][ref.ntotal - 1] and word[0, 1] == 0
+
+
+def test_sentence_crop_and_zlib_metadata(oracle):
+    import zlib
+    from densephrases_b200.mips import MIPS
+    doc_groups, idx_f, _, ref, query = build(oracle)
+    packed = {}
+    for k, g in doc_groups.items():     # the reference keeps compressed blobs + dtypes (compress_metadata.py:32-53)
+        packed[k] = {'word2char_start': zlib.compress(g['word2char_start'].tobytes()), 'word2char_end': zlib.compress(g['word2char_end'].tobytes()),
+                     'f2o_start': zlib.compress(g['f2o_start'].tobytes()), 'context': zlib.compress(g['context'].encode()), 'title': g['title'],
+                     'dtypes': {'word2char_start': g['word2char_start'].dtype, 'word2char_end': g['word2char_end'].dtype, 'f2o_start': g['f2o_start'].dtype}}
+    a = MIPS.from_components(OracleIndexAdapter(ref), idx_f, doc_groups, cuda=False)
+    b = MIPS.from_components(OracleIndexAdapter(ref), idx_f, packed, cuda=False)
+    a.index.nprobe = b.index.nprobe = 8
+    ra = a.search(query, q_texts=['q'] * 6, top_k=4, return_sent=True)
+    rb = b.search(query, q_texts=['q'] * 6, top_k=4, return_sent=True)
+    for x, y in zip(ra, rb):
+        assert [r['context'] for r in x] == [r['context'] for r in y]
+        for r in x:
+            assert r['context'][r['start_pos']:r['end_pos']] == r['answer']
+
+
+@pytest.mark.gpu
+def test_mips_end_to_end_on_gpu(oracle):
+    from densephrases_b200 import IvfPqIndex
+    from densephrases_b200.mips import MIPS, normalize_answer
+    from oracle.mips_ref import ref_search
+    doc_groups, idx_f, (A, pq, Cm, list_len, codes, ids), ref, query = build(oracle, n_docs=40)
+    index = IvfPqIndex.from_arrays(A, Cm, pq, list_len, codes, ids)
+    mips = MIPS.from_components(index, idx_f, doc_groups, cuda=True)
+    assert mips.index.nprobe == 256                                  # fixed at load (index.py:53,62)
+    outs = mips.search(query, q_texts=['q'] * len(query), top_k=10, aggregate=True, agg_strat='opt1', return_idxs=True, nprobe=3)
+    refs = ref_search(ref, idx_f, doc_groups, query, top_k=10, nprobe=256, aggregate=True, agg_strat='opt1', return_idxs=True,
+                      normalize_answer=normalize_answer)
+    compare(outs, refs, vec_tol=1e-3)
