@@ -49,6 +49,13 @@ _SIGS = {
     "dph_index_last_xr": (_vp, [_vp]),
     "dph_index_copy_last": (_i32, [_vp, _i32, _vp, _i64]),
     "dph_index_reconstruct_batch": (_i32, [_vp, _vp, _i64, _vp, _vp, _i32]),
+    "dph_encoder_create": (_i32, [C.POINTER(_vp), _i32, _i32, _i32, _i32]),
+    "dph_encoder_free": (None, [_vp]),
+    "dph_encoder_set_stream": (_i32, [_vp, _vp]),
+    "dph_encoder_tower_floats": (_i64, [_vp]),
+    "dph_encoder_load_tower": (_i32, [_vp, _i32, _vp, _i32]),
+    "dph_encoder_embed_query": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32]),
+    "dph_gemm_tf32_nt": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp]),
     "dph_index_window_scores": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _i32]),
 }
 EXPORTS = tuple(_SIGS)

@@ -1,0 +1,302 @@
+// encoder.cu -- query-side encoder forward: two independent BERT-base towers on the same tokens, hidden state at
+// position 0 of each (Encoder.forward(return_query=True) -> embed_query, /root/reference/densephrases/encoder.py:146-152,
+// 101-118; HF BertModel semantics restated in SURVEY.md Appendix B).  Both towers run as one grouped problem:
+// every GEMM is one launch of the tcgen05 TF32 kernel (gemm_tf32.cu) with blockIdx.z = tower.
+#include "common.cuh"
+#include "../../include/dph_b200.h"
+#include <vector>
+
+#define ENC_H 768
+#define ENC_HEADS 12
+#define ENC_DH 64
+#define ENC_LAYERS 12
+#define ENC_FF 3072
+#define ENC_MAX_S 384          // Makefile:357-375 uses max_query_length 384 for KILT; attention keeps K,V of one head in smem
+
+int dph_launch_gemm_tf32(int group, const float* const* A, const float* const* W, const float* const* bias, const float* const* residual,
+                         float* const* out, int M, int N, int K, int act, cudaStream_t st);
+
+struct LayerW { const float *Wqkv, *bqkv, *Wo, *bo, *ln1g, *ln1b, *Wi, *bi, *Wo2, *bo2, *ln2g, *ln2b; };
+struct TowerW { const float *word, *pos, *type, *embg, *embb; LayerW L[ENC_LAYERS]; };
+
+struct dph_encoder {
+    int device = 0; int vocab = 0, max_pos = 512, type_vocab = 2;
+    cudaStream_t stream = 0;
+    float* blob[2] = {nullptr, nullptr};
+    TowerW tw[2];
+    // workspace for T tokens
+    int64_t cap_tokens = 0;
+    float *x[2] = {}, *qkv[2] = {}, *ctx[2] = {}, *a[2] = {}, *ffn[2] = {};
+    long long *ids = nullptr, *mask = nullptr, *tt = nullptr;
+    float *out_s = nullptr, *out_e = nullptr;
+    int64_t cap_b = 0;
+};
+
+static int64_t tower_floats(const dph_encoder* e) {
+    int64_t n = (int64_t)e->vocab * ENC_H + (int64_t)e->max_pos * ENC_H + (int64_t)e->type_vocab * ENC_H + 2 * ENC_H;
+    int64_t per_layer = (int64_t)3 * ENC_H * ENC_H + 3 * ENC_H + (int64_t)ENC_H * ENC_H + ENC_H + 2 * ENC_H + (int64_t)ENC_FF * ENC_H + ENC_FF +
+                        (int64_t)ENC_H * ENC_FF + ENC_H + 2 * ENC_H;
+    return n + ENC_LAYERS * per_layer;
+}
+static void carve(dph_encoder* e, int t) {
+    const float* p = e->blob[t];
+    TowerW& w = e->tw[t];
+    auto take = [&](int64_t n) { const float* r = p; p += n; return r; };
+    w.word = take((int64_t)e->vocab * ENC_H); w.pos = take((int64_t)e->max_pos * ENC_H); w.type = take((int64_t)e->type_vocab * ENC_H);
+    w.embg = take(ENC_H); w.embb = take(ENC_H);
+    for (int l = 0; l < ENC_LAYERS; l++) {
+        LayerW& L = w.L[l];
+        L.Wqkv = take((int64_t)3 * ENC_H * ENC_H); L.bqkv = take(3 * ENC_H); L.Wo = take((int64_t)ENC_H * ENC_H); L.bo = take(ENC_H);
+        L.ln1g = take(ENC_H); L.ln1b = take(ENC_H); L.Wi = take((int64_t)ENC_FF * ENC_H); L.bi = take(ENC_FF);
+        L.Wo2 = take((int64_t)ENC_H * ENC_FF); L.bo2 = take(ENC_H); L.ln2g = take(ENC_H); L.ln2b = take(ENC_H);
+    }
+}
+
+// ---- LayerNorm helpers: one 256-thread block per token row, 3 elements per thread, eps inside the sqrt (torch.nn.LayerNorm) ----
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += red[i];
+    return t;
+}
+__device__ __forceinline__ void ln_row_256(float v[3], const float* g, const float* b, float* out, float* red) {
+    const float mean = block_sum_256(v[0] + v[1] + v[2], red) * (1.0f / ENC_H);
+    const float d0 = v[0] - mean, d1 = v[1] - mean, d2 = v[2] - mean;
+    const float var = block_sum_256(d0 * d0 + d1 * d1 + d2 * d2, red) * (1.0f / ENC_H);
+    const float rstd = rsqrtf(var + 1e-12f);
+    const int t = threadIdx.x;
+    out[t] = d0 * rstd * g[t] + b[t];
+    out[t + 256] = d1 * rstd * g[t + 256] + b[t + 256];
+    out[t + 512] = d2 * rstd * g[t + 512] + b[t + 512];
+}
+
+struct EmbedArgs { const long long* ids; const long long* tt; int S; const float* word[2]; const float* pos[2]; const float* type[2];
+                   const float* g[2]; const float* b[2]; float* out[2]; };
+__global__ void __launch_bounds__(256) embed_ln_kernel(EmbedArgs a) {
+    __shared__ float red[8];
+    const long long tok = blockIdx.x; const int tw = blockIdx.y, t = threadIdx.x;
+    const long long id = a.ids[tok], ty = a.tt[tok]; const int s = (int)(tok % a.S);
+    const float* w = a.word[tw] + id * ENC_H; const float* p = a.pos[tw] + (long long)s * ENC_H; const float* y = a.type[tw] + ty * ENC_H;
+    float v[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) v[i] = (w[t + 256 * i] + y[t + 256 * i]) + p[t + 256 * i];   // inputs_embeds + token_type, + position (HF order)
+    ln_row_256(v, a.g[tw], a.b[tw], a.out[tw] + tok * ENC_H, red);
+}
+struct LnArgs { const float* in[2]; const float* g[2]; const float* b[2]; float* out[2]; };
+__global__ void __launch_bounds__(256) layernorm_kernel(LnArgs a) {
+    __shared__ float red[8];
+    const long long tok = blockIdx.x; const int tw = blockIdx.y, t = threadIdx.x;
+    const float* x = a.in[tw] + tok * ENC_H;
+    float v[3] = {x[t], x[t + 256], x[t + 512]};
+    ln_row_256(v, a.g[tw], a.b[tw], a.out[tw] + tok * ENC_H, red);
+}
+
+// ---- self attention: one CTA per (head, batch row, tower); K (padded rows) and V of the head in shared memory; a warp per
+// query row: lanes = keys for QK^T and softmax, lanes = output dims for P V.  scores/8 + (1-mask)*-10000, softmax in fp32.
+struct AttnArgs { const float* qkv[2]; float* ctx[2]; const long long* mask; int S; };
+__global__ void __launch_bounds__(256) attention_kernel(AttnArgs a) {
+    extern __shared__ float asm_[];
+    const int S = a.S, h = blockIdx.x, b = blockIdx.y, tw = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    float* Ks = asm_;                       // [S][65]
+    float* Vs = Ks + (size_t)S * 65;        // [S][64]
+    float* mb = Vs + (size_t)S * 64;        // [S] additive mask
+    float* qs = mb + S;                     // [nw][64]
+    float* ps = qs + nw * 64;               // [nw][S]
+    const float* base = a.qkv[tw] + (long long)b * S * (3 * ENC_H) + h * ENC_DH;
+    for (int i = threadIdx.x; i < S * 64; i += blockDim.x) {
+        const int j = i >> 6, d = i & 63;
+        Ks[j * 65 + d] = base[(long long)j * (3 * ENC_H) + ENC_H + d];
+        Vs[j * 64 + d] = base[(long long)j * (3 * ENC_H) + 2 * ENC_H + d];
+    }
+    for (int j = threadIdx.x; j < S; j += blockDim.x) mb[j] = (1.0f - (float)a.mask[(long long)b * S + j]) * -10000.0f;
+    __syncthreads();
+    const int nj = (S + 31) >> 5;
+    for (int i = warp; i < S; i += nw) {
+        float* q = qs + warp * 64;
+        q[lane] = base[(long long)i * (3 * ENC_H) + lane];
+        q[lane + 32] = base[(long long)i * (3 * ENC_H) + lane + 32];
+        __syncwarp();
+        float sc[ENC_MAX_S / 32];
+        float mx = -3.0e38f;
+#pragma unroll
+        for (int jj = 0; jj < ENC_MAX_S / 32; jj++) {
+            if (jj < nj) {
+                const int j = jj * 32 + lane;
+                float dot = 0.f;
+                if (j < S) {
+                    const float* kr = Ks + j * 65;
+#pragma unroll 16
+                    for (int d = 0; d < 64; d++) dot = fmaf(q[d], kr[d], dot);
+                    dot = dot * 0.125f + mb[j];
+                } else dot = -3.0e38f;
+                sc[jj] = dot;
+                mx = fmaxf(mx, dot);
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        float sum = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < ENC_MAX_S / 32; jj++) {
+            if (jj < nj) {
+                const int j = jj * 32 + lane;
+                const float e = (j < S) ? expf(sc[jj] - mx) : 0.f;
+                sc[jj] = e;
+                sum += e;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        const float inv = 1.0f / sum;
+        float* p = ps + (size_t)warp * S;
+#pragma unroll
+        for (int jj = 0; jj < ENC_MAX_S / 32; jj++)
+            if (jj < nj) { const int j = jj * 32 + lane; if (j < S) p[j] = sc[jj] * inv; }
+        __syncwarp();
+        float o0 = 0.f, o1 = 0.f;
+        for (int j = 0; j < S; j++) {
+            const float pj = p[j];
+            o0 = fmaf(pj, Vs[j * 64 + lane], o0);
+            o1 = fmaf(pj, Vs[j * 64 + lane + 32], o1);
+        }
+        float* out = a.ctx[tw] + ((long long)b * S + i) * ENC_H + h * ENC_DH;
+        out[lane] = o0;
+        out[lane + 32] = o1;
+        __syncwarp();
+    }
+}
+
+// ---- C ABI ---------------------------------------------------------------------------------------------
+DPH_API int dph_encoder_create(dph_encoder** out, int device, int vocab_size, int max_pos, int type_vocab) {
+    DPH_CHECK(out && vocab_size > 0 && max_pos > 0 && type_vocab > 0, "bad encoder geometry");
+    DPH_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    DPH_CUDA(cudaGetDeviceProperties(&prop, device));
+    DPH_CHECK(prop.major == 10, "libdph_b200 is built for sm_100a (B200) only");
+    dph_encoder* e = new dph_encoder();
+    e->device = device; e->vocab = vocab_size; e->max_pos = max_pos; e->type_vocab = type_vocab;
+    *out = e;
+    return 0;
+}
+DPH_API void dph_encoder_free(dph_encoder* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    for (int t = 0; t < 2; t++) {
+        if (e->blob[t]) cudaFree(e->blob[t]);
+        float* ws[] = {e->x[t], e->qkv[t], e->ctx[t], e->a[t], e->ffn[t]};
+        for (float* p : ws) if (p) cudaFree(p);
+    }
+    void* misc[] = {e->ids, e->mask, e->tt, e->out_s, e->out_e};
+    for (void* p : misc) if (p) cudaFree(p);
+    delete e;
+}
+DPH_API int dph_encoder_set_stream(dph_encoder* e, void* s) { e->stream = (cudaStream_t)s; return 0; }
+DPH_API int64_t dph_encoder_tower_floats(const dph_encoder* e) { return tower_floats(e); }
+// blob layout (fp32, all nn.Linear weights as stored by torch: [out_features, in_features]):
+//   word_embeddings [V,768] | position_embeddings [P,768] | token_type_embeddings [T,768] | embeddings.LayerNorm weight, bias |
+//   per layer: [Wq;Wk;Wv] [2304,768] | [bq;bk;bv] | attention.output.dense W [768,768], b | attention.output.LayerNorm w, b |
+//              intermediate.dense W [3072,768], b | output.dense W [768,3072], b | output.LayerNorm w, b
+DPH_API int dph_encoder_load_tower(dph_encoder* e, int tower, const float* blob, int mem) {
+    DPH_CHECK(tower == 0 || tower == 1, "tower must be 0 (query_start_encoder) or 1 (query_end_encoder)");
+    DPH_CUDA(cudaSetDevice(e->device));
+    const size_t bytes = (size_t)tower_floats(e) * 4;
+    if (!e->blob[tower]) DPH_CUDA(cudaMalloc((void**)&e->blob[tower], bytes));
+    DPH_CUDA(cudaMemcpy(e->blob[tower], blob, bytes, mem == DPH_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice));
+    carve(e, tower);
+    return 0;
+}
+static int ensure_ws(dph_encoder* e, int64_t T, int64_t B) {
+    if (T > e->cap_tokens) {
+        for (int t = 0; t < 2; t++) {
+            float** ps[] = {&e->x[t], &e->qkv[t], &e->ctx[t], &e->a[t], &e->ffn[t]};
+            size_t sz[] = {(size_t)T * ENC_H, (size_t)T * 3 * ENC_H, (size_t)T * ENC_H, (size_t)T * ENC_H, (size_t)T * ENC_FF};
+            for (int i = 0; i < 5; i++) { if (*ps[i]) cudaFree(*ps[i]); DPH_CUDA(cudaMalloc((void**)ps[i], sz[i] * 4)); }
+        }
+        long long** ip[] = {&e->ids, &e->mask, &e->tt};
+        for (auto p : ip) { if (*p) cudaFree(*p); DPH_CUDA(cudaMalloc((void**)p, (size_t)T * 8)); }
+        e->cap_tokens = T;
+    }
+    if (B > e->cap_b) {
+        if (e->out_s) cudaFree(e->out_s);
+        if (e->out_e) cudaFree(e->out_e);
+        DPH_CUDA(cudaMalloc((void**)&e->out_s, (size_t)B * ENC_H * 4));
+        DPH_CUDA(cudaMalloc((void**)&e->out_e, (size_t)B * ENC_H * 4));
+        e->cap_b = B;
+    }
+    return 0;
+}
+
+// == Encoder.forward(input_ids_, attention_mask_, token_type_ids_, return_query=True) (encoder.py:146-152):
+// ids/mask/tt int64 [B,S]; start_out/end_out fp32 [B,768] (the reference returns [B,1,768]).
+DPH_API int dph_encoder_embed_query(dph_encoder* e, const int64_t* ids, const int64_t* mask, const int64_t* tt, int B, int S, float* start_out,
+                                    float* end_out, int mem) {
+    DPH_CHECK(e && e->blob[0] && e->blob[1], "encoder weights not loaded");
+    DPH_CHECK(B >= 1 && S >= 1 && S <= ENC_MAX_S && S <= e->max_pos, "sequence length out of range (1..384)");
+    DPH_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    const int64_t T = (int64_t)B * S;
+    DPH_TRY(ensure_ws(e, T, B));
+    const long long *d_ids = (const long long*)ids, *d_mask = (const long long*)mask, *d_tt = (const long long*)tt;
+    if (mem == DPH_MEM_HOST) {
+        DPH_CUDA(cudaMemcpyAsync(e->ids, ids, T * 8, cudaMemcpyHostToDevice, st));
+        DPH_CUDA(cudaMemcpyAsync(e->mask, mask, T * 8, cudaMemcpyHostToDevice, st));
+        DPH_CUDA(cudaMemcpyAsync(e->tt, tt, T * 8, cudaMemcpyHostToDevice, st));
+        d_ids = e->ids; d_mask = e->mask; d_tt = e->tt;
+    }
+    {
+        EmbedArgs a;
+        a.ids = d_ids; a.tt = d_tt; a.S = S;
+        for (int t = 0; t < 2; t++) { a.word[t] = e->tw[t].word; a.pos[t] = e->tw[t].pos; a.type[t] = e->tw[t].type; a.g[t] = e->tw[t].embg; a.b[t] = e->tw[t].embb; a.out[t] = e->x[t]; }
+        embed_ln_kernel<<<dim3((unsigned)T, 2), 256, 0, st>>>(a);
+        DPH_CUDA(cudaGetLastError());
+    }
+    const int attn_warps = 8;
+    const size_t attn_smem = ((size_t)S * 65 + (size_t)S * 64 + S + attn_warps * 64 + (size_t)attn_warps * S) * 4;
+    static bool attr = false;
+    if (!attr) { DPH_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+    for (int l = 0; l < ENC_LAYERS; l++) {
+        const LayerW &L0 = e->tw[0].L[l], &L1 = e->tw[1].L[l];
+        const float* X[2] = {e->x[0], e->x[1]};
+        float* QKV[2] = {e->qkv[0], e->qkv[1]};
+        const float* Wqkv[2] = {L0.Wqkv, L1.Wqkv}; const float* bqkv[2] = {L0.bqkv, L1.bqkv};
+        DPH_TRY(dph_launch_gemm_tf32(2, X, Wqkv, bqkv, nullptr, QKV, (int)T, 3 * ENC_H, ENC_H, 0, st));
+        AttnArgs aa; aa.qkv[0] = e->qkv[0]; aa.qkv[1] = e->qkv[1]; aa.ctx[0] = e->ctx[0]; aa.ctx[1] = e->ctx[1]; aa.mask = d_mask; aa.S = S;
+        attention_kernel<<<dim3(ENC_HEADS, (unsigned)B, 2), attn_warps * 32, attn_smem, st>>>(aa);
+        DPH_CUDA(cudaGetLastError());
+        const float* CTX[2] = {e->ctx[0], e->ctx[1]};
+        float* Aout[2] = {e->a[0], e->a[1]};
+        const float* Wo[2] = {L0.Wo, L1.Wo}; const float* bo[2] = {L0.bo, L1.bo};
+        DPH_TRY(dph_launch_gemm_tf32(2, CTX, Wo, bo, X, Aout, (int)T, ENC_H, ENC_H, 0, st));            // dense + residual
+        LnArgs ln1; for (int t = 0; t < 2; t++) { ln1.in[t] = e->a[t]; ln1.out[t] = e->a[t]; } ln1.g[0] = L0.ln1g; ln1.g[1] = L1.ln1g; ln1.b[0] = L0.ln1b; ln1.b[1] = L1.ln1b;
+        layernorm_kernel<<<dim3((unsigned)T, 2), 256, 0, st>>>(ln1);
+        DPH_CUDA(cudaGetLastError());
+        const float* Ain[2] = {e->a[0], e->a[1]};
+        float* FF[2] = {e->ffn[0], e->ffn[1]};
+        const float* Wi[2] = {L0.Wi, L1.Wi}; const float* bi[2] = {L0.bi, L1.bi};
+        DPH_TRY(dph_launch_gemm_tf32(2, Ain, Wi, bi, nullptr, FF, (int)T, ENC_FF, ENC_H, 1, st));        // intermediate + erf-GELU
+        const float* FFin[2] = {e->ffn[0], e->ffn[1]};
+        float* Xout[2] = {e->x[0], e->x[1]};
+        const float* Wo2[2] = {L0.Wo2, L1.Wo2}; const float* bo2[2] = {L0.bo2, L1.bo2};
+        DPH_TRY(dph_launch_gemm_tf32(2, FFin, Wo2, bo2, Ain, Xout, (int)T, ENC_H, ENC_FF, 0, st));       // output dense + residual
+        LnArgs ln2; for (int t = 0; t < 2; t++) { ln2.in[t] = e->x[t]; ln2.out[t] = e->x[t]; } ln2.g[0] = L0.ln2g; ln2.g[1] = L1.ln2g; ln2.b[0] = L0.ln2b; ln2.b[1] = L1.ln2b;
+        layernorm_kernel<<<dim3((unsigned)T, 2), 256, 0, st>>>(ln2);
+        DPH_CUDA(cudaGetLastError());
+    }
+    // hidden state at position 0 of every sequence ([:, :1, :], encoder.py:116-117)
+    float* ds = mem == DPH_MEM_HOST ? e->out_s : start_out;
+    float* de = mem == DPH_MEM_HOST ? e->out_e : end_out;
+    DPH_CUDA(cudaMemcpy2DAsync(ds, ENC_H * 4, e->x[0], (size_t)S * ENC_H * 4, ENC_H * 4, B, cudaMemcpyDeviceToDevice, st));
+    DPH_CUDA(cudaMemcpy2DAsync(de, ENC_H * 4, e->x[1], (size_t)S * ENC_H * 4, ENC_H * 4, B, cudaMemcpyDeviceToDevice, st));
+    if (mem == DPH_MEM_HOST) {
+        DPH_CUDA(cudaMemcpyAsync(start_out, ds, (size_t)B * ENC_H * 4, cudaMemcpyDeviceToHost, st));
+        DPH_CUDA(cudaMemcpyAsync(end_out, de, (size_t)B * ENC_H * 4, cudaMemcpyDeviceToHost, st));
+        DPH_CUDA(cudaStreamSynchronize(st));
+    }
+    return 0;
+}

@@ -1,0 +1,236 @@
+// gemm_tf32.cu -- out[g] = epilogue(A[g] . W[g]^T + bias[g] (+ residual[g]))  on the 5th-gen tensor cores.
+//
+// The dense contractions of the SpanBERT query towers (HF BertModel behind Encoder.embed_query,
+// /root/reference/densephrases/encoder.py:101-118; QKV / attention-output / FFN projections).
+// fp32 operands in shared memory, tcgen05.mma kind::tf32 (the precision torch 1.9 -- the reference's pin -- used for
+// fp32 matmuls on Ampere+ by default), fp32 accumulators in TMEM.
+//
+// One CTA computes a 128 x 128 output tile:  warp 0 = TMA producer (cp.async.bulk.tensor, SWIZZLE_128B, 3-stage
+// mbarrier ring), warp 1 = MMA issuer (one elected thread, 4 x UMMA 128x128x8 per 32-float k block), warp 2 = TMEM
+// allocator, warps 4-7 = epilogue (tcgen05.ld 32x32b -> bias / erf-GELU / residual -> 128-byte row segments to global).
+// ~97 KB of shared memory and 128 TMEM columns per CTA -> two CTAs per SM, so one tile's epilogue overlaps the
+// neighbour's main loop.  blockIdx.z selects the problem of a group (the two towers run as one launch).
+#include "common.cuh"
+#include "../../include/dph_b200.h"
+#include <cuda.h>
+
+#define GM_BM 128
+#define GM_BN 128
+#define GM_BK 32                   // fp32 elements = 128 bytes = one SWIZZLE_128B row
+#define GM_STAGES 3
+#define GM_STAGE_BYTES ((GM_BM + GM_BN) * GM_BK * 4)       // 32768
+#define GM_SMEM_BYTES (GM_STAGES * GM_STAGE_BYTES + 1024)
+#define GM_MAX_GROUP 2
+
+struct GemmMaps { CUtensorMap a[GM_MAX_GROUP]; CUtensorMap b[GM_MAX_GROUP]; };
+struct GemmArgs {
+    const float* bias[GM_MAX_GROUP]; const float* residual[GM_MAX_GROUP]; float* out[GM_MAX_GROUP];
+    int M, N, K, act;     // act: 0 none, 1 erf-GELU
+};
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor, sm_100 version 1).
+__device__ __forceinline__ unsigned long long make_sw128_desc(unsigned smem_addr) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((smem_addr & 0x3FFFF) >> 4);        // start address, bits [0,14)
+    d |= (unsigned long long)1 << 16;                            // leading byte offset (ignored for swizzled K-major), bits [16,30)
+    d |= (unsigned long long)(1024 >> 4) << 32;                  // stride byte offset, bits [32,46)
+    d |= (unsigned long long)1 << 46;                            // descriptor version (Blackwell)
+    d |= (unsigned long long)2 << 61;                            // layout type SWIZZLE_128B
+    return d;
+}
+
+__global__ void __launch_bounds__(256, 2) gemm_tf32_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
+    extern __shared__ __align__(1024) unsigned char gsm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.z, m_blk = blockIdx.y, n_blk = blockIdx.x;
+    unsigned char* tail = gsm + GM_STAGES * GM_STAGE_BYTES;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(tail);        // full[3], empty[3], tmem_full
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(tail + 64);
+    const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + GM_STAGES), tmem_full = smem_u32(bars + 2 * GM_STAGES);
+    const unsigned stage0 = smem_u32(gsm);
+    const CUtensorMap* map_a = &maps.a[g];
+    const CUtensorMap* map_b = &maps.b[g];
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < GM_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(GM_BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_base = *tmem_slot;
+    const int num_k = args.K / GM_BK;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_k; kb++) {
+                const int s = kb % GM_STAGES;
+                const unsigned ph = (kb / GM_STAGES) & 1;
+                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                mbar_expect_tx(full0 + 8 * s, GM_STAGE_BYTES);
+                const unsigned dst = stage0 + s * GM_STAGE_BYTES;
+                tma_load_2d(dst, map_a, kb * GM_BK, m_blk * GM_BM, full0 + 8 * s);
+                tma_load_2d(dst + GM_BM * GM_BK * 4, map_b, kb * GM_BK, n_blk * GM_BN, full0 + 8 * s);
+            }
+        }
+    } else if (warp == 1) {
+        // instruction descriptor: D=F32, A=B=TF32, both K-major, N>>3 at bit 17, M>>4 at bit 24 (cute::UMMA::InstrDescriptor)
+        const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(GM_BN >> 3) << 17) | ((unsigned)(GM_BM >> 4) << 24);
+        for (int kb = 0; kb < num_k; kb++) {
+            const int s = kb % GM_STAGES;
+            const unsigned ph = (kb / GM_STAGES) & 1;
+            mbar_wait(full0 + 8 * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const unsigned a_addr = stage0 + s * GM_STAGE_BYTES, b_addr = a_addr + GM_BM * GM_BK * 4;
+                const unsigned long long adesc = make_sw128_desc(a_addr), bdesc = make_sw128_desc(b_addr);
+#pragma unroll
+                for (int k = 0; k < GM_BK / 8; k++)         // UMMA_K = 8 tf32 = 32 bytes: advance the start address inside the swizzle atom
+                    umma_tf32(tmem_base, adesc + (unsigned long long)(k * 2), bdesc + (unsigned long long)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                umma_commit(empty0 + 8 * s);                 // frees the stage once these MMAs have read it
+                if (kb == num_k - 1) umma_commit(tmem_full); // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;                              // TMEM lane quarter this warp may access
+        mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const long long row = (long long)m_blk * GM_BM + q * 32 + lane;
+        const float* bias = args.bias[g];
+        const float* resid = args.residual[g];
+        float* out = args.out[g];
+#pragma unroll 1
+        for (int c = 0; c < GM_BN / 32; c++) {
+            unsigned v[32];
+            const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(c * 32);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                  "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                  "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int col0 = n_blk * GM_BN + c * 32;
+            if (row < args.M) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o;
+                    float* po = &o.x;
+                    const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + col0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float* pb = &b4.x;
+                    float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (resid) r4 = *reinterpret_cast<const float4*>(resid + row * args.N + col0 + j);
+                    const float* pr = &r4.x;
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        float x = __uint_as_float(v[j + e]) + pb[e];
+                        if (args.act == 1) x = 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+                        po[e] = x + pr[e];
+                    }
+                    *reinterpret_cast<float4*>(out + row * args.N + col0 + j) = o;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(GM_BN) : "memory");
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+static int get_encode() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    DPH_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    DPH_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    g_encode = (PFN_encodeTiled)fn;
+    return 0;
+}
+// rows x K fp32 row-major matrix -> tensor map with a [GM_BK x 128] box, 128-byte swizzle, zero fill out of bounds
+static int make_map(CUtensorMap* map, const float* ptr, long long rows, int K) {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+    cuuint32_t box[2] = {GM_BK, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DPH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
+    return 0;
+}
+
+// Grouped launch used by the encoder: problems share M, N, K and the epilogue; pointers are device pointers.
+int dph_launch_gemm_tf32(int group, const float* const* A, const float* const* W, const float* const* bias, const float* const* residual,
+                         float* const* out, int M, int N, int K, int act, cudaStream_t st) {
+    DPH_CHECK(group >= 1 && group <= GM_MAX_GROUP, "gemm group size");
+    DPH_CHECK(N % GM_BN == 0 && K % GM_BK == 0 && M >= 1, "gemm_tf32 needs N % 128 == 0 and K % 32 == 0");
+    DPH_TRY(get_encode());
+    static bool attr = false;
+    if (!attr) { DPH_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_BYTES)); attr = true; }
+    GemmMaps maps;
+    GemmArgs args;
+    for (int g = 0; g < GM_MAX_GROUP; g++) {
+        int s = g < group ? g : 0;
+        DPH_TRY(make_map(&maps.a[g], A[s], M, K));
+        DPH_TRY(make_map(&maps.b[g], W[s], N, K));
+        args.bias[g] = bias ? bias[s] : nullptr;
+        args.residual[g] = residual ? residual[s] : nullptr;
+        args.out[g] = out[s];
+    }
+    args.M = M; args.N = N; args.K = K; args.act = act;
+    dim3 grid(N / GM_BN, (M + GM_BM - 1) / GM_BM, group);
+    gemm_tf32_kernel<<<grid, 256, GM_SMEM_BYTES, st>>>(maps, args);
+    DPH_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// C ABI (test / standalone use): out [M,N] = act(A [M,K] . W[N,K]^T + bias) + residual, device pointers, fp32, TF32 tensor cores.
+DPH_API int dph_gemm_tf32_nt(const float* A, const float* W, const float* bias, const float* residual, float* out, int64_t M, int64_t N, int64_t K,
+                             int act, void* cuda_stream) {
+    const float* a[1] = {A}; const float* w[1] = {W}; const float* b[1] = {bias}; const float* r[1] = {residual}; float* o[1] = {out};
+    return dph_launch_gemm_tf32(1, a, w, bias ? b : nullptr, residual ? r : nullptr, o, (int)M, (int)N, (int)K, act, (cudaStream_t)cuda_stream);
+}

@@ -111,6 +111,26 @@ int dph_index_reconstruct_batch(dph_index* ix, const int64_t* ids, int64_t m, fl
 int dph_index_window_scores(dph_index* ix, const float* q /*[m,d]*/, const int64_t* first_id /*[m]*/, int64_t m, int L,
                             float* out_scores, int mem);
 
+/* ---- query encoder (replaces Encoder.forward(return_query=True) -> embed_query, densephrases/encoder.py:146-152,101-118) ----
+ * Two BERT-base towers (12 layers, 768 hidden, 12 heads, 3072 FFN; SpanBERT-base-cased geometry, options.py:23) on the same
+ * tokens.  tower 0 = query_start_encoder.*, tower 1 = query_end_encoder.* (encoder.py:51-52).  Weight blob layout: encoder.cu. */
+typedef struct dph_encoder dph_encoder;
+int dph_encoder_create(dph_encoder** out, int device, int vocab_size, int max_position_embeddings, int type_vocab_size);
+void dph_encoder_free(dph_encoder* e);
+int dph_encoder_set_stream(dph_encoder* e, void* cuda_stream);
+int64_t dph_encoder_tower_floats(const dph_encoder* e);
+int dph_encoder_load_tower(dph_encoder* e, int tower, const float* blob, int mem);
+/* input_ids / attention_mask / token_type_ids int64 [B,S] (S <= 384); start_out / end_out fp32 [B,768] = hidden state at
+ * position 0 of each tower (the reference returns them as [B,1,768]). */
+int dph_encoder_embed_query(dph_encoder* e, const int64_t* input_ids, const int64_t* attention_mask, const int64_t* token_type_ids,
+                            int B, int S, float* start_out, float* end_out, int mem);
+
+/* ---- dense fp32 GEMM on the tcgen05 tensor cores (kind::tf32), the encoder's building block ----
+ * out [M,N] = act(A [M,K] . W [N,K]^T + bias [N]) + residual [M,N]; act: 0 none, 1 erf-GELU; device pointers;
+ * N % 128 == 0, K % 32 == 0.  == torch.nn.functional.linear (HF BertSelfAttention/BertOutput/BertIntermediate). */
+int dph_gemm_tf32_nt(const float* A, const float* W, const float* bias, const float* residual, float* out, int64_t M, int64_t N,
+                     int64_t K, int act, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

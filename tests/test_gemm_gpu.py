@@ -1,0 +1,52 @@
+"""tcgen05 TF32 GEMM (densephrases_b200/csrc/gemm_tf32.cu) vs a plain PyTorch fp32 reference of the same op.
+Tolerance: TF32 keeps 10 mantissa bits of each operand (rel. 2^-11 per product), accumulation is fp32; for K <= 3072 and
+unit-scale operands |err| <= 2e-3 * sqrt(K) * scale is comfortably loose; we assert a relative Frobenius error < 1e-3."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gemm(A, W, bias, resid, act):
+    import torch
+    from densephrases_b200 import _lib as L
+    out = torch.empty((A.shape[0], W.shape[0]), dtype=torch.float32, device=A.device)
+    st = torch.cuda.current_stream().cuda_stream
+    L.check(L.lib().dph_gemm_tf32_nt(A.data_ptr(), W.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                     resid.data_ptr() if resid is not None else None, out.data_ptr(), A.shape[0], W.shape[0], A.shape[1], act,
+                                     C.c_void_p(st)))
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 768), (4096, 768, 768), (4096, 2304, 768), (4096, 3072, 768), (4096, 768, 3072),
+                                   (100, 256, 64), (1, 128, 96), (333, 768, 768)])
+@pytest.mark.parametrize("variant", ["plain", "bias_gelu", "bias_resid"])
+def test_gemm_tf32_matches_torch_fp32(M, N, K, variant):
+    import torch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn((M, K), generator=g, device="cuda")
+    W = torch.randn((N, K), generator=g, device="cuda") * 0.05
+    bias = torch.randn((N,), generator=g, device="cuda") if variant != "plain" else None
+    resid = torch.randn((M, N), generator=g, device="cuda") if variant == "bias_resid" else None
+    act = 1 if variant == "bias_gelu" else 0
+    out = run_gemm(A, W, bias, resid, act)
+    ref = A.double() @ W.double().T
+    if bias is not None:
+        ref = ref + bias.double()
+    if act:
+        ref = torch.nn.functional.gelu(ref)
+    if resid is not None:
+        ref = ref + resid.double()
+    err = (out.double() - ref).norm() / ref.norm()
+    assert torch.isfinite(out).all()
+    assert err < 1e-3, f"relative error {err:.3e}"
+    # exactness of the data path: with operands exactly representable in TF32 the result must match fp32 to rounding
+    A2 = (A * 8).round() / 8
+    W2 = (W * 64).round() / 64
+    out2 = run_gemm(A2.contiguous(), W2.contiguous(), None, None, 0)
+    ref2 = (A2.double() @ W2.double().T)
+    assert (out2.double() - ref2).abs().max() < 1e-3 * max(1.0, ref2.abs().max().item() * 1e-3)
