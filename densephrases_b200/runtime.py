@@ -1,0 +1,222 @@
+"""Glue between strings and the two CUDA kernels families: the reference's L2/L3 layers re-stated for this
+package.  Same function names, arguments and return shapes as
+  densephrases/utils/open_utils.py  load_phrase_index :26-43, get_query2vec :83-101, load_qa_pairs :104-160
+  densephrases/utils/single_utils.py load_encoder :59-118
+  densephrases/utils/eval_utils.py  metrics :9-86
+  densephrases/model.py             DensePhrases :14-128
+  eval_phrase_retrieval.py          embed_all_query :33-46, evaluate :49-91 (the search loop; scoring reduced to EM/F1@1,k)
+so the reference's drivers keep working; what changed is where the arithmetic runs."""
+import json
+import logging
+import os
+import random
+import re
+import string
+import unicodedata
+from collections import Counter
+
+import numpy as np
+import torch
+
+from .encoder import BertGeometry, Encoder, random_state_dict
+from .mips import MIPS
+from .options import Options
+from .tokenization import WordPieceTokenizer
+
+logger = logging.getLogger(__name__)
+
+
+# ---- eval_utils ------------------------------------------------------------------------------------------
+def normalize_answer(s):
+    s = ''.join(ch for ch in s.lower() if ch not in set(string.punctuation))
+    return ' '.join(re.sub(r'\b(a|an|the)\b', ' ', s).split())
+
+
+def f1_score(prediction, ground_truth):
+    p, g = normalize_answer(prediction), normalize_answer(ground_truth)
+    if (p in ('yes', 'no', 'noanswer') or g in ('yes', 'no', 'noanswer')) and p != g:
+        return (0, 0, 0)
+    pt, gt = p.split(), g.split()
+    same = sum((Counter(pt) & Counter(gt)).values())
+    if same == 0:
+        return (0, 0, 0)
+    precision, recall = same / len(pt), same / len(gt)
+    return 2 * precision * recall / (precision + recall), precision, recall
+
+
+def exact_match_score(prediction, ground_truth):
+    return normalize_answer(prediction) == normalize_answer(ground_truth)
+
+
+def drqa_normalize(text):
+    return unicodedata.normalize('NFD', text)
+
+
+def drqa_exact_match_score(prediction, ground_truth):
+    return normalize_answer(prediction) == normalize_answer(ground_truth)
+
+
+def drqa_regex_match_score(prediction, pattern):
+    try:
+        compiled = re.compile(pattern, flags=re.IGNORECASE + re.UNICODE + re.MULTILINE)
+    except BaseException:
+        return False
+    return compiled.match(prediction) is not None
+
+
+def drqa_metric_max_over_ground_truths(metric_fn, prediction, ground_truths):
+    return max(metric_fn(prediction, gt) for gt in ground_truths)
+
+
+# ---- single_utils.load_encoder -------------------------------------------------------------------------------
+def load_encoder(device, args, phrase_only=False):
+    """-> (model, tokenizer, config).  `args.load_dir/pytorch_model.bin` (a reference checkpoint) is used when present;
+    otherwise seeded random weights (no checkpoint is reachable offline)."""
+    if phrase_only:
+        raise NotImplementedError('the phrase tower is only used offline (generate_phrase_vecs.py); out of scope')
+    load_dir = getattr(args, 'load_dir', '') or ''
+    config = BertGeometry()
+    cfg_json = os.path.join(load_dir, 'config.json')
+    if os.path.exists(cfg_json):
+        config = BertGeometry(**json.load(open(cfg_json)))
+    tokenizer = WordPieceTokenizer.from_pretrained_or_synthetic(load_dir, do_lower_case=getattr(args, 'do_lower_case', False),
+                                                               vocab_size=config.vocab_size)
+    ckpt = os.path.join(load_dir, 'pytorch_model.bin')
+    if os.path.exists(ckpt):
+        sd = torch.load(ckpt, map_location='cpu')
+        logger.info(f'DensePhrases encoder loaded from {load_dir}')
+    else:
+        sd = random_state_dict(config, getattr(args, 'seed', 42))
+        logger.info('DensePhrases query encoder initialised with seeded random weights (no checkpoint found)')
+    dev_index = torch.cuda.current_device() if str(device).startswith('cuda') else 0
+    model = Encoder(config, tokenizer=tokenizer, state_dict=sd, device=dev_index)
+    return model, tokenizer, config
+
+
+# ---- open_utils ------------------------------------------------------------------------------------------------
+def load_phrase_index(args, ignore_logging=False):
+    phrase_dump_dir = os.path.join(args.dump_dir, args.phrase_dir)
+    index_dir = os.path.join(args.dump_dir, args.index_name)
+    return MIPS(phrase_dump_dir=phrase_dump_dir, index_path=os.path.join(index_dir, args.index_path),
+                idx2id_path=os.path.join(index_dir, args.idx2id_path), cuda=args.cuda,
+                logging_level=logging.WARNING if ignore_logging else (logging.DEBUG if args.verbose_logging else logging.INFO))
+
+
+def get_query2vec(query_encoder, tokenizer, args, batch_size=64):
+    """-> query2vec(list[str]) -> list of (start_vec [1][768] list, end_vec [1][768] list, tokens) like open_utils.py:85-100."""
+    def query2vec(queries):
+        outs = []
+        for i in range(0, len(queries), batch_size):
+            feats = [tokenizer.encode_question(q, args.max_query_length) for q in queries[i:i + batch_size]]
+            ids, mask, tt = (torch.tensor([f[j] for f in feats], dtype=torch.int64) for j in range(3))
+            with torch.no_grad():
+                start, end = query_encoder(input_ids_=ids, attention_mask_=mask, token_type_ids_=tt, return_query=True)
+            start, end = start.cpu().numpy(), end.cpu().numpy()       # one device->host copy per batch (reference: one per row)
+            outs += [(start[j].tolist(), end[j].tolist(), feats[j][3]) for j in range(len(feats))]
+        return outs
+    return query2vec
+
+
+def load_qa_pairs(data_path, args, q_idx=None, draft_num_examples=100, shuffle=False):
+    q_ids, questions, answers, titles = [], [], [], []
+    for data_idx, item in enumerate(json.load(open(data_path))['data']):
+        if q_idx is not None and data_idx != q_idx:
+            continue
+        if len(item['answers']) == 0:
+            continue
+        q_id = item['id'] if 'origin' not in item else item['origin'].split('.')[0] + '-' + item['id']
+        question = item['question']
+        if '[START_ENT]' in question:
+            question = question[max(question.index('[START_ENT]') - 300, 0):question.index('[END_ENT]') + 300]
+        q_ids.append(q_id)
+        questions.append(question[:-1] if question.endswith('?') else question)
+        answers.append(item['answers'])
+        titles.append(item.get('titles', ['']))
+    if getattr(args, 'do_lower_case', False):
+        questions = [q.lower() for q in questions]
+    if shuffle:
+        pack = list(zip(q_ids, questions, answers, titles))
+        random.shuffle(pack)
+        q_ids, questions, answers, titles = map(list, zip(*pack))
+    if getattr(args, 'draft', False):
+        q_ids, questions, answers, titles = (x[:draft_num_examples] for x in (q_ids, questions, answers, titles))
+    # truecasing needs $DATA_DIR/truecase/english_with_questions.dist (options.py:83); the reference swallows its absence too
+    logger.info(f'Loading {len(questions)} questions from {data_path}')
+    return q_ids, questions, answers, titles
+
+
+# ---- eval_phrase_retrieval ---------------------------------------------------------------------------------------
+def embed_all_query(questions, args, query_encoder, tokenizer, batch_size=64):
+    query2vec = get_query2vec(query_encoder=query_encoder, tokenizer=tokenizer, args=args, batch_size=batch_size)
+    outs = []
+    for i in range(0, len(questions), batch_size):
+        outs += query2vec(questions[i:i + batch_size])
+    start = np.concatenate([o[0] for o in outs], 0)
+    end = np.concatenate([o[1] for o in outs], 0)
+    return np.concatenate([start, end], 1)
+
+
+def evaluate(args, mips=None, query_encoder=None, tokenizer=None, q_idx=None):
+    """The search loop of eval_phrase_retrieval.evaluate (:49-91) + EM/F1 at 1 and top_k."""
+    qids, questions, answers, _ = load_qa_pairs(args.test_path, args, q_idx)
+    if query_encoder is None:
+        query_encoder, tokenizer, _ = load_encoder('cuda' if args.cuda else 'cpu', args)
+    query_vec = embed_all_query(questions, args, query_encoder, tokenizer)
+    if mips is None:
+        mips = load_phrase_index(args)
+    step = args.eval_batch_size
+    predictions, scores = [], []
+    for i in range(0, len(questions), step):
+        result = mips.search(query_vec[i:i + step], q_texts=questions[i:i + step], nprobe=args.nprobe, top_k=args.top_k,
+                             max_answer_length=args.max_answer_length, aggregate=args.aggregate, agg_strat=args.agg_strat,
+                             return_sent=args.return_sent)
+        predictions += [[r['answer'] for r in out][:args.top_k] if len(out) > 0 else [''] for out in result]
+        scores += [[r['score'] for r in out][:args.top_k] if len(out) > 0 else [-1e10] for out in result]
+    em1 = np.mean([max(exact_match_score(p[0], a) for a in ans) for p, ans in zip(predictions, answers)])
+    f11 = np.mean([max(f1_score(p[0], a)[0] for a in ans) for p, ans in zip(predictions, answers)])
+    emk = np.mean([max(exact_match_score(pp, a) for pp in p for a in ans) for p, ans in zip(predictions, answers)])
+    f1k = np.mean([max(f1_score(pp, a)[0] for pp in p for a in ans) for p, ans in zip(predictions, answers)])
+    logger.info(f'exact_match_top1 {100*em1:.2f} f1_score_top1 {100*f11:.2f} | exact_match_top{args.top_k} {100*emk:.2f} f1 {100*f1k:.2f}')
+    return {'exact_match_top1': em1, 'f1_score_top1': f11, f'exact_match_top{args.top_k}': emk, f'f1_score_top{args.top_k}': f1k,
+            'predictions': predictions, 'scores': scores}
+
+
+# ---- model.DensePhrases ----------------------------------------------------------------------------------------------
+class DensePhrases(object):
+    _AGG = {'phrase': 'opt1', 'sentence': 'opt2', 'paragraph': 'opt2', 'document': 'opt3'}
+
+    def __init__(self, load_dir, dump_dir, index_name='start/1048576_flat_OPQ96', device='cuda', verbose=False, mips=None, **kwargs):
+        options = Options()
+        options.add_model_options(); options.add_index_options(); options.add_retrieval_options(); options.add_data_options()
+        self.args = options.parse([])            # the reference parses the live sys.argv here (model.py:30-35); we do not
+        self.args.load_dir, self.args.dump_dir, self.args.index_name = load_dir, dump_dir, index_name
+        self.args.cache_dir = os.environ.get('CACHE_DIR', '')
+        self.args.cuda = device == 'cuda'
+        self.args.__dict__.update(kwargs)
+        self.set_encoder(load_dir, device)
+        self.mips = mips if mips is not None else load_phrase_index(self.args, ignore_logging=not verbose)
+        self.truecase = None                     # TrueCaser needs $DATA_DIR/truecase/*.dist, absent offline (model.py:52)
+
+    def set_encoder(self, load_dir, device='cuda'):
+        self.args.load_dir = load_dir
+        self.model, self.tokenizer, self.config = load_encoder(device, self.args)
+        self.query2vec = get_query2vec(query_encoder=self.model, tokenizer=self.tokenizer, args=self.args, batch_size=64)
+
+    def search(self, query='', retrieval_unit='phrase', top_k=10, truecase=True, return_meta=False):
+        single = isinstance(query, str)
+        batch_query = [query] if single else query
+        assert isinstance(batch_query, list)
+        if retrieval_unit not in self._AGG:
+            raise NotImplementedError(f'"{retrieval_unit}" not supported. Choose one of {self._AGG.keys()}.')
+        outs = self.query2vec(batch_query)
+        query_vec = np.concatenate([np.concatenate([o[0] for o in outs], 0), np.concatenate([o[1] for o in outs], 0)], 1)
+        search_top_k = top_k * 2 if retrieval_unit in ('sentence', 'paragraph', 'document') else top_k
+        rets = self.mips.search(query_vec, q_texts=batch_query, nprobe=256, top_k=search_top_k, max_answer_length=10, return_idxs=False,
+                                aggregate=True, agg_strat=self._AGG[retrieval_unit], return_sent=retrieval_unit == 'sentence')
+        rets = [ret[:top_k] for ret in rets]
+        field = {'phrase': lambda r: r['answer'], 'sentence': lambda r: r['context'], 'paragraph': lambda r: r['context'],
+                 'document': lambda r: r['title'][0]}[retrieval_unit]
+        retrieved = [[field(r) for r in ret][:top_k] for ret in rets]
+        if single:
+            rets, retrieved = rets[0], retrieved[0]
+        return (retrieved, rets) if return_meta else retrieved

@@ -1,0 +1,95 @@
+"""WordPiece tokenisation of questions into the `[CLS] q [SEP] [PAD]...` features the query towers consume
+(reference: squad_utils.py question-only path :117-141,401-431,594-608 via HF BertTokenizer.encode_plus, padded to
+max_query_length, token_type_ids all 0).  CPU work, kept (not accelerated), written from the published BERT algorithm:
+whitespace+punctuation basic tokenisation, then greedy longest-match-first WordPiece.
+No vocabulary file is reachable offline; `WordPieceTokenizer.from_pretrained_or_synthetic` loads `vocab.txt` when a
+directory has one and otherwise builds a deterministic synthetic cased vocabulary of the SpanBERT size (28 996)."""
+import os
+import unicodedata
+
+PAD, UNK, CLS, SEP, MASK = '[PAD]', '[UNK]', '[CLS]', '[SEP]', '[MASK]'
+_SPECIAL_IDS = {PAD: 0, UNK: 100, CLS: 101, SEP: 102, MASK: 103}
+
+
+def _is_punct(ch):
+    cp = ord(ch)
+    if (33 <= cp <= 47) or (58 <= cp <= 64) or (91 <= cp <= 96) or (123 <= cp <= 126):
+        return True
+    return unicodedata.category(ch).startswith('P')
+
+
+def basic_tokenize(text, do_lower_case=False):
+    out = []
+    for tok in text.strip().split():
+        if do_lower_case:
+            tok = ''.join(c for c in unicodedata.normalize('NFD', tok.lower()) if unicodedata.category(c) != 'Mn')
+        cur = ''
+        for ch in tok:
+            if _is_punct(ch):
+                if cur:
+                    out.append(cur)
+                    cur = ''
+                out.append(ch)
+            else:
+                cur += ch
+        if cur:
+            out.append(cur)
+    return out
+
+
+class WordPieceTokenizer(object):
+    def __init__(self, vocab, do_lower_case=False, max_chars=100):
+        self.vocab = vocab
+        self.ids_to_tokens = {i: t for t, i in vocab.items()}
+        self.do_lower_case = do_lower_case
+        self.max_chars = max_chars
+        self.pad_token_id, self.unk_token_id = vocab[PAD], vocab[UNK]
+        self.cls_token_id, self.sep_token_id = vocab[CLS], vocab[SEP]
+
+    @classmethod
+    def from_pretrained_or_synthetic(cls, path=None, do_lower_case=False, vocab_size=28996, extra_words=()):
+        vocab_file = os.path.join(path, 'vocab.txt') if path and os.path.isdir(path) else None
+        if vocab_file and os.path.exists(vocab_file):
+            vocab = {line.rstrip('\n'): i for i, line in enumerate(open(vocab_file, encoding='utf-8'))}
+            return cls(vocab, do_lower_case)
+        vocab = {f'[unused{i}]': i for i in range(vocab_size)}          # placeholder rows, overwritten below
+        vocab = {}
+        for tok, i in _SPECIAL_IDS.items():
+            vocab[tok] = i
+        nxt = 104
+        chars = [chr(c) for c in range(33, 127)]
+        for piece in chars + ['##' + c for c in chars] + sorted(set(extra_words)):
+            while nxt in _SPECIAL_IDS.values():
+                nxt += 1
+            if piece not in vocab and nxt < vocab_size:
+                vocab[piece] = nxt
+                nxt += 1
+        return cls(vocab, do_lower_case)
+
+    def wordpiece(self, word):
+        if len(word) > self.max_chars:
+            return [UNK]
+        pieces, start = [], 0
+        while start < len(word):
+            end, cur = len(word), None
+            while start < end:
+                sub = word[start:end] if start == 0 else '##' + word[start:end]
+                if sub in self.vocab:
+                    cur = sub
+                    break
+                end -= 1
+            if cur is None:
+                return [UNK]
+            pieces.append(cur)
+            start = end
+        return pieces
+
+    def tokenize(self, text):
+        return [p for w in basic_tokenize(text, self.do_lower_case) for p in self.wordpiece(w)]
+
+    def encode_question(self, text, max_query_length=64):
+        """-> (input_ids, attention_mask, token_type_ids, tokens): [CLS] + pieces (truncated) + [SEP], zero padded."""
+        toks = [CLS] + self.tokenize(text)[:max_query_length - 2] + [SEP]
+        ids = [self.vocab.get(t, self.unk_token_id) for t in toks]
+        pad = max_query_length - len(ids)
+        return ids + [self.pad_token_id] * pad, [1] * len(ids) + [0] * pad, [0] * max_query_length, toks

@@ -1,0 +1,92 @@
+"""Drop-in surface: the `densephrases` facade, Options flags, tokenizer, QA loader, metrics;
+on the GPU: DensePhrases.search() and the evaluate() loop end to end over a synthetic corpus."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+
+def test_reference_eval_script_imports_against_facade():
+    ref = "/root/reference/eval_phrase_retrieval.py"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not present (GPU box)")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_eval_phrase_retrieval", ref)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)                       # executes its `import faiss`, `from densephrases... import ...` lines (:12,:19-25)
+    assert callable(mod.evaluate) and callable(mod.embed_all_query)
+    import faiss
+    with pytest.raises(RuntimeError):
+        faiss.read_index
+
+
+def test_options_defaults_match_reference():
+    from densephrases import Options
+    o = Options()
+    o.add_model_options(); o.add_index_options(); o.add_retrieval_options(); o.add_data_options()
+    a = o.parse([])
+    assert (a.top_k, a.nprobe, a.eval_batch_size, a.max_query_length, a.max_answer_length) == (10, 256, 64, 64, 10)   # options.py:150-160,38,41
+    assert (a.phrase_dir, a.index_path, a.idx2id_path, a.agg_strat, a.cuda) == ("phrase", "index.faiss", "idx2id.hdf5", "opt1", False)
+    b = o.parse(["--cuda", "--top_k", "40", "--aggregate", "--index_name", "start/1048576_flat_OPQ96", "--unknown_flag", "1"])
+    assert b.cuda and b.top_k == 40 and b.aggregate and b.index_name.endswith("OPQ96")
+
+
+def test_tokenizer_question_features():
+    from densephrases_b200.tokenization import WordPieceTokenizer
+    t = WordPieceTokenizer.from_pretrained_or_synthetic(None, extra_words=["river", "##s"])
+    ids, mask, tt, toks = t.encode_question("Which rivers?", 12)
+    assert toks[0] == "[CLS]" and toks[-1] == "[SEP]" and "river" in toks and "##s" in toks and "?" in toks
+    assert len(ids) == len(mask) == len(tt) == 12 and ids[0] == 101 and sum(mask) == len(toks) and set(tt) == {0}
+    long_ids, long_mask, _, long_toks = t.encode_question("a " * 100, 8)
+    assert len(long_ids) == 8 and sum(long_mask) == 8 and long_toks[-1] == "[SEP]"          # truncated to max_query_length
+    assert t.wordpiece("中") == ["[UNK]"]
+
+
+def test_load_qa_pairs_and_metrics(tmp_path):
+    from densephrases_b200.runtime import exact_match_score, f1_score, load_qa_pairs, normalize_answer
+
+    class A:
+        do_lower_case = False; draft = False; truecase = False
+    p = tmp_path / "qa.json"
+    json.dump({"data": [{"id": "1", "question": "Who wrote it?", "answers": ["The Author"]}, {"id": "2", "question": "none", "answers": []},
+                        {"id": "3", "origin": "nq.x", "question": "When", "answers": ["1999"], "titles": ["T"]}]}, open(p, "w"))
+    ids, qs, ans, titles = load_qa_pairs(str(p), A())
+    assert ids == ["1", "nq-3"] and qs == ["Who wrote it", "When"] and titles == [[""], ["T"]]
+    assert normalize_answer("The  Author!") == "author" and exact_match_score("the author", "Author")
+    assert f1_score("big red dog", "red dog")[0] == pytest.approx(0.8)
+
+
+@pytest.mark.gpu
+def test_densephrases_search_and_evaluate_end_to_end(oracle, tmp_path):
+    from densephrases import DensePhrases
+    from densephrases_b200 import IvfPqIndex
+    from densephrases_b200.mips import MIPS
+    from densephrases_b200.runtime import evaluate
+    from densephrases_b200.synthetic import make_corpus, make_phrase_index_arrays
+    from tests.helpers import opq_matrix
+    doc_groups, idx_f, ntotal = make_corpus(30, 5)
+    list_len, codes, ids = make_phrase_index_arrays(ntotal, 32, 5)
+    index = IvfPqIndex.from_arrays(opq_matrix(5), oracle.gen_centroids(5, 0, 32), oracle.gen_pq(5), list_len, codes, ids)
+    mips = MIPS.from_components(index, idx_f, doc_groups, cuda=True)
+    model = DensePhrases(load_dir="", dump_dir="unused", mips=mips)
+    qs = ["which river crosses the city", "Who signed the treaty?", "museum of the island"]
+    single = model.search(qs[0], retrieval_unit="phrase", top_k=5)
+    batch, meta = model.search(qs, retrieval_unit="phrase", top_k=5, return_meta=True)
+    assert isinstance(single, list) and single == batch[0] and len(batch) == 3
+    for rets in meta:
+        assert 0 < len(rets) <= 5 and all(r["context"][r["start_pos"]:r["end_pos"]] == r["answer"] for r in rets)
+        assert [r["score"] for r in rets] == sorted((r["score"] for r in rets), reverse=True)
+    assert all(isinstance(t, str) for t in model.search(qs, retrieval_unit="document", top_k=3)[0])
+    sents = model.search(qs, retrieval_unit="sentence", top_k=3)
+    assert all(len(s) <= 3 for s in sents)
+    # query2vec contract (open_utils.py:94-100): python lists [1][768] + tokens
+    out = model.query2vec(qs[:2])
+    assert len(out) == 2 and len(out[0][0]) == 1 and len(out[0][0][0]) == 768 and out[0][2][0] == "[CLS]"
+    # evaluate loop
+    p = tmp_path / "test.json"
+    json.dump({"data": [{"id": str(i), "question": q, "answers": [meta[i][0]["answer"]]} for i, q in enumerate(qs)]}, open(p, "w"))
+    args = model.args
+    args.test_path, args.top_k, args.aggregate = str(p), 5, True
+    res = evaluate(args, mips=mips, query_encoder=model.model, tokenizer=model.tokenizer)
+    assert res["exact_match_top1"] == 1.0 and res["exact_match_top5"] == 1.0
