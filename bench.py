@@ -301,6 +301,41 @@ def run_ours(args):
         cpu = {"value": nq / dt, "unit": "queries/s", "cores": oracle.lib().ref_num_threads(), "kind": "port",
                "sample": f"{nq} queries of the last timed batch, full nprobe={wl['nprobe']} scan, {note}; GPU results bit-identical: {same}"}
 
+    # ---- C3: query encoder (2 x SpanBERT-base towers, random-init weights, synthetic tokens) + search, device resident ----
+    enc_info = None
+    if rank == 0 and world == 1 and not args.no_encoder:
+        from densephrases_b200.encoder import BertGeometry, Encoder, random_state_dict, synthetic_query_batch
+        geo = BertGeometry()
+        enc = Encoder(geo, state_dict=random_state_dict(geo, 1), device=local_rank)
+        ids, mask, tt = (t.to(dev) for t in synthetic_query_batch(64, 64, geo.vocab_size, 2))
+        enc_info = {}
+        for mode in ("tf32", "3xtf32"):
+            enc.set_precision(mode == "3xtf32")
+            for _ in range(3):
+                enc.embed_query(ids, mask, tt)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(10):
+                qs, qe = enc.embed_query(ids, mask, tt)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            flops = 64 * 22.05e9
+            enc_info[mode] = {"ms_per_64_questions": ms, "questions_per_s": 64000.0 / ms, "tensor_tflops": flops / ms / 1e9,
+                              "frac_of_tf32_peak": flops / ms / 1e9 / (pk["bf16_tflops"] / 2.0) / (3.0 if mode == "3xtf32" else 1.0) * (3.0 if mode == "3xtf32" else 1.0)}
+        # end to end: 64 questions -> encoder (tf32) -> [128,768] search
+        enc.set_precision(False)
+        e0.record()
+        for _ in range(5):
+            qs, qe = enc.embed_query(ids, mask, tt)
+            ix.search_device(torch.cat([qs[:, 0], qe[:, 0]], 0).contiguous()[:64], k)
+            ix.search_device(torch.cat([qs[:, 0], qe[:, 0]], 0).contiguous()[64:], k)
+        e1.record()
+        torch.cuda.synchronize()
+        enc_info["c3_questions_per_s"] = 64 * 5 / (e0.elapsed_time(e1) / 1000.0)
+        enc_info["note"] = "B=64,S=64; 22.05 GFLOP/question over both towers; GEMMs on tcgen05 kind::tf32 (peak taken as half the measured bf16 peak)"
+        del enc
+
     if rank == 0:
         B = wl["batch"]
         line = {"metric": "queries/sec top-10 over PQ96 phrase index", "value": B * K / (ms_dev / 1000.0), "unit": "queries/s", "n_gpus": world,
@@ -309,7 +344,7 @@ def run_ours(args):
                 "e2e": {"value": B * K / (ms_e2e / 1000.0), "unit": "queries/s", "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * k * 12,
                         "ms_per_step": ms_e2e / K},
                 "gpu_launches": K * (12 + (1 if world > 1 else 0)), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-                "exact_fallback_queries_last_batch": flags}
+                "exact_fallback_queries_last_batch": flags, "encoder": enc_info}
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
@@ -325,6 +360,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="debug only: shrink the per-GPU index (the headline run uses 1.0)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-encoder", action="store_true", help="skip the C3 encoder leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     return run_reference(args) if args.impl == "reference" else run_ours(args)

@@ -14,7 +14,8 @@
 #define ENC_MAX_S 384          // Makefile:357-375 uses max_query_length 384 for KILT; attention keeps K,V of one head in smem
 
 int dph_launch_gemm_tf32(int group, const float* const* A, const float* const* W, const float* const* bias, const float* const* residual,
-                         float* const* out, int M, int N, int K, int act, cudaStream_t st);
+                         float* const* out, int M, int N, int K, int act, cudaStream_t st, const float* const* A_lo, const float* const* W_lo);
+int dph_launch_split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t st);
 
 struct LayerW { const float *Wqkv, *bqkv, *Wo, *bo, *ln1g, *ln1b, *Wi, *bi, *Wo2, *bo2, *ln2g, *ln2b; };
 struct TowerW { const float *word, *pos, *type, *embg, *embb; LayerW L[ENC_LAYERS]; };
@@ -24,6 +25,10 @@ struct dph_encoder {
     cudaStream_t stream = 0;
     float* blob[2] = {nullptr, nullptr};
     TowerW tw[2];
+    // 3xTF32 mode: (hi, lo) copies of the four GEMM weight matrices of every layer, made lazily on the first precise forward
+    int precise = 0;
+    float* wsplit[2] = {nullptr, nullptr};       // per tower: for each layer [Wqkv_hi, Wqkv_lo, Wo_hi, Wo_lo, Wi_hi, Wi_lo, Wo2_hi, Wo2_lo]
+    float *act_hi[2] = {}, *act_lo[2] = {};      // split copy of the current GEMM input activation (up to T x 3072)
     // workspace for T tokens
     int64_t cap_tokens = 0;
     float *x[2] = {}, *qkv[2] = {}, *ctx[2] = {}, *a[2] = {}, *ffn[2] = {};
@@ -189,7 +194,7 @@ DPH_API void dph_encoder_free(dph_encoder* e) {
     cudaSetDevice(e->device);
     for (int t = 0; t < 2; t++) {
         if (e->blob[t]) cudaFree(e->blob[t]);
-        float* ws[] = {e->x[t], e->qkv[t], e->ctx[t], e->a[t], e->ffn[t]};
+        float* ws[] = {e->x[t], e->qkv[t], e->ctx[t], e->a[t], e->ffn[t], e->wsplit[t], e->act_hi[t], e->act_lo[t]};
         for (float* p : ws) if (p) cudaFree(p);
     }
     void* misc[] = {e->ids, e->mask, e->tt, e->out_s, e->out_e};
@@ -197,6 +202,28 @@ DPH_API void dph_encoder_free(dph_encoder* e) {
     delete e;
 }
 DPH_API int dph_encoder_set_stream(dph_encoder* e, void* s) { e->stream = (cudaStream_t)s; return 0; }
+DPH_API int dph_encoder_set_precision(dph_encoder* e, int precise) { e->precise = precise ? 1 : 0; return 0; }
+
+static const int64_t kGemmW[4] = {(int64_t)3 * ENC_H * ENC_H, (int64_t)ENC_H * ENC_H, (int64_t)ENC_FF * ENC_H, (int64_t)ENC_H * ENC_FF};
+static int64_t split_layer_floats() { return 2 * (kGemmW[0] + kGemmW[1] + kGemmW[2] + kGemmW[3]); }
+static int ensure_split_weights(dph_encoder* e) {
+    for (int t = 0; t < 2; t++) {
+        if (e->wsplit[t]) continue;
+        DPH_CUDA(cudaMalloc((void**)&e->wsplit[t], (size_t)split_layer_floats() * ENC_LAYERS * 4));
+        for (int l = 0; l < ENC_LAYERS; l++) {
+            const LayerW& L = e->tw[t].L[l];
+            const float* src[4] = {L.Wqkv, L.Wo, L.Wi, L.Wo2};
+            float* p = e->wsplit[t] + (size_t)l * split_layer_floats();
+            for (int m = 0; m < 4; m++) { DPH_TRY(dph_launch_split_tf32(src[m], p, p + kGemmW[m], kGemmW[m], e->stream)); p += 2 * kGemmW[m]; }
+        }
+    }
+    return 0;
+}
+static void split_ptrs(const dph_encoder* e, int t, int l, int m, const float** hi, const float** lo) {
+    const float* p = e->wsplit[t] + (size_t)l * split_layer_floats();
+    for (int i = 0; i < m; i++) p += 2 * kGemmW[i];
+    *hi = p; *lo = p + kGemmW[m];
+}
 DPH_API int64_t dph_encoder_tower_floats(const dph_encoder* e) { return tower_floats(e); }
 // blob layout (fp32, all nn.Linear weights as stored by torch: [out_features, in_features]):
 //   word_embeddings [V,768] | position_embeddings [P,768] | token_type_embeddings [T,768] | embeddings.LayerNorm weight, bias |
@@ -209,6 +236,7 @@ DPH_API int dph_encoder_load_tower(dph_encoder* e, int tower, const float* blob,
     if (!e->blob[tower]) DPH_CUDA(cudaMalloc((void**)&e->blob[tower], bytes));
     DPH_CUDA(cudaMemcpy(e->blob[tower], blob, bytes, mem == DPH_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice));
     carve(e, tower);
+    if (e->wsplit[tower]) { cudaFree(e->wsplit[tower]); e->wsplit[tower] = nullptr; }
     return 0;
 }
 static int ensure_ws(dph_encoder* e, int64_t T, int64_t B) {
@@ -217,6 +245,10 @@ static int ensure_ws(dph_encoder* e, int64_t T, int64_t B) {
             float** ps[] = {&e->x[t], &e->qkv[t], &e->ctx[t], &e->a[t], &e->ffn[t]};
             size_t sz[] = {(size_t)T * ENC_H, (size_t)T * 3 * ENC_H, (size_t)T * ENC_H, (size_t)T * ENC_H, (size_t)T * ENC_FF};
             for (int i = 0; i < 5; i++) { if (*ps[i]) cudaFree(*ps[i]); DPH_CUDA(cudaMalloc((void**)ps[i], sz[i] * 4)); }
+            if (e->act_hi[t]) cudaFree(e->act_hi[t]);
+            if (e->act_lo[t]) cudaFree(e->act_lo[t]);
+            DPH_CUDA(cudaMalloc((void**)&e->act_hi[t], (size_t)T * ENC_FF * 4));
+            DPH_CUDA(cudaMalloc((void**)&e->act_lo[t], (size_t)T * ENC_FF * 4));
         }
         long long** ip[] = {&e->ids, &e->mask, &e->tt};
         for (auto p : ip) { if (*p) cudaFree(*p); DPH_CUDA(cudaMalloc((void**)p, (size_t)T * 8)); }
@@ -260,30 +292,44 @@ DPH_API int dph_encoder_embed_query(dph_encoder* e, const int64_t* ids, const in
     const size_t attn_smem = ((size_t)S * 65 + (size_t)S * 64 + S + attn_warps * 64 + (size_t)attn_warps * S) * 4;
     static bool attr = false;
     if (!attr) { DPH_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+    if (e->precise) DPH_TRY(ensure_split_weights(e));
+    // one grouped (two-tower) linear layer: out = act(in . W^T + b) + residual; m = which weight of the layer (0 qkv, 1 attn out, 2 ffn in, 3 ffn out)
+    auto linear = [&](int l, int m, float* const in[2], const float* const bias[2], float* const resid[2], float* const out[2], int N, int K, int act) -> int {
+        const LayerW &L0 = e->tw[0].L[l], &L1 = e->tw[1].L[l];
+        const float* Wfull[2];
+        switch (m) { case 0: Wfull[0] = L0.Wqkv; Wfull[1] = L1.Wqkv; break; case 1: Wfull[0] = L0.Wo; Wfull[1] = L1.Wo; break;
+                     case 2: Wfull[0] = L0.Wi; Wfull[1] = L1.Wi; break; default: Wfull[0] = L0.Wo2; Wfull[1] = L1.Wo2; }
+        const float* R[2] = {resid ? resid[0] : nullptr, resid ? resid[1] : nullptr};
+        if (!e->precise) {
+            const float* A[2] = {in[0], in[1]};
+            return dph_launch_gemm_tf32(2, A, Wfull, bias, resid ? R : nullptr, out, (int)T, N, K, act, st, nullptr, nullptr);
+        }
+        const float *Whi[2], *Wlo[2];
+        for (int t = 0; t < 2; t++) {
+            split_ptrs(e, t, l, m, &Whi[t], &Wlo[t]);
+            DPH_TRY(dph_launch_split_tf32(in[t], e->act_hi[t], e->act_lo[t], (long long)T * K, st));
+        }
+        const float* Ahi[2] = {e->act_hi[0], e->act_hi[1]}; const float* Alo[2] = {e->act_lo[0], e->act_lo[1]};
+        return dph_launch_gemm_tf32(2, Ahi, Whi, bias, resid ? R : nullptr, out, (int)T, N, K, act, st, Alo, Wlo);
+    };
     for (int l = 0; l < ENC_LAYERS; l++) {
         const LayerW &L0 = e->tw[0].L[l], &L1 = e->tw[1].L[l];
-        const float* X[2] = {e->x[0], e->x[1]};
+        float* X[2] = {e->x[0], e->x[1]};
         float* QKV[2] = {e->qkv[0], e->qkv[1]};
-        const float* Wqkv[2] = {L0.Wqkv, L1.Wqkv}; const float* bqkv[2] = {L0.bqkv, L1.bqkv};
-        DPH_TRY(dph_launch_gemm_tf32(2, X, Wqkv, bqkv, nullptr, QKV, (int)T, 3 * ENC_H, ENC_H, 0, st));
+        float* CTX[2] = {e->ctx[0], e->ctx[1]};
+        float* A2[2] = {e->a[0], e->a[1]};
+        float* FF[2] = {e->ffn[0], e->ffn[1]};
+        const float* bqkv[2] = {L0.bqkv, L1.bqkv}; const float* bo[2] = {L0.bo, L1.bo}; const float* bi[2] = {L0.bi, L1.bi}; const float* bo2[2] = {L0.bo2, L1.bo2};
+        DPH_TRY(linear(l, 0, X, bqkv, nullptr, QKV, 3 * ENC_H, ENC_H, 0));
         AttnArgs aa; aa.qkv[0] = e->qkv[0]; aa.qkv[1] = e->qkv[1]; aa.ctx[0] = e->ctx[0]; aa.ctx[1] = e->ctx[1]; aa.mask = d_mask; aa.S = S;
         attention_kernel<<<dim3(ENC_HEADS, (unsigned)B, 2), attn_warps * 32, attn_smem, st>>>(aa);
         DPH_CUDA(cudaGetLastError());
-        const float* CTX[2] = {e->ctx[0], e->ctx[1]};
-        float* Aout[2] = {e->a[0], e->a[1]};
-        const float* Wo[2] = {L0.Wo, L1.Wo}; const float* bo[2] = {L0.bo, L1.bo};
-        DPH_TRY(dph_launch_gemm_tf32(2, CTX, Wo, bo, X, Aout, (int)T, ENC_H, ENC_H, 0, st));            // dense + residual
+        DPH_TRY(linear(l, 1, CTX, bo, X, A2, ENC_H, ENC_H, 0));                                         // dense + residual
         LnArgs ln1; for (int t = 0; t < 2; t++) { ln1.in[t] = e->a[t]; ln1.out[t] = e->a[t]; } ln1.g[0] = L0.ln1g; ln1.g[1] = L1.ln1g; ln1.b[0] = L0.ln1b; ln1.b[1] = L1.ln1b;
         layernorm_kernel<<<dim3((unsigned)T, 2), 256, 0, st>>>(ln1);
         DPH_CUDA(cudaGetLastError());
-        const float* Ain[2] = {e->a[0], e->a[1]};
-        float* FF[2] = {e->ffn[0], e->ffn[1]};
-        const float* Wi[2] = {L0.Wi, L1.Wi}; const float* bi[2] = {L0.bi, L1.bi};
-        DPH_TRY(dph_launch_gemm_tf32(2, Ain, Wi, bi, nullptr, FF, (int)T, ENC_FF, ENC_H, 1, st));        // intermediate + erf-GELU
-        const float* FFin[2] = {e->ffn[0], e->ffn[1]};
-        float* Xout[2] = {e->x[0], e->x[1]};
-        const float* Wo2[2] = {L0.Wo2, L1.Wo2}; const float* bo2[2] = {L0.bo2, L1.bo2};
-        DPH_TRY(dph_launch_gemm_tf32(2, FFin, Wo2, bo2, Ain, Xout, (int)T, ENC_H, ENC_FF, 0, st));       // output dense + residual
+        DPH_TRY(linear(l, 2, A2, bi, nullptr, FF, ENC_FF, ENC_H, 1));                                    // intermediate + erf-GELU
+        DPH_TRY(linear(l, 3, FF, bo2, A2, X, ENC_H, ENC_FF, 0));                                         // output dense + residual
         LnArgs ln2; for (int t = 0; t < 2; t++) { ln2.in[t] = e->x[t]; ln2.out[t] = e->x[t]; } ln2.g[0] = L0.ln2g; ln2.g[1] = L1.ln2g; ln2.b[0] = L0.ln2b; ln2.b[1] = L1.ln2b;
         layernorm_kernel<<<dim3((unsigned)T, 2), 256, 0, st>>>(ln2);
         DPH_CUDA(cudaGetLastError());

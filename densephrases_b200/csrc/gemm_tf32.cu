@@ -18,11 +18,12 @@
 #define GM_BN 128
 #define GM_BK 32                   // fp32 elements = 128 bytes = one SWIZZLE_128B row
 #define GM_STAGES 3
-#define GM_STAGE_BYTES ((GM_BM + GM_BN) * GM_BK * 4)       // 32768
-#define GM_SMEM_BYTES (GM_STAGES * GM_STAGE_BYTES + 1024)
+#define GM_TILE_BYTES (GM_BM * GM_BK * 4)                   // 16384 (BM == BN)
 #define GM_MAX_GROUP 2
 
-struct GemmMaps { CUtensorMap a[GM_MAX_GROUP]; CUtensorMap b[GM_MAX_GROUP]; };
+// SPLIT = 1 ("3xTF32", fp32-accurate): every operand arrives as an exact-TF32 pair (hi, lo) with x ~= hi + lo, and the
+// kernel accumulates hi.hi + hi.lo + lo.hi in the same fp32 TMEM accumulator (the dropped lo.lo term is ~2^-22 relative).
+struct GemmMaps { CUtensorMap a[GM_MAX_GROUP]; CUtensorMap b[GM_MAX_GROUP]; CUtensorMap a_lo[GM_MAX_GROUP]; CUtensorMap b_lo[GM_MAX_GROUP]; };
 struct GemmArgs {
     const float* bias[GM_MAX_GROUP]; const float* residual[GM_MAX_GROUP]; float* out[GM_MAX_GROUP];
     int M, N, K, act;     // act: 0 none, 1 erf-GELU
@@ -67,7 +68,9 @@ __device__ __forceinline__ unsigned long long make_sw128_desc(unsigned smem_addr
     return d;
 }
 
-__global__ void __launch_bounds__(256, 2) gemm_tf32_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
+template <int SPLIT>
+__global__ void __launch_bounds__(256, SPLIT ? 1 : 2) gemm_tf32_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
+    constexpr int GM_STAGE_BYTES = (SPLIT ? 4 : 2) * GM_TILE_BYTES;
     extern __shared__ __align__(1024) unsigned char gsm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.z, m_blk = blockIdx.y, n_blk = blockIdx.x;
@@ -107,7 +110,11 @@ __global__ void __launch_bounds__(256, 2) gemm_tf32_kernel(const __grid_constant
                 mbar_expect_tx(full0 + 8 * s, GM_STAGE_BYTES);
                 const unsigned dst = stage0 + s * GM_STAGE_BYTES;
                 tma_load_2d(dst, map_a, kb * GM_BK, m_blk * GM_BM, full0 + 8 * s);
-                tma_load_2d(dst + GM_BM * GM_BK * 4, map_b, kb * GM_BK, n_blk * GM_BN, full0 + 8 * s);
+                tma_load_2d(dst + GM_TILE_BYTES, map_b, kb * GM_BK, n_blk * GM_BN, full0 + 8 * s);
+                if (SPLIT) {
+                    tma_load_2d(dst + 2 * GM_TILE_BYTES, &maps.a_lo[g], kb * GM_BK, m_blk * GM_BM, full0 + 8 * s);
+                    tma_load_2d(dst + 3 * GM_TILE_BYTES, &maps.b_lo[g], kb * GM_BK, n_blk * GM_BN, full0 + 8 * s);
+                }
             }
         }
     } else if (warp == 1) {
@@ -119,11 +126,20 @@ __global__ void __launch_bounds__(256, 2) gemm_tf32_kernel(const __grid_constant
             mbar_wait(full0 + 8 * s, ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
-                const unsigned a_addr = stage0 + s * GM_STAGE_BYTES, b_addr = a_addr + GM_BM * GM_BK * 4;
+                const unsigned a_addr = stage0 + s * GM_STAGE_BYTES, b_addr = a_addr + GM_TILE_BYTES;
                 const unsigned long long adesc = make_sw128_desc(a_addr), bdesc = make_sw128_desc(b_addr);
+                const unsigned long long alo = make_sw128_desc(a_addr + 2 * GM_TILE_BYTES), blo = make_sw128_desc(a_addr + 3 * GM_TILE_BYTES);
 #pragma unroll
-                for (int k = 0; k < GM_BK / 8; k++)         // UMMA_K = 8 tf32 = 32 bytes: advance the start address inside the swizzle atom
-                    umma_tf32(tmem_base, adesc + (unsigned long long)(k * 2), bdesc + (unsigned long long)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                for (int k = 0; k < GM_BK / 8; k++) {       // UMMA_K = 8 tf32 = 32 bytes: advance the start address inside the swizzle atom
+                    const unsigned long long ko = (unsigned long long)(k * 2);
+                    if (SPLIT) {                             // small cross terms first, then the hi.hi term
+                        umma_tf32(tmem_base, adesc + ko, blo + ko, idesc, (kb | k) ? 1u : 0u);
+                        umma_tf32(tmem_base, alo + ko, bdesc + ko, idesc, 1u);
+                        umma_tf32(tmem_base, adesc + ko, bdesc + ko, idesc, 1u);
+                    } else {
+                        umma_tf32(tmem_base, adesc + ko, bdesc + ko, idesc, (kb | k) ? 1u : 0u);
+                    }
+                }
                 umma_commit(empty0 + 8 * s);                 // frees the stage once these MMAs have read it
                 if (kb == num_k - 1) umma_commit(tmem_full); // accumulator complete
             }
@@ -203,34 +219,86 @@ static int make_map(CUtensorMap* map, const float* ptr, long long rows, int K) {
     return 0;
 }
 
+// x -> (hi, lo): hi = round-to-nearest TF32 of x, lo = round-to-nearest TF32 of (x - hi)  (both exact TF32 values)
+__global__ void split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo, long long n4) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = x[i];
+    float4 h, l;
+    const float* pv = &v.x; float* ph = &h.x; float* pl = &l.x;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        unsigned hb, lb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(pv[e]));
+        const float hf = __uint_as_float(hb);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(pv[e] - hf));
+        ph[e] = hf; pl[e] = __uint_as_float(lb);
+    }
+    hi[i] = h; lo[i] = l;
+}
+int dph_launch_split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t st) {
+    DPH_CHECK(n % 4 == 0, "split_tf32: n must be a multiple of 4");
+    if (n == 0) return 0;
+    split_tf32_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>((const float4*)x, (float4*)hi, (float4*)lo, n / 4);
+    DPH_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // Grouped launch used by the encoder: problems share M, N, K and the epilogue; pointers are device pointers.
+// A_lo / W_lo non-null -> 3xTF32 mode (A, W are then the hi parts).
 int dph_launch_gemm_tf32(int group, const float* const* A, const float* const* W, const float* const* bias, const float* const* residual,
-                         float* const* out, int M, int N, int K, int act, cudaStream_t st) {
+                         float* const* out, int M, int N, int K, int act, cudaStream_t st, const float* const* A_lo, const float* const* W_lo) {
     DPH_CHECK(group >= 1 && group <= GM_MAX_GROUP, "gemm group size");
     DPH_CHECK(N % GM_BN == 0 && K % GM_BK == 0 && M >= 1, "gemm_tf32 needs N % 128 == 0 and K % 32 == 0");
     DPH_TRY(get_encode());
+    const bool split = A_lo != nullptr && W_lo != nullptr;
+    const int smem_fast = GM_STAGES * 2 * GM_TILE_BYTES + 1024, smem_split = GM_STAGES * 4 * GM_TILE_BYTES + 1024;
     static bool attr = false;
-    if (!attr) { DPH_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_BYTES)); attr = true; }
+    if (!attr) {
+        DPH_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fast));
+        DPH_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_split));
+        attr = true;
+    }
     GemmMaps maps;
     GemmArgs args;
     for (int g = 0; g < GM_MAX_GROUP; g++) {
         int s = g < group ? g : 0;
         DPH_TRY(make_map(&maps.a[g], A[s], M, K));
         DPH_TRY(make_map(&maps.b[g], W[s], N, K));
+        DPH_TRY(make_map(&maps.a_lo[g], split ? A_lo[s] : A[s], M, K));
+        DPH_TRY(make_map(&maps.b_lo[g], split ? W_lo[s] : W[s], N, K));
         args.bias[g] = bias ? bias[s] : nullptr;
         args.residual[g] = residual ? residual[s] : nullptr;
         args.out[g] = out[s];
     }
     args.M = M; args.N = N; args.K = K; args.act = act;
     dim3 grid(N / GM_BN, (M + GM_BM - 1) / GM_BM, group);
-    gemm_tf32_kernel<<<grid, 256, GM_SMEM_BYTES, st>>>(maps, args);
+    if (split) gemm_tf32_kernel<1><<<grid, 256, smem_split, st>>>(maps, args);
+    else gemm_tf32_kernel<0><<<grid, 256, smem_fast, st>>>(maps, args);
     DPH_CUDA(cudaGetLastError());
     return 0;
 }
 
-// C ABI (test / standalone use): out [M,N] = act(A [M,K] . W[N,K]^T + bias) + residual, device pointers, fp32, TF32 tensor cores.
+// C ABI (test / standalone use): out [M,N] = act(A [M,K] . W[N,K]^T + bias) + residual, device pointers, fp32 in/out.
+// precise = 0: one TF32 MMA per product (operands truncated to 10 mantissa bits); precise = 1: 3xTF32 split (fp32-accurate;
+// allocates 2 x (M + N) x K floats of scratch for the split operands).
 DPH_API int dph_gemm_tf32_nt(const float* A, const float* W, const float* bias, const float* residual, float* out, int64_t M, int64_t N, int64_t K,
-                             int act, void* cuda_stream) {
-    const float* a[1] = {A}; const float* w[1] = {W}; const float* b[1] = {bias}; const float* r[1] = {residual}; float* o[1] = {out};
-    return dph_launch_gemm_tf32(1, a, w, bias ? b : nullptr, residual ? r : nullptr, o, (int)M, (int)N, (int)K, act, (cudaStream_t)cuda_stream);
+                             int act, int precise, void* cuda_stream) {
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const float* b[1] = {bias}; const float* r[1] = {residual}; float* o[1] = {out};
+    if (!precise) {
+        const float* a[1] = {A}; const float* w[1] = {W};
+        return dph_launch_gemm_tf32(1, a, w, bias ? b : nullptr, residual ? r : nullptr, o, (int)M, (int)N, (int)K, act, st, nullptr, nullptr);
+    }
+    float* scratch = nullptr;
+    const size_t na = (size_t)M * K, nw = (size_t)N * K;
+    DPH_CUDA(cudaMalloc((void**)&scratch, (2 * na + 2 * nw) * 4));
+    float *ahi = scratch, *alo = scratch + na, *whi = scratch + 2 * na, *wlo = whi + nw;
+    int rc = dph_launch_split_tf32(A, ahi, alo, (long long)na, st);
+    if (!rc) rc = dph_launch_split_tf32(W, whi, wlo, (long long)nw, st);
+    const float* a[1] = {ahi}; const float* w[1] = {whi}; const float* al[1] = {alo}; const float* wl[1] = {wlo};
+    if (!rc) rc = dph_launch_gemm_tf32(1, a, w, bias ? b : nullptr, residual ? r : nullptr, o, (int)M, (int)N, (int)K, act, st, al, wl);
+    cudaStreamSynchronize(st);
+    cudaFree(scratch);
+    return rc;
 }

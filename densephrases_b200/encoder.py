@@ -47,7 +47,7 @@ def tower_blob(sd, prefix, config):
 
 
 class Encoder(object):
-    def __init__(self, config, tokenizer=None, state_dict=None, device=0):
+    def __init__(self, config, tokenizer=None, state_dict=None, device=0, precise=False):
         self.config = config if isinstance(config, BertGeometry) else BertGeometry(**{k: getattr(config, k) for k in
                                                                                      ('vocab_size', 'max_position_embeddings', 'type_vocab_size', 'hidden_size',
                                                                                       'num_hidden_layers', 'num_attention_heads', 'intermediate_size')})
@@ -58,6 +58,7 @@ class Encoder(object):
         L.check(L.lib().dph_encoder_create(C.byref(self._h), device, self.config.vocab_size, self.config.max_position_embeddings,
                                            self.config.type_vocab_size))
         self.training = False
+        self.set_precision(precise)
         if state_dict is not None:
             self.load_state_dict(state_dict)
 
@@ -65,6 +66,11 @@ class Encoder(object):
         h, self._h = getattr(self, '_h', None), None
         if h and L is not None and L._lib is not None:
             L._lib.dph_encoder_free(h)
+
+    def set_precision(self, precise):
+        """False (default): 1xTF32 GEMMs (== torch 1.9's default for fp32 matmuls on Ampere+); True: 3xTF32 split, fp32-accurate."""
+        self.precise = bool(precise)
+        L.check(L.lib().dph_encoder_set_precision(self._h, int(self.precise)))
 
     # -- torch.nn.Module-style surface the callers touch (embed_utils.py:393, single_utils.py:116) --
     def eval(self):

@@ -120,6 +120,9 @@ void dph_encoder_free(dph_encoder* e);
 int dph_encoder_set_stream(dph_encoder* e, void* cuda_stream);
 int64_t dph_encoder_tower_floats(const dph_encoder* e);
 int dph_encoder_load_tower(dph_encoder* e, int tower, const float* blob, int mem);
+/* 0 (default): GEMMs as one TF32 MMA per product -- what torch 1.9 (the reference's pin) does for fp32 matmuls on Ampere+;
+ * 1: 3xTF32 split GEMMs, fp32-accurate (matches the reference's CPU/fp32 path to ~1e-5). */
+int dph_encoder_set_precision(dph_encoder* e, int precise);
 /* input_ids / attention_mask / token_type_ids int64 [B,S] (S <= 384); start_out / end_out fp32 [B,768] = hidden state at
  * position 0 of each tower (the reference returns them as [B,1,768]). */
 int dph_encoder_embed_query(dph_encoder* e, const int64_t* input_ids, const int64_t* attention_mask, const int64_t* token_type_ids,
@@ -129,7 +132,7 @@ int dph_encoder_embed_query(dph_encoder* e, const int64_t* input_ids, const int6
  * out [M,N] = act(A [M,K] . W [N,K]^T + bias [N]) + residual [M,N]; act: 0 none, 1 erf-GELU; device pointers;
  * N % 128 == 0, K % 32 == 0.  == torch.nn.functional.linear (HF BertSelfAttention/BertOutput/BertIntermediate). */
 int dph_gemm_tf32_nt(const float* A, const float* W, const float* bias, const float* residual, float* out, int64_t M, int64_t N,
-                     int64_t K, int act, void* cuda_stream);
+                     int64_t K, int act, int precise /* 0: 1xTF32, 1: 3xTF32 split (fp32-accurate) */, void* cuda_stream);
 
 #ifdef __cplusplus
 }

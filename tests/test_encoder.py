@@ -79,3 +79,19 @@ def test_cuda_encoder_c3_batch_and_legacy_state_dict():
     print("mean|diff|", (s - rs).abs().mean().item(), "min cos", cos(s, rs).min().item())
     with pytest.raises(NotImplementedError):
         enc(input_ids=ids, attention_mask=mask, token_type_ids=tt, return_phrase=True)
+
+
+@pytest.mark.gpu
+def test_cuda_encoder_3xtf32_is_fp32_accurate():
+    """precise=True (3xTF32 split GEMMs): within 1e-3 (the north-star tolerance) of the unmodified fp32 reference class."""
+    from densephrases_b200.encoder import BertGeometry, Encoder, random_state_dict
+    seed, vocab, ids, mask, tt, start, end = load_case("b4_s64")
+    geo = BertGeometry(vocab_size=vocab)
+    enc = Encoder(geo, state_dict=random_state_dict(geo, seed), precise=True)
+    s, e = enc(input_ids_=ids, attention_mask_=mask, token_type_ids_=tt, return_query=True)
+    ds, de = (s.cpu() - start).abs().max().item(), (e.cpu() - end).abs().max().item()
+    print(f"3xTF32: max|diff| start {ds:.2e} end {de:.2e}")
+    assert ds < 1e-3 and de < 1e-3
+    enc.set_precision(False)
+    s2, _ = enc(input_ids_=ids, attention_mask_=mask, token_type_ids_=tt, return_query=True)
+    assert (s2.cpu() - start).abs().max().item() > ds

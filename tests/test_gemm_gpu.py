@@ -9,14 +9,14 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def run_gemm(A, W, bias, resid, act):
+def run_gemm(A, W, bias, resid, act, precise=0):
     import torch
     from densephrases_b200 import _lib as L
     out = torch.empty((A.shape[0], W.shape[0]), dtype=torch.float32, device=A.device)
     st = torch.cuda.current_stream().cuda_stream
     L.check(L.lib().dph_gemm_tf32_nt(A.data_ptr(), W.data_ptr(), bias.data_ptr() if bias is not None else None,
                                      resid.data_ptr() if resid is not None else None, out.data_ptr(), A.shape[0], W.shape[0], A.shape[1], act,
-                                     C.c_void_p(st)))
+                                     precise, C.c_void_p(st)))
     torch.cuda.synchronize()
     return out
 
@@ -44,6 +44,16 @@ def test_gemm_tf32_matches_torch_fp32(M, N, K, variant):
     err = (out.double() - ref).norm() / ref.norm()
     assert torch.isfinite(out).all()
     assert err < 1e-3, f"relative error {err:.3e}"
+    # 3xTF32 split mode: fp32-accurate
+    outp = run_gemm(A, W, bias, resid, act, precise=1)
+    errp = (outp.double() - ref).norm() / ref.norm()
+    ref32 = torch.nn.functional.linear(A, W, bias)
+    if act:
+        ref32 = torch.nn.functional.gelu(ref32)
+    if resid is not None:
+        ref32 = ref32 + resid
+    err32 = (ref32.double() - ref).norm() / ref.norm()
+    assert errp < 5e-5, f"3xTF32 relative error {errp:.3e} (torch fp32: {err32:.3e})"
     # exactness of the data path: with operands exactly representable in TF32 the result must match fp32 to rounding
     A2 = (A * 8).round() / 8
     W2 = (W * 64).round() / 64
