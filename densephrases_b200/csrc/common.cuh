@@ -104,3 +104,7 @@ struct __align__(16) DphSeg {
 struct DphWork {       // device scalars written by the plan kernel
     long long total_blocks;
 };
+struct DphPairWork {   // pair mode: total (list, item, block) work units and the per-CTA share
+    long long total_blocks;
+    long long per;
+};

@@ -116,7 +116,8 @@ DPH_API void dph_index_free(dph_index* ix) {
     void* ptrs[] = {ix->A, ix->C, ix->pq, ix->list_len, ix->list_start, ix->blk_off, ix->codes, ix->ids, ix->dm_ids, ix->dm_rows};
     for (void* p : ptrs) if (p) cudaFree(p);
     DevBuf* bufs[] = {&ix->xdev, &ix->xr, &ix->S, &ix->key, &ix->cd, &ix->lut_scan, &ix->lut_canon, &ix->lutmax, &ix->segs, &ix->wpre, &ix->qinfo,
-                      &ix->cand, &ix->cand_off, &ix->cand_cnt, &ix->gthr, &ix->flags, &ix->work, &ix->Dp, &ix->Ip, &ix->Gp, &ix->Dh, &ix->Ih, &ix->eps, &ix->nseg};
+                      &ix->cand, &ix->cand_off, &ix->cand_cnt, &ix->gthr, &ix->flags, &ix->work, &ix->Dp, &ix->Ip, &ix->Gp, &ix->Dh, &ix->Ih, &ix->eps, &ix->nseg, &ix->lutmin, &ix->lutmaxv, &ix->lutq, &ix->qparams, &ix->gdense,
+                      &ix->pl_cnt, &ix->pl_fill, &ix->pl_off, &ix->pl_blockpre, &ix->pl_entries, &ix->pairwork};
     for (DevBuf* b : bufs) b->release();
     delete ix;
 }
@@ -251,7 +252,7 @@ DPH_API int dph_index_set_nprobe(dph_index* ix, int nprobe) {
     return 0;
 }
 DPH_API int dph_index_set_scan_mode(dph_index* ix, int mode) {
-    DPH_CHECK(mode == DPH_SCAN_FAST || mode == DPH_SCAN_EXACT, "bad scan mode");
+    DPH_CHECK(mode >= 0 && mode <= 3, "bad scan mode");
     ix->scan_mode = mode;
     return 0;
 }
@@ -291,6 +292,7 @@ DPH_API const int32_t* dph_index_last_flags(const dph_index* ix) { return ix->fl
 DPH_API const int32_t* dph_index_last_probes(const dph_index* ix) { return ix->key.as<int32_t>(); }
 DPH_API const float* dph_index_last_coarse(const dph_index* ix) { return ix->cd.as<float>(); }
 DPH_API const float* dph_index_last_xr(const dph_index* ix) { return ix->xr.as<float>(); }
+DPH_API int dph_index_last_used_pair_mode(const dph_index* ix) { return ix->last_pair ? 1 : 0; }
 DPH_API int dph_index_copy_last(dph_index* ix, int which, void* dst_host, int64_t bytes) {
     const void* src = which == 0 ? ix->flags.p : which == 1 ? ix->key.p : which == 2 ? ix->cd.p : which == 3 ? ix->xr.p : nullptr;
     DPH_CHECK(src != nullptr, "copy_last: nothing to copy");
@@ -306,8 +308,11 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
     cudaStream_t st = ix->stream;
     const int nprobe = ix->nprobe;
     const int grid = ix->num_sms;
-    const int keep_fast = k + DPH_KEEP_SLACK;
-    const int keep_max = keep_fast;
+    // candidates kept per CTA: k + slack.  The proof needs T_k - (k+slack)-th score > 2 eps; the pair filter's eps is dominated by
+    // the 10-bit quantisation, so its slack grows with k (order statistics: the gap between ranks k and 1.5k is ~0.1 sigma).
+    const int keep_single = k + DPH_KEEP_SLACK;
+    const int keep_pair = k + (k / 2 > DPH_KEEP_SLACK ? k / 2 : DPH_KEEP_SLACK);
+    const int keep_max = keep_pair;
     DPH_TRY(ix->xr.ensure((size_t)n * ix->d * 4));
     DPH_TRY(ix->S.ensure((size_t)n * ix->nlist * 4));
     DPH_TRY(ix->key.ensure((size_t)n * nprobe * 4));
@@ -320,31 +325,53 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
     DPH_TRY(ix->qinfo.ensure((size_t)n * 4));
     DPH_TRY(ix->eps.ensure((size_t)n * 4));
     DPH_TRY(ix->nseg.ensure((size_t)n * 4));
-    DPH_TRY(ix->cand.ensure((size_t)(2 * grid + 2 * n + 2) * keep_max * 8));
+    // pair mode (two queries per gather) pays when lists are probed by >= ~1.5 queries of the batch on average
+    const int64_t eff_probe = std::min<int64_t>(nprobe, ix->nlist);
+    bool pair = ix->scan_mode == DPH_SCAN_PAIR || (ix->scan_mode == DPH_SCAN_FAST && n * eff_probe * 2 >= ix->nlist * 3);
+    if (keep_pair > 1536 - DPH_SCAN_THREADS || ix->scan_mode == DPH_SCAN_SINGLE) pair = false;
+    const int keep_fast = pair ? keep_pair : keep_single;
+    DPH_TRY(ix->cand.ensure(((size_t)(2 * grid + 2 * n + 2) + (pair ? (size_t)(3 * n * nprobe + 3 * grid + n + 16) : 0)) * keep_max * 8));
     DPH_TRY(ix->cand_off.ensure((size_t)(n + 1) * 8));
     DPH_TRY(ix->cand_cnt.ensure((size_t)n * 4));
     DPH_TRY(ix->gthr.ensure((size_t)n * 4));
     DPH_TRY(ix->flags.ensure((size_t)n * 4));
     DPH_TRY(ix->work.ensure(sizeof(DphWork)));
+    DPH_TRY(ix->lutmin.ensure((size_t)n * DPH_M * 4));
+    DPH_TRY(ix->lutmaxv.ensure((size_t)n * DPH_M * 4));
+    if (pair) {
+        DPH_TRY(ix->lutq.ensure((size_t)n * DPH_LUT_SCAN_FLOATS * 2));
+        DPH_TRY(ix->qparams.ensure((size_t)n * 8));
+        DPH_TRY(ix->gdense.ensure((size_t)n * nprobe * 4));
+        DPH_TRY(ix->pl_cnt.ensure((size_t)ix->nlist * 4));
+        DPH_TRY(ix->pl_fill.ensure((size_t)ix->nlist * 4));
+        DPH_TRY(ix->pl_off.ensure((size_t)(ix->nlist + 1) * 4));
+        DPH_TRY(ix->pl_blockpre.ensure((size_t)(ix->nlist + 1) * 8));
+        DPH_TRY(ix->pl_entries.ensure((size_t)n * nprobe * 4));
+        DPH_TRY(ix->pairwork.ensure(sizeof(DphPairWork)));
+    }
     ix->last_n = n;
+    ix->last_pair = pair;
 
     DPH_TRY(dph_launch_sgemm_nt_seq(x_dev, n, ix->A, ix->d, ix->d, ix->xr.as<float>(), st));                       // OPQ rotation
     DPH_TRY(dph_launch_sgemm_nt_seq(ix->xr.as<float>(), n, ix->C, ix->nlist, ix->d, ix->S.as<float>(), st));       // coarse scores
     DPH_TRY(dph_launch_coarse_select(ix->S.as<float>(), n, ix->nlist, nprobe, ix->key.as<int32_t>(), ix->cd.as<float>(), st));
-    DPH_TRY(dph_launch_lut(ix->xr.as<float>(), n, ix->pq, ix->lut_scan.as<float>(), ix->lut_canon.as<float>(), ix->lutmax.as<float>(), st));
-    if (ix->scan_mode == DPH_SCAN_FAST) {
-        DPH_TRY(dph_launch_plan(ix, n, k, keep_fast, grid, nullptr, st));
+    DPH_TRY(dph_launch_lut(ix->xr.as<float>(), n, ix->pq, ix->lut_scan.as<float>(), ix->lut_canon.as<float>(), ix->lutmax.as<float>(),
+                           ix->lutmin.as<float>(), ix->lutmaxv.as<float>(), pair ? ix->lutq.as<unsigned short>() : nullptr,
+                           pair ? ix->qparams.as<float2>() : nullptr, st));
+    if (ix->scan_mode != DPH_SCAN_EXACT) {
+        DPH_TRY(dph_launch_plan(ix, n, k, keep_fast, grid, nullptr, st, pair));
         if (ix->profile) DPH_CUDA(cudaEventRecord(ix->ev0[ix->prof_n % DPH_PROF_RING], st));
-        DPH_TRY(dph_launch_scan(ix, n, k, keep_fast, DPH_SCAN_FAST, grid, st));
+        if (pair) DPH_TRY(dph_launch_scan_pair(ix, n, keep_fast, grid, st));
+        else DPH_TRY(dph_launch_scan(ix, n, k, keep_fast, DPH_SCAN_FAST, grid, st));
         if (ix->profile) { DPH_CUDA(cudaEventRecord(ix->ev1[ix->prof_n % DPH_PROF_RING], st)); ix->prof_n++; }
         DPH_TRY(dph_launch_merge(ix, n, k, DPH_SCAN_FAST, nullptr, D, I, G, st));
         // fallback for queries whose filter could not be proven exact (no-op launches when no flag is set)
-        DPH_TRY(dph_launch_plan(ix, n, k, k, grid, ix->flags.as<int32_t>(), st));
+        DPH_TRY(dph_launch_plan(ix, n, k, k, grid, ix->flags.as<int32_t>(), st, false));
         DPH_TRY(dph_launch_scan(ix, n, k, k, DPH_SCAN_EXACT, grid, st));
         DPH_TRY(dph_launch_merge(ix, n, k, DPH_SCAN_EXACT, ix->flags.as<int32_t>(), D, I, G, st));
     } else {
         DPH_CUDA(cudaMemsetAsync(ix->flags.p, 0, (size_t)n * 4, st));
-        DPH_TRY(dph_launch_plan(ix, n, k, k, grid, nullptr, st));
+        DPH_TRY(dph_launch_plan(ix, n, k, k, grid, nullptr, st, false));
         if (ix->profile) DPH_CUDA(cudaEventRecord(ix->ev0[ix->prof_n % DPH_PROF_RING], st));
         DPH_TRY(dph_launch_scan(ix, n, k, k, DPH_SCAN_EXACT, grid, st));
         if (ix->profile) { DPH_CUDA(cudaEventRecord(ix->ev1[ix->prof_n % DPH_PROF_RING], st)); ix->prof_n++; }

@@ -7,6 +7,8 @@
 #define DPH_SCAN_THREADS 512
 #define DPH_SCAN_WARPS (DPH_SCAN_THREADS / 32)
 #define DPH_CAND_CAP 3072          // shared-memory candidate buffer (u64 keys) per scan CTA
+#define DPH_PAIR_CAP 1280          // pair mode: one buffer per query of the pair
+
 #define DPH_KEEP_SLACK 32          // fast mode keeps k + slack candidates per CTA
 #define DPH_MAX_K 1024
 #define DPH_PROF_RING 64
@@ -56,8 +58,10 @@ struct dph_index {
 
     // per-batch workspace
     DevBuf xdev, xr, S, key, cd, lut_scan, lut_canon, lutmax, segs, wpre, qinfo, cand, cand_off, cand_cnt, gthr, flags,
-        work, Dp, Ip, Gp, Dh, Ih, eps, nseg;
+        work, Dp, Ip, Gp, Dh, Ih, eps, nseg,
+        lutmin, lutmaxv, lutq, qparams, gdense, pl_cnt, pl_fill, pl_off, pl_blockpre, pl_entries, pairwork;
     int64_t last_n = 0;
+    bool last_pair = false;
     bool profile = false;              // CUDA events around the scan kernel of the last search chunk
     cudaEvent_t ev0[DPH_PROF_RING] = {}, ev1[DPH_PROF_RING] = {};
     int64_t prof_n = 0;
@@ -66,8 +70,10 @@ struct dph_index {
 // ---- prep.cu ----
 int dph_launch_sgemm_nt_seq(const float* X, int64_t n, const float* W, int64_t m, int K, float* out, cudaStream_t st);
 int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprobe, int32_t* key, float* cd, cudaStream_t st);
-int dph_launch_lut(const float* xr, int64_t n, const float* pq, float* lut_scan, float* lut_canon, float* lutmax, cudaStream_t st);
-int dph_launch_plan(dph_index* ix, int64_t n, int k, int keep, int grid, const int32_t* only_flagged, cudaStream_t st);
+int dph_launch_lut(const float* xr, int64_t n, const float* pq, float* lut_scan, float* lut_canon, float* lutmax, float* lutmin, float* lutmaxv,
+                   unsigned short* lutq, float2* qparams, cudaStream_t st);
+int dph_launch_plan(dph_index* ix, int64_t n, int k, int keep, int grid, const int32_t* only_flagged, cudaStream_t st, bool pair);
+int dph_launch_scan_pair(dph_index* ix, int64_t n, int keep, int grid, cudaStream_t st);
 // ---- scan.cu ----
 int dph_launch_scan(dph_index* ix, int64_t n, int k, int keep, int mode, int grid, cudaStream_t st);
 int dph_launch_merge(dph_index* ix, int64_t n, int k, int mode, const int32_t* only_flagged, float* D, int64_t* I,

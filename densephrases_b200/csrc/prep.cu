@@ -85,10 +85,75 @@ __global__ void __launch_bounds__(256) sgemm_nt_seq_kernel(const float* __restri
     }
 }
 
+// Same contract, 64x64 tile / 4x4 micro-tile: 4x the CTAs and a 4x shorter per-k-tile dependency chain -- used when the
+// 128x128 grid cannot fill the GPU (small query batches: the sequential-k definition forbids split-K).
+__global__ void __launch_bounds__(256) sgemm_nt_seq_small_kernel(const float* __restrict__ X, long long n, const float* __restrict__ W,
+                                                                  long long m, int K, float* __restrict__ out) {
+    __shared__ __align__(16) float As[2][GBK][64];
+    __shared__ __align__(16) float Bs[2][GBK][64];
+    const int tid = threadIdx.x;
+    const long long row0 = (long long)blockIdx.y * 64, col0 = (long long)blockIdx.x * 64;
+    const int lr = tid & 63, lk4 = (tid >> 6) & 1, isB = tid >> 7;
+    const long long grow = (isB ? col0 : row0) + lr;
+    const bool ok = grow < (isB ? m : n);
+    const float4* gp = reinterpret_cast<const float4*>((isB ? W : X) + (ok ? grow : 0) * K) + lk4;
+    float (*dst)[GBK][64] = isB ? Bs : As;
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 r = ok ? __ldg(gp) : z4;
+    const int ktiles = K / GBK;
+    int buf = 0;
+    dst[0][lk4 * 4 + 0][lr] = r.x; dst[0][lk4 * 4 + 1][lr] = r.y; dst[0][lk4 * 4 + 2][lr] = r.z; dst[0][lk4 * 4 + 3][lr] = r.w;
+    __syncthreads();
+    for (int kt = 0; kt < ktiles; kt++) {
+        if (kt + 1 < ktiles) r = ok ? __ldg(gp + (kt + 1) * 2) : z4;
+#pragma unroll
+        for (int k = 0; k < GBK; k++) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (kt + 1 < ktiles) {
+            const int nb = buf ^ 1;
+            dst[nb][lk4 * 4 + 0][lr] = r.x; dst[nb][lk4 * 4 + 1][lr] = r.y; dst[nb][lk4 * 4 + 2][lr] = r.z; dst[nb][lk4 * 4 + 3][lr] = r.w;
+            __syncthreads();
+            buf = nb;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const long long rr = row0 + ty * 4 + i;
+        if (rr >= n) continue;
+        const long long c = col0 + tx * 4;
+        float* o = out + rr * m + c;
+        if (c + 3 < m && ((m & 3) == 0)) *reinterpret_cast<float4*>(o) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        else {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (c + j < m) o[j] = acc[i][j];
+        }
+    }
+}
+
 int dph_launch_sgemm_nt_seq(const float* X, int64_t n, const float* W, int64_t m, int K, float* out, cudaStream_t st) {
     DPH_CHECK(K % GBK == 0 && K % 4 == 0, "sgemm_nt_seq: K must be a multiple of 8");
     if (n == 0 || m == 0) return 0;
     dim3 grid((unsigned)((m + GBN - 1) / GBN), (unsigned)((n + GBM - 1) / GBM));
+    if ((long long)grid.x * grid.y < 2 * 148) {
+        dim3 gs((unsigned)((m + 63) / 64), (unsigned)((n + 63) / 64));
+        sgemm_nt_seq_small_kernel<<<gs, 256, 0, st>>>(X, n, W, m, K, out);
+        DPH_CUDA(cudaGetLastError());
+        return 0;
+    }
     sgemm_nt_seq_kernel<<<grid, 256, 0, st>>>(X, n, W, m, K, out);
     DPH_CUDA(cudaGetLastError());
     return 0;
@@ -152,10 +217,10 @@ int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprob
 // =================================================================================================
 __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ xr, const float* __restrict__ pq,
                                                    float* __restrict__ lut_scan, float* __restrict__ lut_canon,
-                                                   float* __restrict__ lutmax) {
+                                                   float* __restrict__ lutmax, float* __restrict__ lutmin, float* __restrict__ lutmaxv) {
     __shared__ float tile[256 * 33];
     __shared__ float xs[32 * 8];
-    __shared__ float wmax[8][32];
+    __shared__ float wmax[8][32], wmin[8][32], wmxv[8][32];
     const long long q = blockIdx.x;
     const int seg = blockIdx.y, j = threadIdx.x, lane = j & 31, warp = j >> 5;
     xs[j] = xr[q * DPH_D + seg * 256 + j];
@@ -171,17 +236,23 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ xr, 
         acc = fmaf(x[4], c1.x, acc); acc = fmaf(x[5], c1.y, acc); acc = fmaf(x[6], c1.z, acc); acc = fmaf(x[7], c1.w, acc);
         tile[j * 33 + ml] = acc;
         lut_canon[(q * DPH_M + m) * 256 + j] = acc;
-        float a = fabsf(acc);
+        float a = fabsf(acc), lo = acc, hi = acc;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, off));
-        if (lane == 0) wmax[warp][ml] = a;
+        for (int off = 16; off > 0; off >>= 1) {
+            a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, off));
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+        }
+        if (lane == 0) { wmax[warp][ml] = a; wmin[warp][ml] = lo; wmxv[warp][ml] = hi; }
     }
     __syncthreads();
     if (j < 32) {
-        float a = wmax[0][j];
+        float a = wmax[0][j], lo = wmin[0][j], hi = wmxv[0][j];
 #pragma unroll
-        for (int w = 1; w < 8; w++) a = fmaxf(a, wmax[w][j]);
+        for (int w = 1; w < 8; w++) { a = fmaxf(a, wmax[w][j]); lo = fminf(lo, wmin[w][j]); hi = fmaxf(hi, wmxv[w][j]); }
         lutmax[q * DPH_M + seg * 32 + j] = a;
+        lutmin[q * DPH_M + seg * 32 + j] = lo;
+        lutmaxv[q * DPH_M + seg * 32 + j] = hi;
     }
     float* dst = lut_scan + ((size_t)q * 3 + seg) * (256 * 64);
     for (int idx = j; idx < 256 * 64; idx += 256) {
@@ -191,10 +262,51 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ xr, 
     }
 }
 
-int dph_launch_lut(const float* xr, int64_t n, const float* pq, float* lut_scan, float* lut_canon, float* lutmax, cudaStream_t st) {
+// Quantised LUT for the pair-packed scan: qv[m][j] = round((LUT[m][j] - min_m) / step) in [0, 682], one step per query
+// (step = max_m range_m / 682) so that 96 entries sum below 2^16 and two queries' tables can share one 32-bit word.
+// Written in the scan layout ([3][256][64] u16); qparams[q] = (step, sum_m min_m).
+#define DPH_QMAX 682
+__global__ void __launch_bounds__(256) lutq_kernel(const float* __restrict__ lut_canon, const float* __restrict__ lutmin,
+                                                    const float* __restrict__ lutmaxv, unsigned short* __restrict__ lutq,
+                                                    float2* __restrict__ qparams) {
+    __shared__ unsigned short tile[256 * 34];
+    __shared__ float s_step, s_base;
+    const long long q = blockIdx.x;
+    const int seg = blockIdx.y, j = threadIdx.x, lane = j & 31;
+    if (j < 32) {
+        float r = 0.f, b = 0.f;
+        for (int m = lane; m < DPH_M; m += 32) { r = fmaxf(r, lutmaxv[q * DPH_M + m] - lutmin[q * DPH_M + m]); b += lutmin[q * DPH_M + m]; }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, off)); b += __shfl_xor_sync(0xffffffffu, b, off); }
+        if (lane == 0) { s_step = fmaxf(r / (float)DPH_QMAX, 1e-30f); s_base = b; }
+    }
+    __syncthreads();
+    const float inv = 1.0f / s_step;
+    for (int ml = 0; ml < 32; ml++) {
+        const int m = seg * 32 + ml;
+        const float v = lut_canon[(q * DPH_M + m) * 256 + j];
+        int qv = (int)((v - lutmin[q * DPH_M + m]) * inv + 0.5f);
+        qv = qv < 0 ? 0 : (qv > DPH_QMAX ? DPH_QMAX : qv);
+        tile[j * 34 + ml] = (unsigned short)qv;
+    }
+    __syncthreads();
+    unsigned short* dst = lutq + ((size_t)q * 3 + seg) * (256 * 64);
+    for (int idx = j; idx < 256 * 64; idx += 256) {
+        const int row = idx >> 6, w = idx & 63;
+        dst[idx] = (w < 63) ? tile[row * 34 + (w & 31)] : (unsigned short)0;
+    }
+    if (seg == 0 && j == 0) qparams[q] = make_float2(s_step, s_base);
+}
+
+int dph_launch_lut(const float* xr, int64_t n, const float* pq, float* lut_scan, float* lut_canon, float* lutmax, float* lutmin, float* lutmaxv,
+                   unsigned short* lutq, float2* qparams, cudaStream_t st) {
     if (n == 0) return 0;
-    lut_kernel<<<dim3((unsigned)n, 3), 256, 0, st>>>(xr, pq, lut_scan, lut_canon, lutmax);
+    lut_kernel<<<dim3((unsigned)n, 3), 256, 0, st>>>(xr, pq, lut_scan, lut_canon, lutmax, lutmin, lutmaxv);
     DPH_CUDA(cudaGetLastError());
+    if (lutq) {
+        lutq_kernel<<<dim3((unsigned)n, 3), 256, 0, st>>>(lut_canon, lutmin, lutmaxv, lutq, qparams);
+        DPH_CUDA(cudaGetLastError());
+    }
     return 0;
 }
 
@@ -209,6 +321,8 @@ struct PlanArgs {
     const int* only_flagged;       // nullable: plan work only for queries with flag != 0
     const float* lutmax;
     DphSeg* segs; unsigned* qblocks; int* nseg; float* eps;
+    unsigned* gdense;              // nullable: canonical scan position of every (query, probe), dense [n, nprobe] (pair mode)
+    const float2* qparams;         // nullable: quantisation (step, base) -> the pair filter's extra error term
 };
 // One warp per query.  Writes the COMPACTED list of in-shard, non-empty segments (probe-rank order) to
 // segs[q][0..nseg[q]); gstart stays the canonical scan position over ALL probed lists (tie-break key across shards).
@@ -239,6 +353,7 @@ __global__ void __launch_bounds__(256) plan_segs_kernel(PlanArgs a) {
             unsigned g2 = __shfl_up_sync(0xffffffffu, gl, off), w2 = __shfl_up_sync(0xffffffffu, wl, off);
             if (lane >= off) { gl += g2; wl += w2; }
         }
+        if (a.gdense && r < a.nprobe) a.gdense[q * a.nprobe + r] = gacc + gl - (unsigned)len;
         const unsigned have = __ballot_sync(0xffffffffu, nb > 0);
         if (nb > 0) {
             DphSeg s;
@@ -262,13 +377,17 @@ __global__ void __launch_bounds__(256) plan_segs_kernel(PlanArgs a) {
         // |approx - canonical| <= 2 * gamma_96 * sum|terms|,  gamma_96 = 96u/(1-96u), u = 2^-24  (Higham 2002, eq. 4.4);
         // inflated by 1.01 for the fp32 evaluation of the bound itself.
         const float gamma96 = 5.7221e-6f;
-        a.eps[q] = 2.0f * gamma96 * (dmax + lsum) * 1.01f;
+        float e = 2.0f * gamma96 * (dmax + lsum) * 1.01f;
+        // pair mode: every quantised entry is within 0.5 step of the fp32 entry (+ rounding of the dequantisation) -> 96 * 0.502 * step
+        if (a.qparams) e += 96.0f * 0.502f * a.qparams[q].x + 8e-6f * (dmax + lsum);
+        a.eps[q] = e;
     }
 }
 
 struct PlanScanArgs {
     const unsigned* qblocks; long long n; int keep; int grid;
     long long* qpre; long long* cand_off; int* cand_cnt; unsigned* gthr; DphWork* work;
+    const DphPairWork* pairwork; const int* nseg;     // pair mode (nullable): a query is flushed once per (CTA, item) visit
 };
 __global__ void __launch_bounds__(1024) plan_scan_kernel(PlanScanArgs a) {
     __shared__ long long wsum[32];
@@ -301,13 +420,18 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(PlanScanArgs a) {
     __syncthreads();
     // pass 2: candidate-region offsets; a query spanning `parts` scan CTAs may receive parts*keep entries
     const long long T = total;
-    const long long per = T / a.grid > 0 ? T / a.grid : 1;
+    const long long per = a.pairwork ? a.pairwork->per : (T / a.grid > 0 ? T / a.grid : 1);
     for (long long base = 0; base < a.n; base += 1024) {
         long long q = base + tid;
         long long v = 0;
         if (q < a.n) {
             long long qb = (long long)a.qblocks[q];
-            if (qb > 0) { long long parts = qb / per + 2; if (parts > a.grid) parts = a.grid; v = parts * a.keep; }
+            if (qb > 0) {
+                long long parts = qb / per + 2;
+                if (a.pairwork) parts = 3ll * a.nseg[q] + qb / per + 1;
+                else if (parts > a.grid) parts = a.grid;
+                v = parts * a.keep;
+            }
         }
         long long incl = v;
 #pragma unroll
@@ -330,16 +454,100 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(PlanScanArgs a) {
     if (tid == 0) a.cand_off[a.n] = carry;
 }
 
-int dph_launch_plan(dph_index* ix, int64_t n, int k, int keep, int grid, const int32_t* only_flagged, cudaStream_t st) {
+// =================================================================================================
+// pair plan: invert (query -> probed lists) into (list -> probing queries), pair the probes of each list two by two into
+// work items, and linearise (list, item, block) for the pair-packed scan kernel.
+// =================================================================================================
+struct PairPlanArgs {
+    const int* key; long long nq_probes; int nprobe; const int* list_len; long long list_lo, list_hi, nlist; int grid;
+    int* cnt; int* fill; int* off; long long* blockpre; unsigned* entries; DphPairWork* work;
+};
+__global__ void pair_count_kernel(PairPlanArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.nq_probes) return;
+    const int l = a.key[i];
+    if (l >= a.list_lo && l < a.list_hi && a.list_len[l] > 0) atomicAdd(&a.cnt[l], 1);
+}
+__global__ void __launch_bounds__(1024) pair_scan_kernel(PairPlanArgs a) {
+    __shared__ long long wsa[32], wsb[32];
+    __shared__ long long ca, cb;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { ca = 0; cb = 0; }
+    __syncthreads();
+    for (long long base = a.list_lo; base < a.list_hi; base += 1024) {
+        const long long l = base + tid;
+        long long va = 0, vb = 0;
+        if (l < a.list_hi) {
+            const int c = a.cnt[l];
+            va = c;
+            vb = (long long)((c + 1) >> 1) * (long long)((a.list_len[l] + 31) >> 5);
+        }
+        long long ia = va, ib = vb;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            long long t1 = __shfl_up_sync(0xffffffffu, ia, off), t2 = __shfl_up_sync(0xffffffffu, ib, off);
+            if (lane >= off) { ia += t1; ib += t2; }
+        }
+        if (lane == 31) { wsa[warp] = ia; wsb[warp] = ib; }
+        __syncthreads();
+        if (warp == 0) {
+            long long w1 = wsa[lane], w2 = wsb[lane], i1 = w1, i2 = w2;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                long long t1 = __shfl_up_sync(0xffffffffu, i1, off), t2 = __shfl_up_sync(0xffffffffu, i2, off);
+                if (lane >= off) { i1 += t1; i2 += t2; }
+            }
+            wsa[lane] = i1 - w1; wsb[lane] = i2 - w2;
+        }
+        __syncthreads();
+        const long long ea = ca + wsa[warp] + ia - va, eb = cb + wsb[warp] + ib - vb;
+        if (l < a.list_hi) { a.off[l] = (int)ea; a.blockpre[l] = eb; }
+        __syncthreads();
+        if (tid == 1023) { ca = ea + va; cb = eb + vb; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        a.off[a.list_hi] = (int)ca; a.blockpre[a.list_hi] = cb;
+        a.work->total_blocks = cb;
+        a.work->per = cb / a.grid > 0 ? cb / a.grid : 1;
+    }
+}
+__global__ void pair_fill_kernel(PairPlanArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.nq_probes) return;
+    const int l = a.key[i];
+    if (l >= a.list_lo && l < a.list_hi && a.list_len[l] > 0) {
+        const int pos = a.off[l] + atomicAdd(&a.fill[l], 1);
+        a.entries[pos] = (unsigned)((i / a.nprobe) << 10) | (unsigned)(i % a.nprobe);
+    }
+}
+
+int dph_launch_plan(dph_index* ix, int64_t n, int k, int keep, int grid, const int32_t* only_flagged, cudaStream_t st, bool pair) {
     (void)k;
     if (n == 0) return 0;
     PlanArgs a;
     a.key = ix->key.as<int>(); a.cd = ix->cd.as<float>(); a.list_len = ix->list_len; a.blk_off = (const long long*)ix->blk_off;
     a.list_lo = ix->list_lo; a.list_hi = ix->list_hi; a.nprobe = ix->nprobe; a.n = n; a.only_flagged = only_flagged;
     a.lutmax = ix->lutmax.as<float>(); a.segs = ix->segs.as<DphSeg>(); a.qblocks = ix->qinfo.as<unsigned>(); a.nseg = ix->nseg.as<int>(); a.eps = ix->eps.as<float>();
+    a.gdense = pair ? ix->gdense.as<unsigned>() : nullptr; a.qparams = pair ? ix->qparams.as<float2>() : nullptr;
     plan_segs_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(a);
     DPH_CUDA(cudaGetLastError());
+    if (pair) {
+        PairPlanArgs p;
+        p.key = ix->key.as<int>(); p.nq_probes = n * ix->nprobe; p.nprobe = ix->nprobe; p.list_len = ix->list_len; p.list_lo = ix->list_lo;
+        p.list_hi = ix->list_hi; p.nlist = ix->nlist; p.grid = grid; p.cnt = ix->pl_cnt.as<int>(); p.fill = ix->pl_fill.as<int>();
+        p.off = ix->pl_off.as<int>(); p.blockpre = ix->pl_blockpre.as<long long>(); p.entries = ix->pl_entries.as<unsigned>();
+        p.work = ix->pairwork.as<DphPairWork>();
+        DPH_CUDA(cudaMemsetAsync(p.cnt, 0, (size_t)ix->nlist * 4, st));
+        DPH_CUDA(cudaMemsetAsync(p.fill, 0, (size_t)ix->nlist * 4, st));
+        const unsigned nb = (unsigned)((p.nq_probes + 255) / 256);
+        pair_count_kernel<<<nb, 256, 0, st>>>(p);
+        pair_scan_kernel<<<1, 1024, 0, st>>>(p);
+        pair_fill_kernel<<<nb, 256, 0, st>>>(p);
+        DPH_CUDA(cudaGetLastError());
+    }
     PlanScanArgs b;
+    b.pairwork = pair ? ix->pairwork.as<DphPairWork>() : nullptr; b.nseg = ix->nseg.as<int>();
     b.qblocks = ix->qinfo.as<unsigned>(); b.n = n; b.keep = keep; b.grid = grid; b.qpre = ix->wpre.as<long long>();
     b.cand_off = ix->cand_off.as<long long>(); b.cand_cnt = ix->cand_cnt.as<int>(); b.gthr = ix->gthr.as<unsigned>();
     b.work = ix->work.as<DphWork>();

@@ -269,6 +269,205 @@ __global__ void __launch_bounds__(NT, 1) scan_kernel(ScanArgs a) {
     }
 }
 
+// =================================================================================================
+// PAIR mode: when a list is probed by several queries of the batch (C2: 64 x 256 probes over 4096 lists = 4 per list),
+// two of them share every gather: their LUTs are quantised to 10-bit integers (plan: lutq_kernel) and packed into one
+// 32-bit word (query a in the low half, query b in the high half), so ONE PRMT + LDS + IADD advances both running sums
+// (96 x 682 < 2^16: the halves cannot carry into each other).  Per (query, byte) that halves the code bytes read from HBM,
+// the shared-memory gathers and the instructions.  The integer sums are exact; the only error is the quantisation
+// (<= 0.5 step per entry), which the plan folds into eps, so the same proof + exact canonical re-scoring applies.
+// Work: the plan inverts probes into per-list query groups and pairs them; an item = (list, query pair), linearised by
+// blocks; a CTA takes a contiguous block range, rebuilding the packed LUT (192 KB, from L2) at every item boundary.
+// =================================================================================================
+struct PairScanArgs {
+    const uint8_t* codes; const long long* blk_off; const int* list_len;
+    const int* pl_cnt; const int* pl_off; const long long* blockpre; const unsigned* entries; const DphPairWork* work;
+    const unsigned short* lutq; const float2* qparams; const float* cd; const unsigned* gdense;
+    unsigned* gthr; unsigned long long* cand; const long long* cand_off; int* cand_cnt;
+    long long list_lo, list_hi; int nprobe; int keep;
+};
+#define PCAP 1536
+struct PairShared {
+    unsigned long long cbuf[2][PCAP];
+    SelectScratch sc;
+    int cnt[2]; unsigned thr[2]; int base[2]; int ndone; int ndone_snap;
+};
+template <int IMM> __device__ __forceinline__ unsigned lds_imm_u32(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
+template <int T0> __device__ __forceinline__ void pair_word(unsigned wv, unsigned y, unsigned& a0, unsigned& a1, unsigned& a2, unsigned& a3) {
+    constexpr int TB = DPH_DYN_SMEM_BASE + (T0 >> 5) * 65536 + (T0 & 31) * 4;
+    a0 += lds_imm_u32<TB + 0>(__byte_perm(wv, y, 0x7504));
+    a1 += lds_imm_u32<TB + 4>(__byte_perm(wv, y, 0x7514));
+    a2 += lds_imm_u32<TB + 8>(__byte_perm(wv, y, 0x7524));
+    a3 += lds_imm_u32<TB + 12>(__byte_perm(wv, y, 0x7534));
+}
+template <int C> __device__ __forceinline__ void pair_chunk(const uint4& v, unsigned y, unsigned& a0, unsigned& a1, unsigned& a2, unsigned& a3) {
+    pair_word<C * 16 + 0>(v.x, y, a0, a1, a2, a3);
+    pair_word<C * 16 + 4>(v.y, y, a0, a1, a2, a3);
+    pair_word<C * 16 + 8>(v.z, y, a0, a1, a2, a3);
+    pair_word<C * 16 + 12>(v.w, y, a0, a1, a2, a3);
+}
+template <int CAP>
+__device__ __forceinline__ void compact_buffer(unsigned long long* cb, int* cnt, unsigned* thr, int keep, unsigned* gthr_q, SelectScratch* sc) {
+    const int tid = threadIdx.x;
+    const int n = *cnt;
+    unsigned long long pivot = block_radix_select([&](int i) { return cb[i]; }, n, keep, sc);
+    unsigned long long mine[CAP / NT];
+#pragma unroll
+    for (int e = 0; e < CAP / NT; e++) { int i = tid + e * NT; mine[e] = (i < n) ? cb[i] : 0ull; }
+    __syncthreads();
+    if (tid == 0) *cnt = 0;
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < CAP / NT; e++)
+        if (mine[e] >= pivot && mine[e] != 0ull) { int p = atomicAdd(cnt, 1); cb[p] = mine[e]; }
+    if (tid == 0) {
+        unsigned t = (unsigned)(pivot >> 32);
+        unsigned old = atomicMax(gthr_q, t);
+        *thr = t > old ? t : old;
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void warp_append(bool pass, unsigned long long key, unsigned long long* cb, int* cnt, int cap, int lane) {
+    const unsigned pm = __ballot_sync(0xffffffffu, pass);
+    if (pm) {
+        int basep = 0;
+        if (lane == 0) basep = atomicAdd(cnt, __popc(pm));
+        basep = __shfl_sync(0xffffffffu, basep, 0);
+        if (pass) { int p = basep + __popc(pm & ((1u << lane) - 1u)); if (p < cap) cb[p] = key; }
+    }
+}
+
+__global__ void __launch_bounds__(NT, 1) scan_pair_kernel(PairScanArgs a) {
+    unsigned char* const smem = dph_smem;
+    PairShared* sh = reinterpret_cast<PairShared*>(smem + SMEM_LUT_FAST);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long T = a.work->total_blocks;
+    const long long G = gridDim.x, c = blockIdx.x;
+    const long long g0 = T * c / G, g1 = T * (c + 1) / G;
+    if (g0 >= g1) return;
+    long long lo = a.list_lo, hi = a.list_hi;                  // last l with blockpre[l] <= g0
+    while (hi - lo > 1) { long long mid = (lo + hi) >> 1; if (a.blockpre[mid] <= g0) lo = mid; else hi = mid; }
+    long long l = lo, g = g0;
+    const unsigned ywin = (((unsigned)__cvta_generic_to_shared(dph_smem)) & 0xFF000000u) | ((unsigned)lane * 4u);
+
+    while (g < g1) {
+        while (a.blockpre[l + 1] <= g) l++;
+        const int len = a.list_len[l];
+        const long long nb = (len + 31) >> 5;
+        const long long rel = g - a.blockpre[l];
+        const int it = (int)(rel / nb);
+        const unsigned bi0 = (unsigned)(rel % nb);
+        const unsigned bend = (unsigned)((nb - bi0 < g1 - g) ? nb : bi0 + (g1 - g));
+        const int e0 = a.pl_off[l] + 2 * it;
+        const bool has_b = (2 * it + 1) < a.pl_cnt[l];
+        const unsigned ea = a.entries[e0], eb = has_b ? a.entries[e0 + 1] : ea;
+        const long long qa = ea >> 10, qb = eb >> 10;
+        const int ra = (int)(ea & 1023u), rb = (int)(eb & 1023u);
+        __syncthreads();
+        {   // ---- packed LUT: word = qa entry | qb entry << 16, same [3][256][64] scan layout ----
+            const uint4* A4 = reinterpret_cast<const uint4*>(a.lutq + (size_t)qa * DPH_LUT_SCAN_FLOATS);
+            const uint4* B4 = reinterpret_cast<const uint4*>(a.lutq + (size_t)qb * DPH_LUT_SCAN_FLOATS);
+            uint4* dst = reinterpret_cast<uint4*>(smem);
+            for (int i = tid; i < DPH_LUT_SCAN_FLOATS / 8; i += NT) {
+                const uint4 va = __ldg(A4 + i);
+                uint4 vb = make_uint4(0u, 0u, 0u, 0u);
+                if (has_b) vb = __ldg(B4 + i);
+                uint4 o0, o1;
+                o0.x = (va.x & 0xFFFFu) | (vb.x << 16); o0.y = (va.x >> 16) | (vb.x & 0xFFFF0000u);
+                o0.z = (va.y & 0xFFFFu) | (vb.y << 16); o0.w = (va.y >> 16) | (vb.y & 0xFFFF0000u);
+                o1.x = (va.z & 0xFFFFu) | (vb.z << 16); o1.y = (va.z >> 16) | (vb.z & 0xFFFF0000u);
+                o1.z = (va.w & 0xFFFFu) | (vb.w << 16); o1.w = (va.w >> 16) | (vb.w & 0xFFFF0000u);
+                dst[2 * i] = o0; dst[2 * i + 1] = o1;
+            }
+        }
+        if (tid == 0) {
+            sh->cnt[0] = 0; sh->cnt[1] = 0; sh->ndone = 0; sh->ndone_snap = 0;
+            sh->thr[0] = *((volatile unsigned*)(a.gthr + qa));
+            sh->thr[1] = has_b ? *((volatile unsigned*)(a.gthr + qb)) : 0xFFFFFFFFu;
+        }
+        __syncthreads();
+        const float2 pa = a.qparams[qa], pb = a.qparams[qb];
+        const float base_a = a.cd[qa * a.nprobe + ra] + pa.y, base_b = a.cd[qb * a.nprobe + rb] + pb.y;
+        const unsigned gs_a = a.gdense[qa * a.nprobe + ra], gs_b = a.gdense[qb * a.nprobe + rb];
+        const uint4* lbase = reinterpret_cast<const uint4*>(a.codes + a.blk_off[l] * DPH_BLK_BYTES);
+
+        unsigned b = bi0 + warp, bp = bi0 + warp;
+        uint4 nxt[6];
+#pragma unroll 1
+        for (int r = 0; r < DPH_L2_PREFETCH_ROUNDS && bp < bend; r++, bp += NW)
+            if (lane == 0) l2_prefetch_block(lbase + (size_t)bp * (DPH_BLK_BYTES / 16));
+        bool more = b < bend;
+        if (more) {
+            const uint4* p = lbase + (size_t)b * (DPH_BLK_BYTES / 16) + lane;
+#pragma unroll
+            for (int c6 = 0; c6 < 6; c6++) nxt[c6] = ldg_stream(p + c6 * 32);
+        }
+        bool counted = false;
+        while (true) {
+            while (more) {
+                if (*((volatile int*)&sh->cnt[0]) > PCAP - NT || *((volatile int*)&sh->cnt[1]) > PCAP - NT) break;
+                uint4 cur[6];
+#pragma unroll
+                for (int c6 = 0; c6 < 6; c6++) cur[c6] = nxt[c6];
+                const unsigned bcur = b;
+                if (bp < bend) { if (lane == 0) l2_prefetch_block(lbase + (size_t)bp * (DPH_BLK_BYTES / 16)); bp += NW; }
+                b += NW;
+                more = b < bend;
+                if (more) {
+                    const uint4* p = lbase + (size_t)b * (DPH_BLK_BYTES / 16) + lane;
+#pragma unroll
+                    for (int c6 = 0; c6 < 6; c6++) nxt[c6] = ldg_stream(p + c6 * 32);
+                }
+                unsigned s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+                pair_chunk<0>(cur[0], ywin, s0, s1, s2, s3);
+                pair_chunk<1>(cur[1], ywin, s0, s1, s2, s3);
+                pair_chunk<2>(cur[2], ywin, s0, s1, s2, s3);
+                pair_chunk<3>(cur[3], ywin, s0, s1, s2, s3);
+                pair_chunk<4>(cur[4], ywin, s0, s1, s2, s3);
+                pair_chunk<5>(cur[5], ywin, s0, s1, s2, s3);
+                const unsigned tot = (s0 + s1) + (s2 + s3);
+                const float sc_a = fmaf(pa.x, (float)(tot & 0xFFFFu), base_a);
+                const float sc_b = fmaf(pb.x, (float)(tot >> 16), base_b);
+                const unsigned j = bcur * 32u + lane;
+                const bool valid = (int)j < len;
+                const unsigned ka = dph_fkey(sc_a), kb = dph_fkey(sc_b);
+                warp_append(valid && ka >= *((volatile unsigned*)&sh->thr[0]), ((unsigned long long)ka << 32) | (unsigned long long)(0xFFFFFFFFu - (gs_a + j)),
+                            sh->cbuf[0], &sh->cnt[0], PCAP, lane);
+                warp_append(valid && kb >= *((volatile unsigned*)&sh->thr[1]), ((unsigned long long)kb << 32) | (unsigned long long)(0xFFFFFFFFu - (gs_b + j)),
+                            sh->cbuf[1], &sh->cnt[1], PCAP, lane);
+            }
+            if (!more && !counted) { counted = true; if (lane == 0) atomicAdd(&sh->ndone, 1); }
+            __syncthreads();
+            if (sh->cnt[0] > a.keep) compact_buffer<PCAP>(sh->cbuf[0], &sh->cnt[0], &sh->thr[0], a.keep, a.gthr + qa, &sh->sc);
+            if (sh->cnt[1] > a.keep) compact_buffer<PCAP>(sh->cbuf[1], &sh->cnt[1], &sh->thr[1], a.keep, a.gthr + qb, &sh->sc);
+            if (tid == 0) {
+                unsigned ga = *((volatile unsigned*)(a.gthr + qa));
+                if (ga > sh->thr[0]) sh->thr[0] = ga;
+                if (has_b) { unsigned gb = *((volatile unsigned*)(a.gthr + qb)); if (gb > sh->thr[1]) sh->thr[1] = gb; }
+                sh->ndone_snap = sh->ndone;
+            }
+            __syncthreads();
+            if (sh->ndone_snap == NW) break;
+        }
+        // ---- publish both candidate sets ----
+        for (int s2i = 0; s2i < (has_b ? 2 : 1); s2i++) {
+            const long long q = s2i ? qb : qa;
+            const int cnt = sh->cnt[s2i];
+            if (tid == 0) sh->base[s2i] = atomicAdd(a.cand_cnt + q, cnt);
+            __syncthreads();
+            const long long off = a.cand_off[q], cap = a.cand_off[q + 1] - off;
+            const int basep = sh->base[s2i];
+            for (int i = tid; i < cnt; i += NT)
+                if (basep + i < cap) a.cand[off + basep + i] = sh->cbuf[s2i][i];
+        }
+        g += (long long)(bend - bi0);
+    }
+}
+
 __global__ void smem_base_probe_kernel(unsigned* out) { *out = (unsigned)__cvta_generic_to_shared(dph_smem) & 0x00FFFFFFu; }
 
 static bool g_attrs_set = false;
@@ -284,6 +483,7 @@ int dph_scan_setup_attrs() {
     }
     DPH_CUDA(cudaFuncSetAttribute(scan_kernel<DPH_SCAN_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LUT_FAST + (int)sizeof(ScanShared)));
     DPH_CUDA(cudaFuncSetAttribute(scan_kernel<DPH_SCAN_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LUT_EXACT + (int)sizeof(ScanShared)));
+    DPH_CUDA(cudaFuncSetAttribute(scan_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LUT_FAST + (int)sizeof(PairShared)));
     g_attrs_set = true;
     return 0;
 }
@@ -301,6 +501,21 @@ int dph_launch_scan(dph_index* ix, int64_t n, int k, int keep, int mode, int gri
         scan_kernel<DPH_SCAN_FAST><<<grid, NT, SMEM_LUT_FAST + sizeof(ScanShared), st>>>(a);
     else
         scan_kernel<DPH_SCAN_EXACT><<<grid, NT, SMEM_LUT_EXACT + sizeof(ScanShared), st>>>(a);
+    DPH_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int dph_launch_scan_pair(dph_index* ix, int64_t n, int keep, int grid, cudaStream_t st) {
+    if (n == 0) return 0;
+    DPH_TRY(dph_scan_setup_attrs());
+    PairScanArgs a;
+    a.codes = ix->codes; a.blk_off = (const long long*)ix->blk_off; a.list_len = ix->list_len; a.pl_cnt = ix->pl_cnt.as<int>();
+    a.pl_off = ix->pl_off.as<int>(); a.blockpre = ix->pl_blockpre.as<long long>(); a.entries = ix->pl_entries.as<unsigned>();
+    a.work = ix->pairwork.as<DphPairWork>(); a.lutq = ix->lutq.as<unsigned short>(); a.qparams = ix->qparams.as<float2>();
+    a.cd = ix->cd.as<float>(); a.gdense = ix->gdense.as<unsigned>(); a.gthr = ix->gthr.as<unsigned>();
+    a.cand = ix->cand.as<unsigned long long>(); a.cand_off = ix->cand_off.as<long long>(); a.cand_cnt = ix->cand_cnt.as<int>();
+    a.list_lo = ix->list_lo; a.list_hi = ix->list_hi; a.nprobe = ix->nprobe; a.keep = keep;
+    scan_pair_kernel<<<grid, NT, SMEM_LUT_FAST + sizeof(PairShared), st>>>(a);
     DPH_CUDA(cudaGetLastError());
     return 0;
 }

@@ -102,6 +102,9 @@ class IvfPqIndex:
     def set_scan_mode(self, mode):
         L.check(L.lib().dph_index_set_scan_mode(self._h, mode))
 
+    def last_used_pair_mode(self):
+        return bool(L.lib().dph_index_last_used_pair_mode(self._h))
+
     def set_stream(self, cuda_stream_ptr):
         L.check(L.lib().dph_index_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 

@@ -29,8 +29,10 @@ extern "C" {
 #define DPH_MEM_DEVICE 1
 
 /* scan kernel selection (dph_index_set_scan_mode) */
-#define DPH_SCAN_FAST 0  /* conflict-free diagonal ADC filter + exact fp32 re-scoring (default) */
-#define DPH_SCAN_EXACT 1 /* canonical-order fp32 ADC for every code (slow; fallback + cross-check) */
+#define DPH_SCAN_FAST 0   /* default: conflict-free gather filter + proof + exact fp32 re-scoring; picks PAIR or SINGLE per batch */
+#define DPH_SCAN_EXACT 1  /* canonical-order fp32 ADC for every code (slow; fallback + cross-check) */
+#define DPH_SCAN_PAIR 2   /* force: two queries share every gather (int16-packed quantised LUTs), lists grouped by probing queries */
+#define DPH_SCAN_SINGLE 3 /* force: one query per gather (fp32 LUT) */
 
 typedef struct dph_index dph_index;
 
@@ -96,6 +98,7 @@ const int32_t* dph_index_last_flags(const dph_index* ix);
 const int32_t* dph_index_last_probes(const dph_index* ix);
 const float* dph_index_last_coarse(const dph_index* ix);
 const float* dph_index_last_xr(const dph_index* ix);
+int dph_index_last_used_pair_mode(const dph_index* ix);
 /* Copy one of them to the host (synchronises): which = 0 flags, 1 probes, 2 coarse scores, 3 rotated queries. */
 int dph_index_copy_last(dph_index* ix, int which, void* dst_host, int64_t bytes);
 

@@ -47,7 +47,7 @@ def test_generators_match_oracle(oracle):
     assert np.array_equal(gpu.opq_matrix(), ref.A)
 
 
-@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("mode", [1, 3, 2, 0])        # exact | single-query gathers | pair-packed gathers | auto
 @pytest.mark.parametrize("nlist,N,nprobe,k,nq", [(16, 5000, 4, 10, 9), (64, 40000, 16, 10, 33), (1, 3000, 256, 10, 5),
                                                   (40, 2000, 256, 100, 7), (8, 100, 8, 200, 3)])
 def test_search_matches_oracle(oracle, mode, nlist, N, nprobe, k, nq):
@@ -63,7 +63,7 @@ def test_search_matches_oracle(oracle, mode, nlist, N, nprobe, k, nq):
     assert_topk_equal(D, I, Dr, Ir, f"mode={mode}")
 
 
-@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("mode", [1, 3, 2])
 def test_ragged_empty_lists_and_explicit_ids(oracle, mode):
     rng = np.random.default_rng(5)
     nlist = 48
@@ -98,7 +98,7 @@ def test_duplicate_codes_ties(oracle):
     base = oracle.gen_codes(3, 0, 0, 8)
     codes = base[np.random.default_rng(0).integers(0, 8, int(lens.sum()))]      # only 8 distinct code rows
     ref = oracle.RefIndex(A, pq, lens, centroids=Cm, codes=codes)
-    for mode in (1, 0):
+    for mode in (1, 3, 2):
         gpu = IvfPqIndex(nlist)
         gpu.set_opq(A); gpu.set_pq(pq); gpu.set_centroids(Cm); gpu.set_lists(lens, codes)
         gpu.nprobe = 4
@@ -108,7 +108,7 @@ def test_duplicate_codes_ties(oracle):
         Dr, Ir = ref.search(x, 20, 4)
         assert_topk_equal(D, I, Dr, Ir, f"ties mode={mode}")
         # canonical order inside a tie group: scan order (probe rank, offset) ascending == label ascending within a list
-        if mode == 0:
+        if mode != 1:
             flags = gpu.last_flags(6)
             assert flags.any(), "heavy ties must trip the exactness proof and take the exact fallback"
 
@@ -120,13 +120,15 @@ def test_device_tensor_api_and_fast_equals_exact(oracle):
     gpu.nprobe = 32
     x = near_queries(ref, 64, 7)
     xt = torch.from_numpy(x).cuda()
-    gpu.set_scan_mode(0)
-    D0, I0 = gpu.search(xt, 10)
-    flags = gpu.last_flags(64)
     gpu.set_scan_mode(1)
     D1, I1 = gpu.search(xt, 10)
-    assert torch.equal(D0, D1) and torch.equal(I0, I1)
-    assert flags.sum() == 0, "fast filter should prove exactness on generic data"
+    for mode in (3, 2, 0):
+        gpu.set_scan_mode(mode)
+        D0, I0 = gpu.search(xt, 10)
+        flags = gpu.last_flags(64)
+        assert torch.equal(D0, D1) and torch.equal(I0, I1), f"mode {mode}"
+        assert flags.sum() == 0, f"mode {mode}: the filter should prove exactness on generic data"
+        assert gpu.last_used_pair_mode() == (mode != 3)          # 64 queries x 32 probes over 128 lists -> auto picks pair
     Dr, Ir = ref.search(x, 10, 32)
     assert_topk_equal(D0.cpu().numpy(), I0.cpu().numpy(), Dr, Ir)
 
@@ -138,7 +140,7 @@ def test_golden_fixture_on_gpu():
     gd = os.path.join(os.path.dirname(__file__), "golden")
     g = np.load(os.path.join(gd, "ivfpq_small.npz"))
     meta = json.load(open(os.path.join(gd, "ivfpq_small.json")))
-    for mode in (0, 1):
+    for mode in (3, 2, 1):
         ix = IvfPqIndex(len(g["list_len"]))
         ix.set_opq(g["A"]); ix.set_pq(g["pq"]); ix.set_centroids(g["centroids"]); ix.set_lists(g["list_len"], g["codes"], g["ids"])
         ix.nprobe = meta["nprobe"]
@@ -164,9 +166,10 @@ def test_list_range_shards_on_one_device(oracle, nshards):
     xt = torch.from_numpy(x).cuda()
     k, nprobe = 10, 24
     parts = []
-    for lo, hi in shard_ranges(lens, nshards):
+    for si, (lo, hi) in enumerate(shard_ranges(lens, nshards)):
         _, sh = make_pair(oracle, nlist, lens, shard=(lo, hi))
         sh.nprobe = nprobe
+        sh.set_scan_mode(2 if si % 2 == 0 else 3)            # mix pair-packed and single-query shards
         parts.append(sh.search_partial(xt, k))
         assert sh.ntotal_local == int(lens[lo:hi].sum()) and sh.ntotal == int(lens.sum())
     Dg, Ig, Gg = (torch.stack([p[i] for p in parts]).contiguous() for i in range(3))
@@ -190,8 +193,9 @@ def test_mid_size_skewed_lists_and_large_k(oracle):
     ref, gpu = make_pair(oracle, nlist, lens)
     gpu.nprobe = 64
     x = near_queries(ref, 32, 5)
-    for k in (10, 400):                       # top_k up to 200 x2 in the reference (Makefile:490, model.py:79-81)
+    for k, mode in ((10, 2), (10, 3), (400, 2), (400, 0), (1024, 0)):   # top_k up to 200 x2 in the reference (Makefile:490, model.py:79-81)
+        gpu.set_scan_mode(mode)
         D, I = gpu.search(x, k)
         Dr, Ir = ref.search(x, k, 64)
-        assert_topk_equal(D, I, Dr, Ir, f"k={k}")
-    assert gpu.last_flags(32).sum() == 0
+        assert_topk_equal(D, I, Dr, Ir, f"k={k} mode={mode}")
+        assert gpu.last_flags(32).sum() == 0
