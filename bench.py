@@ -175,7 +175,7 @@ def run_reference(args):
             "config": config_dict(wl, args.gpus, "cpu"),
             "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     return 0
 
 
@@ -223,6 +223,11 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def stage(msg):
+        if rank == 0 and args.verbose:
+            print(f"[bench] {msg}", file=sys.stderr, flush=True)
+
+    stage("index built, queries made")
     # ---- device-resident timing (value) ----
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -242,6 +247,7 @@ def run_ours(args):
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     last_dev = (Dd.cpu().numpy(), Id.cpu().numpy())
+    stage(f"device pass done: {ms_dev / K:.3f} ms/step")
 
     # ---- end to end through the host API (pinned host in, host out) ----
     for s in range(W):
@@ -254,6 +260,7 @@ def run_ours(args):
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     assert np.array_equal(np.asarray(Dh), last_dev[0]) and np.array_equal(np.asarray(Ih), last_dev[1])
+    stage(f"e2e pass done: {ms_e2e / K:.3f} ms/step")
 
     # ---- roofline of the dominant kernel (PQ scan), CUDA events around the kernel itself ----
     # (a) algorithmic bytes of each timed batch (untimed pass), (b) the same K steps back to back with events around the scan
@@ -347,7 +354,8 @@ def run_ours(args):
                         "ms_per_step": ms_e2e / K},
                 "gpu_launches": K * (12 + (1 if world > 1 else 0)), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                 "exact_fallback_queries_last_batch": flags, "encoder": enc_info}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    del ix
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -357,10 +365,11 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="debug only: shrink the per-GPU index (the headline run uses 1.0)")
+    ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-encoder", action="store_true", help="skip the C3 encoder leg")
     args = ap.parse_args()

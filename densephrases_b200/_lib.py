@@ -42,6 +42,8 @@ _SIGS = {
     "dph_index_profile_count": (_i32, [_vp]),
     "dph_index_search": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i32]),
     "dph_index_search_partial": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "dph_index_coarse_local": (_i32, [_vp, _vp, _i64, _vp]),
+    "dph_index_search_preassigned": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
     "dph_merge_shards": (_i32, [_vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
     "dph_index_last_flags": (_vp, [_vp]),
     "dph_index_last_probes": (_vp, [_vp]),
@@ -56,6 +58,7 @@ _SIGS = {
     "dph_encoder_tower_floats": (_i64, [_vp]),
     "dph_encoder_load_tower": (_i32, [_vp, _i32, _vp, _i32]),
     "dph_encoder_embed_query": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32]),
+    "dph_sgemm_nt_seq": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _vp]),
     "dph_gemm_tf32_nt": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp]),
     "dph_encoder_set_precision": (_i32, [_vp, _i32]),
     "dph_index_window_scores": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _i32]),

@@ -304,7 +304,10 @@ DPH_API int dph_index_copy_last(dph_index* ix, int which, void* dst_host, int64_
 // -------------------------------------------------------------------------------------------------
 // search
 // -------------------------------------------------------------------------------------------------
-static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, float* D, int64_t* I, uint32_t* G) {
+// stage: 0 = whole search; 1 = only rotation + this shard's coarse candidates (keys64 out); 2 = everything after the coarse
+// quantizer, probes (key, cd) already in ix->key / ix->cd and rotated queries in ix->xr (sharded coarse quantizer, see sharded.py)
+static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, float* D, int64_t* I, uint32_t* G, int stage = 0,
+                        unsigned long long* keys64 = nullptr) {
     cudaStream_t st = ix->stream;
     const int nprobe = ix->nprobe;
     const int grid = ix->num_sms;
@@ -350,11 +353,21 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
         DPH_TRY(ix->pairwork.ensure(sizeof(DphPairWork)));
     }
     ix->last_n = n;
-    ix->last_pair = pair;
+    if (stage != 1) ix->last_pair = pair;
+    if (stage == 1) ix->last_coarse_n = n;
 
-    DPH_TRY(dph_launch_sgemm_nt_seq(x_dev, n, ix->A, ix->d, ix->d, ix->xr.as<float>(), st));                       // OPQ rotation
-    DPH_TRY(dph_launch_sgemm_nt_seq(ix->xr.as<float>(), n, ix->C, ix->nlist, ix->d, ix->S.as<float>(), st));       // coarse scores
-    DPH_TRY(dph_launch_coarse_select(ix->S.as<float>(), n, ix->nlist, nprobe, ix->key.as<int32_t>(), ix->cd.as<float>(), st));
+    if (stage == 1) {
+        const int64_t nl = ix->list_hi - ix->list_lo;
+        DPH_TRY(dph_launch_sgemm_nt_seq(x_dev, n, ix->A, ix->d, ix->d, ix->xr.as<float>(), st));                   // OPQ rotation
+        DPH_TRY(dph_launch_sgemm_nt_seq(ix->xr.as<float>(), n, ix->C + ix->list_lo * ix->d, nl, ix->d, ix->S.as<float>(), st));   // this shard's centroids only
+        DPH_TRY(dph_launch_coarse_select(ix->S.as<float>(), n, nl, nprobe, nullptr, nullptr, st, keys64, (unsigned)ix->list_lo));
+        return 0;
+    }
+    if (stage == 0) {
+        DPH_TRY(dph_launch_sgemm_nt_seq(x_dev, n, ix->A, ix->d, ix->d, ix->xr.as<float>(), st));                   // OPQ rotation
+        DPH_TRY(dph_launch_sgemm_nt_seq(ix->xr.as<float>(), n, ix->C, ix->nlist, ix->d, ix->S.as<float>(), st));   // coarse scores
+        DPH_TRY(dph_launch_coarse_select(ix->S.as<float>(), n, ix->nlist, nprobe, ix->key.as<int32_t>(), ix->cd.as<float>(), st));
+    }
     DPH_TRY(dph_launch_lut(ix->xr.as<float>(), n, ix->pq, ix->lut_scan.as<float>(), ix->lut_canon.as<float>(), ix->lutmax.as<float>(),
                            ix->lutmin.as<float>(), ix->lutmaxv.as<float>(), pair ? ix->lutq.as<unsigned short>() : nullptr,
                            pair ? ix->qparams.as<float2>() : nullptr, st));
@@ -400,6 +413,25 @@ DPH_API int dph_index_search_partial(dph_index* ix, const float* x_dev, int64_t 
         DPH_TRY(search_chunk(ix, x_dev + o * ix->d, m, k, D + o * k, I + o * k, G + o * k));
     }
     return 0;
+}
+
+// ---- sharded coarse quantizer (every rank scores only its own lists' centroids; SURVEY.md 8e "Partitioning") ----
+DPH_API int dph_index_coarse_local(dph_index* ix, const float* x_dev, int64_t n, uint64_t* keys_dev) {
+    DPH_TRY(check_ready(ix, 1));
+    DPH_CUDA(cudaSetDevice(ix->device));
+    DPH_CHECK(n <= chunk_size(ix, n), "coarse_local: batch too large for one chunk");
+    return search_chunk(ix, x_dev, n, 1, nullptr, nullptr, nullptr, 1, (unsigned long long*)keys_dev);
+}
+DPH_API int dph_index_search_preassigned(dph_index* ix, const uint64_t* keys_gathered_dev, int nshards, int64_t n, int k, float* D_dev,
+                                         int64_t* I_dev, uint32_t* G_dev) {
+    DPH_TRY(check_ready(ix, k));
+    DPH_CUDA(cudaSetDevice(ix->device));
+    DPH_CHECK(n == ix->last_coarse_n, "search_preassigned must follow coarse_local with the same batch");
+    DPH_TRY(ix->key.ensure((size_t)n * ix->nprobe * 4));
+    DPH_TRY(ix->cd.ensure((size_t)n * ix->nprobe * 4));
+    DPH_TRY(dph_launch_coarse_merge((const unsigned long long*)keys_gathered_dev, nshards, n, ix->nprobe, ix->key.as<int32_t>(), ix->cd.as<float>(),
+                                    ix->stream));
+    return search_chunk(ix, nullptr, n, k, D_dev, I_dev, G_dev, 2, nullptr);
 }
 
 DPH_API int dph_index_search(dph_index* ix, const float* x, int64_t n, int k, float* D, int64_t* I, int mem) {

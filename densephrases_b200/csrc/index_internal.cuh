@@ -62,6 +62,7 @@ struct dph_index {
         lutmin, lutmaxv, lutq, qparams, gdense, pl_cnt, pl_fill, pl_off, pl_blockpre, pl_entries, pairwork;
     int64_t last_n = 0;
     bool last_pair = false;
+    int64_t last_coarse_n = -1;
     bool profile = false;              // CUDA events around the scan kernel of the last search chunk
     cudaEvent_t ev0[DPH_PROF_RING] = {}, ev1[DPH_PROF_RING] = {};
     int64_t prof_n = 0;
@@ -69,7 +70,9 @@ struct dph_index {
 
 // ---- prep.cu ----
 int dph_launch_sgemm_nt_seq(const float* X, int64_t n, const float* W, int64_t m, int K, float* out, cudaStream_t st);
-int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprobe, int32_t* key, float* cd, cudaStream_t st);
+int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprobe, int32_t* key, float* cd, cudaStream_t st,
+                             unsigned long long* keys64 = nullptr, unsigned list_base = 0);
+int dph_launch_coarse_merge(const unsigned long long* keys, int W, int64_t n, int nprobe, int32_t* key, float* cd, cudaStream_t st);
 int dph_launch_lut(const float* xr, int64_t n, const float* pq, float* lut_scan, float* lut_canon, float* lutmax, float* lutmin, float* lutmaxv,
                    unsigned short* lutq, float2* qparams, cudaStream_t st);
 int dph_launch_plan(dph_index* ix, int64_t n, int k, int keep, int grid, const int32_t* only_flagged, cudaStream_t st, bool pair);

@@ -85,19 +85,21 @@ __global__ void __launch_bounds__(256) sgemm_nt_seq_kernel(const float* __restri
     }
 }
 
-// Same contract, 64x64 tile / 4x4 micro-tile: 4x the CTAs and a 4x shorter per-k-tile dependency chain -- used when the
-// 128x128 grid cannot fill the GPU (small query batches: the sequential-k definition forbids split-K).
+// Same contract, 64x64 tile / 4x4 micro-tile / 32-deep k tiles: 4x the CTAs, a 4x shorter per-k-step dependency chain and a
+// quarter of the (latency-bound) global-load round trips -- used when the 128x128 grid cannot fill the GPU (small query
+// batches; the sequential-k definition forbids split-K).
+#define GSK 32
 __global__ void __launch_bounds__(256) sgemm_nt_seq_small_kernel(const float* __restrict__ X, long long n, const float* __restrict__ W,
                                                                   long long m, int K, float* __restrict__ out) {
-    __shared__ __align__(16) float As[2][GBK][64];
-    __shared__ __align__(16) float Bs[2][GBK][64];
+    __shared__ __align__(16) float As[2][GSK][64];
+    __shared__ __align__(16) float Bs[2][GSK][64];
     const int tid = threadIdx.x;
     const long long row0 = (long long)blockIdx.y * 64, col0 = (long long)blockIdx.x * 64;
-    const int lr = tid & 63, lk4 = (tid >> 6) & 1, isB = tid >> 7;
-    const long long grow = (isB ? col0 : row0) + lr;
-    const bool ok = grow < (isB ? m : n);
-    const float4* gp = reinterpret_cast<const float4*>((isB ? W : X) + (ok ? grow : 0) * K) + lk4;
-    float (*dst)[GBK][64] = isB ? Bs : As;
+    const int lr = tid & 63, q4 = tid >> 6;                 // tile row, float4 slot along K (q4 and q4 + 4 of 8)
+    const long long arow = row0 + lr, brow = col0 + lr;
+    const bool aok = arow < n, bok = brow < m;
+    const float4* ap = reinterpret_cast<const float4*>(X + (aok ? arow : 0) * K) + q4;
+    const float4* bp = reinterpret_cast<const float4*>(W + (bok ? brow : 0) * K) + q4;
     const int tx = tid & 15, ty = tid >> 4;
     float acc[4][4];
 #pragma unroll
@@ -105,15 +107,25 @@ __global__ void __launch_bounds__(256) sgemm_nt_seq_small_kernel(const float* __
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 r = ok ? __ldg(gp) : z4;
-    const int ktiles = K / GBK;
+    float4 ra0 = aok ? __ldg(ap) : z4, ra1 = aok ? __ldg(ap + 4) : z4, rb0 = bok ? __ldg(bp) : z4, rb1 = bok ? __ldg(bp + 4) : z4;
+    const int ktiles = K / GSK;
     int buf = 0;
-    dst[0][lk4 * 4 + 0][lr] = r.x; dst[0][lk4 * 4 + 1][lr] = r.y; dst[0][lk4 * 4 + 2][lr] = r.z; dst[0][lk4 * 4 + 3][lr] = r.w;
+    auto stash = [&](int b) {
+        As[b][q4 * 4 + 0][lr] = ra0.x; As[b][q4 * 4 + 1][lr] = ra0.y; As[b][q4 * 4 + 2][lr] = ra0.z; As[b][q4 * 4 + 3][lr] = ra0.w;
+        As[b][16 + q4 * 4 + 0][lr] = ra1.x; As[b][16 + q4 * 4 + 1][lr] = ra1.y; As[b][16 + q4 * 4 + 2][lr] = ra1.z; As[b][16 + q4 * 4 + 3][lr] = ra1.w;
+        Bs[b][q4 * 4 + 0][lr] = rb0.x; Bs[b][q4 * 4 + 1][lr] = rb0.y; Bs[b][q4 * 4 + 2][lr] = rb0.z; Bs[b][q4 * 4 + 3][lr] = rb0.w;
+        Bs[b][16 + q4 * 4 + 0][lr] = rb1.x; Bs[b][16 + q4 * 4 + 1][lr] = rb1.y; Bs[b][16 + q4 * 4 + 2][lr] = rb1.z; Bs[b][16 + q4 * 4 + 3][lr] = rb1.w;
+    };
+    stash(0);
     __syncthreads();
     for (int kt = 0; kt < ktiles; kt++) {
-        if (kt + 1 < ktiles) r = ok ? __ldg(gp + (kt + 1) * 2) : z4;
+        if (kt + 1 < ktiles) {
+            const int o = (kt + 1) * 8;
+            ra0 = aok ? __ldg(ap + o) : z4; ra1 = aok ? __ldg(ap + o + 4) : z4;
+            rb0 = bok ? __ldg(bp + o) : z4; rb1 = bok ? __ldg(bp + o + 4) : z4;
+        }
 #pragma unroll
-        for (int k = 0; k < GBK; k++) {
+        for (int k = 0; k < GSK; k++) {
             const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
             const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
             const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
@@ -123,10 +135,9 @@ __global__ void __launch_bounds__(256) sgemm_nt_seq_small_kernel(const float* __
                 for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
         if (kt + 1 < ktiles) {
-            const int nb = buf ^ 1;
-            dst[nb][lk4 * 4 + 0][lr] = r.x; dst[nb][lk4 * 4 + 1][lr] = r.y; dst[nb][lk4 * 4 + 2][lr] = r.z; dst[nb][lk4 * 4 + 3][lr] = r.w;
+            stash(buf ^ 1);
             __syncthreads();
-            buf = nb;
+            buf ^= 1;
         }
     }
 #pragma unroll
@@ -145,7 +156,7 @@ __global__ void __launch_bounds__(256) sgemm_nt_seq_small_kernel(const float* __
 }
 
 int dph_launch_sgemm_nt_seq(const float* X, int64_t n, const float* W, int64_t m, int K, float* out, cudaStream_t st) {
-    DPH_CHECK(K % GBK == 0 && K % 4 == 0, "sgemm_nt_seq: K must be a multiple of 8");
+    DPH_CHECK(K % GSK == 0, "sgemm_nt_seq: K must be a multiple of 32");
     if (n == 0 || m == 0) return 0;
     dim3 grid((unsigned)((m + GBN - 1) / GBN), (unsigned)((n + GBM - 1) / GBM));
     if ((long long)grid.x * grid.y < 2 * 148) {
@@ -166,7 +177,8 @@ int dph_launch_sgemm_nt_seq(const float* X, int64_t n, const float* W, int64_t m
 //  ties is heap-dependent in faiss and canonicalised here.)
 // =================================================================================================
 __global__ void __launch_bounds__(256) coarse_select_kernel(const float* __restrict__ S, long long nlist, int nprobe,
-                                                             int* __restrict__ key, float* __restrict__ cd) {
+                                                             int* __restrict__ key, float* __restrict__ cd,
+                                                             unsigned long long* __restrict__ keys64, unsigned list_base) {
     __shared__ SelectScratch sc;
     __shared__ unsigned long long sel[DPH_MAX_NPROBE];
     __shared__ int cnt;
@@ -188,7 +200,11 @@ __global__ void __launch_bounds__(256) coarse_select_kernel(const float* __restr
     __syncthreads();
     block_bitonic_sort_desc(sel, p2);
     for (int r = tid; r < nprobe; r += blockDim.x) {
-        if (r < take) {
+        if (keys64) {      // sharded coarse quantizer: (score key, ~global list id); 0 = empty slot
+            unsigned long long k = r < take ? sel[r] : 0ull;
+            if (k) k = (k & 0xFFFFFFFF00000000ull) | (unsigned long long)(0xFFFFFFFFu - ((0xFFFFFFFFu - (unsigned)k) + list_base));
+            keys64[q * nprobe + r] = k;
+        } else if (r < take) {
             unsigned long long k = sel[r];
             key[q * nprobe + r] = (int)(0xFFFFFFFFu - (unsigned)k);
             cd[q * nprobe + r] = dph_fkey_inv((unsigned)(k >> 32));
@@ -199,11 +215,40 @@ __global__ void __launch_bounds__(256) coarse_select_kernel(const float* __restr
     }
 }
 
-int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprobe, int32_t* key, float* cd, cudaStream_t st) {
+// Merge of the per-shard coarse candidates (all-gathered): keys [W, n, nprobe] -> global top-nprobe per query,
+// (score desc, list asc) -- bit-identical to selecting over all lists at once, because every shard computes the
+// same sequential-FMA scores for its own lists.
+__global__ void __launch_bounds__(256) coarse_merge_kernel(const unsigned long long* __restrict__ keys, int W, long long n, int nprobe,
+                                                            int* __restrict__ key, float* __restrict__ cd) {
+    extern __shared__ unsigned long long cm[];
+    const long long q = blockIdx.x;
+    const int tot = W * nprobe, p2 = dph_next_pow2(tot);
+    for (int i = threadIdx.x; i < p2; i += blockDim.x) cm[i] = i < tot ? keys[((long long)(i / nprobe) * n + q) * nprobe + (i % nprobe)] : 0ull;
+    __syncthreads();
+    block_bitonic_sort_desc(cm, p2);
+    for (int r = threadIdx.x; r < nprobe; r += blockDim.x) {
+        const unsigned long long k = cm[r];
+        key[q * nprobe + r] = k ? (int)(0xFFFFFFFFu - (unsigned)k) : -1;
+        cd[q * nprobe + r] = k ? dph_fkey_inv((unsigned)(k >> 32)) : DPH_NEUTRAL;
+    }
+}
+int dph_launch_coarse_merge(const unsigned long long* keys, int W, int64_t n, int nprobe, int32_t* key, float* cd, cudaStream_t st) {
+    DPH_CHECK((long long)W * nprobe <= 8192, "coarse merge: world * nprobe must be <= 8192");
+    if (n == 0) return 0;
+    int p2 = 1; while (p2 < W * nprobe) p2 <<= 1;
+    static bool attr = false;
+    if (!attr) { DPH_CUDA(cudaFuncSetAttribute(coarse_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8)); attr = true; }
+    coarse_merge_kernel<<<(unsigned)n, 256, p2 * 8, st>>>(keys, W, n, nprobe, key, cd);
+    DPH_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprobe, int32_t* key, float* cd, cudaStream_t st,
+                             unsigned long long* keys64, unsigned list_base) {
     DPH_CHECK(nprobe >= 1 && nprobe <= DPH_MAX_NPROBE, "nprobe out of range [1,1024]");
     DPH_CHECK(nlist < (1ll << 31), "nlist too large");
     if (n == 0) return 0;
-    coarse_select_kernel<<<(unsigned)n, 256, 0, st>>>(S, nlist, nprobe, key, cd);
+    coarse_select_kernel<<<(unsigned)n, 256, 0, st>>>(S, nlist, nprobe, key, cd, keys64, list_base);
     DPH_CUDA(cudaGetLastError());
     return 0;
 }
@@ -554,4 +599,9 @@ int dph_launch_plan(dph_index* ix, int64_t n, int k, int keep, int grid, const i
     plan_scan_kernel<<<1, 1024, 0, st>>>(b);
     DPH_CUDA(cudaGetLastError());
     return 0;
+}
+
+// C ABI: out [n,m] = X [n,K] . W [m,K]^T with one sequential fp32 FMA chain per output (the oracle's inner-product definition).
+DPH_API int dph_sgemm_nt_seq(const float* X, int64_t n, const float* W, int64_t m, int64_t K, float* out, void* cuda_stream) {
+    return dph_launch_sgemm_nt_seq(X, n, W, m, (int)K, out, (cudaStream_t)cuda_stream);
 }

@@ -23,8 +23,8 @@ class IvfPqIndex:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
-            L.lib().dph_index_free(h)
+        if h and L is not None and getattr(L, "_lib", None) is not None:      # interpreter shutdown: the module may already be gone
+            L._lib.dph_index_free(h)
 
     @classmethod
     def from_arrays(cls, A, centroids, pq, list_len, codes, ids=None, device=0, shard=None):
@@ -160,6 +160,26 @@ class IvfPqIndex:
         G = torch.empty((n, k), dtype=torch.int32, device=x.device)
         self.set_stream(torch.cuda.current_stream(x.device).cuda_stream)
         L.check(L.lib().dph_index_search_partial(self._h, x.data_ptr(), n, k, D.data_ptr(), I.data_ptr(), G.data_ptr()))
+        return D, I, G
+
+    def coarse_local(self, x):
+        """torch cuda [n,d] -> int64 [n,nprobe] keys of this shard's best lists (score key << 32 | ~global list id)."""
+        import torch
+        n = x.shape[0]
+        keys = torch.empty((n, self.nprobe), dtype=torch.int64, device=x.device)
+        self.set_stream(torch.cuda.current_stream(x.device).cuda_stream)
+        L.check(L.lib().dph_index_coarse_local(self._h, x.data_ptr(), n, keys.data_ptr()))
+        return keys
+
+    def search_preassigned(self, keys_gathered, k):
+        """all-gathered keys [nshards,n,nprobe] -> this shard's partial (D, I, G) for the batch passed to coarse_local."""
+        import torch
+        W, n, _ = keys_gathered.shape
+        D = torch.empty((n, k), dtype=torch.float32, device=keys_gathered.device)
+        I = torch.empty((n, k), dtype=torch.int64, device=keys_gathered.device)
+        G = torch.empty((n, k), dtype=torch.int32, device=keys_gathered.device)
+        self.set_stream(torch.cuda.current_stream(keys_gathered.device).cuda_stream)
+        L.check(L.lib().dph_index_search_preassigned(self._h, keys_gathered.data_ptr(), W, n, k, D.data_ptr(), I.data_ptr(), G.data_ptr()))
         return D, I, G
 
     def _last(self, which, shape, dtype):

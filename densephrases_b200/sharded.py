@@ -71,7 +71,17 @@ class ShardedIvfPq:
         """x torch cuda [n,d] (same on every rank) -> (D, I) torch cuda [n,k] (same on every rank)."""
         if self.world == 1:
             return self.local.search(x, k)
-        D, I, G = self.local.search_partial(x, k)
+        import torch.distributed as dist
+        n = x.shape[0]
+        if n > 4096:        # one chunk per collective round
+            parts = [self.search_device(x[i:i + 4096], k) for i in range(0, n, 4096)]
+            return torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
+        # exchange 1: every rank scores only its own centroids; all-gather the per-shard best-nprobe keys
+        keys = self.local.coarse_local(x)
+        keys_g = torch.empty((self.world * n, keys.shape[1]), dtype=torch.int64, device=x.device)
+        dist.all_gather_into_tensor(keys_g, keys, group=self.group)
+        D, I, G = self.local.search_preassigned(keys_g.view(self.world, n, -1), k)
+        # exchange 2: per-shard partial top-k
         return gather_and_merge(D, I, G, k, self.world, self.group)
 
     def search(self, x, k):

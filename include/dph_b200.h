@@ -87,6 +87,13 @@ int dph_index_search(dph_index* ix, const float* x, int64_t n, int k, float* D, 
  * global over all shards).  Buffers on device.  After an all-gather over shards feed dph_merge_shards. */
 int dph_index_search_partial(dph_index* ix, const float* x_dev, int64_t n, int k, float* D_dev, int64_t* I_dev,
                              uint32_t* G_dev);
+/* Sharded coarse quantizer (scales the IndexFlatIP coarse search with the number of shards): every shard scores only its own
+ * lists' centroids and emits its best nprobe as keys (score key << 32 | ~global list id, 0 = empty) [n,nprobe];
+ * after an all-gather of the keys [nshards,n,nprobe], search_preassigned merges them into the global top-nprobe (identical to
+ * the unsharded selection) and runs the rest of the search on this shard's lists.  n must fit one chunk (<= 4096). */
+int dph_index_coarse_local(dph_index* ix, const float* x_dev, int64_t n, uint64_t* keys_dev);
+int dph_index_search_preassigned(dph_index* ix, const uint64_t* keys_gathered_dev, int nshards, int64_t n, int k, float* D_dev,
+                                 int64_t* I_dev, uint32_t* G_dev);
 /* Dg/Ig/Gg [nshards,n,k] (all-gathered, device) -> D/I [n,k] (device).  Order: score desc, scan position asc. */
 int dph_merge_shards(const float* Dg, const int64_t* Ig, const uint32_t* Gg, int nshards, int64_t n, int k, float* D,
                      int64_t* I, void* cuda_stream);
@@ -130,6 +137,10 @@ int dph_encoder_set_precision(dph_encoder* e, int precise);
  * position 0 of each tower (the reference returns them as [B,1,768]). */
 int dph_encoder_embed_query(dph_encoder* e, const int64_t* input_ids, const int64_t* attention_mask, const int64_t* token_type_ids,
                             int B, int S, float* start_out, float* end_out, int mem);
+
+/* ---- exact sequential-k fp32 GEMM (the inner-product definition shared with the oracle): out [n,m] = X [n,K] . W [m,K]^T,
+ * acc = fmaf(x[t], w[t], acc) for t ascending; device pointers; K % 32 == 0.  Used for the OPQ rotation and the coarse quantizer. */
+int dph_sgemm_nt_seq(const float* X, int64_t n, const float* W, int64_t m, int64_t K, float* out, void* cuda_stream);
 
 /* ---- dense fp32 GEMM on the tcgen05 tensor cores (kind::tf32), the encoder's building block ----
  * out [M,N] = act(A [M,K] . W [N,K]^T + bias [N]) + residual [M,N]; act: 0 none, 1 erf-GELU; device pointers;

@@ -165,13 +165,19 @@ def test_list_range_shards_on_one_device(oracle, nshards):
     x = near_queries(ref, 40, 12)
     xt = torch.from_numpy(x).cuda()
     k, nprobe = 10, 24
-    parts = []
+    shards = []
     for si, (lo, hi) in enumerate(shard_ranges(lens, nshards)):
         _, sh = make_pair(oracle, nlist, lens, shard=(lo, hi))
         sh.nprobe = nprobe
         sh.set_scan_mode(2 if si % 2 == 0 else 3)            # mix pair-packed and single-query shards
-        parts.append(sh.search_partial(xt, k))
         assert sh.ntotal_local == int(lens[lo:hi].sum()) and sh.ntotal == int(lens.sum())
+        shards.append(sh)
+    if nshards == 2:      # replicated coarse quantizer: every shard selects the global probes itself
+        parts = [sh.search_partial(xt, k) for sh in shards]
+    else:                 # sharded coarse quantizer: per-shard candidates -> "all-gather" -> merge -> preassigned search
+        keys_g = torch.stack([sh.coarse_local(xt) for sh in shards]).contiguous()
+        parts = [sh.search_preassigned(keys_g, k) for sh in shards]
+        assert np.array_equal(shards[0].last_probes(len(x)), ref.search(x, k, nprobe, return_key=True)[2].astype(np.int32))
     Dg, Ig, Gg = (torch.stack([p[i] for p in parts]).contiguous() for i in range(3))
     D, I = merge_shards(Dg, Ig, Gg, k)
     Dr, Ir = ref.search(x, k, nprobe)
