@@ -365,7 +365,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=None, help="default: 100 (ours), 10 (--impl reference: each step is ~1.5 s of all-core CPU work)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="debug only: shrink the per-GPU index (the headline run uses 1.0)")
@@ -374,6 +374,8 @@ def main():
     ap.add_argument("--no-encoder", action="store_true", help="skip the C3 encoder leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.steps is None:
+        args.steps = 10 if args.impl == "reference" else 100
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 
 
