@@ -330,7 +330,10 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
     DPH_TRY(ix->nseg.ensure((size_t)n * 4));
     // pair mode (two queries per gather) pays when lists are probed by >= ~1.5 queries of the batch on average
     const int64_t eff_probe = std::min<int64_t>(nprobe, ix->nlist);
-    bool pair = ix->scan_mode == DPH_SCAN_PAIR || (ix->scan_mode == DPH_SCAN_FAST && n * eff_probe * 2 >= ix->nlist * 3);
+    // ... and when lists are long enough to amortise rebuilding the packed 192 KB LUT at every (list, pair) item
+    const int64_t nl_local = std::max<int64_t>(ix->list_hi - ix->list_lo, 1);
+    const bool long_lists = ix->ntotal_local / nl_local >= 4096;
+    bool pair = ix->scan_mode == DPH_SCAN_PAIR || (ix->scan_mode == DPH_SCAN_FAST && long_lists && n * eff_probe * 2 >= ix->nlist * 3);
     if (keep_pair > 1536 - DPH_SCAN_THREADS || ix->scan_mode == DPH_SCAN_SINGLE) pair = false;
     const int keep_fast = pair ? keep_pair : keep_single;
     DPH_TRY(ix->cand.ensure(((size_t)(2 * grid + 2 * n + 2) + (pair ? (size_t)(3 * n * nprobe + 3 * grid + n + 16) : 0)) * keep_max * 8));
