@@ -45,6 +45,8 @@ _SIGS = {
     "dph_index_coarse_local": (_i32, [_vp, _vp, _i64, _vp]),
     "dph_index_search_preassigned": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
     "dph_merge_shards": (_i32, [_vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
+    "dph_pack_topk": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "dph_merge_shards_packed": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _vp]),
     "dph_index_last_flags": (_vp, [_vp]),
     "dph_index_last_probes": (_vp, [_vp]),
     "dph_index_last_coarse": (_vp, [_vp]),

@@ -320,7 +320,6 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
     DPH_TRY(ix->S.ensure((size_t)n * ix->nlist * 4));
     DPH_TRY(ix->key.ensure((size_t)n * nprobe * 4));
     DPH_TRY(ix->cd.ensure((size_t)n * nprobe * 4));
-    DPH_TRY(ix->lut_scan.ensure((size_t)n * DPH_LUT_SCAN_FLOATS * 4));
     DPH_TRY(ix->lut_canon.ensure((size_t)n * DPH_LUT_CANON_FLOATS * 4));
     DPH_TRY(ix->lutmax.ensure((size_t)n * DPH_M * 4));
     DPH_TRY(ix->segs.ensure((size_t)n * nprobe * sizeof(DphSeg)));
@@ -336,6 +335,7 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
     bool pair = ix->scan_mode == DPH_SCAN_PAIR || (ix->scan_mode == DPH_SCAN_FAST && long_lists && n * eff_probe * 2 >= ix->nlist * 3);
     if (keep_pair > 1536 - DPH_SCAN_THREADS || ix->scan_mode == DPH_SCAN_SINGLE) pair = false;
     const int keep_fast = pair ? keep_pair : keep_single;
+    if (!pair) DPH_TRY(ix->lut_scan.ensure((size_t)n * DPH_LUT_SCAN_FLOATS * 4));
     DPH_TRY(ix->cand.ensure(((size_t)(2 * grid + 2 * n + 2) + (pair ? (size_t)(3 * n * nprobe + 3 * grid + n + 16) : 0)) * keep_max * 8));
     DPH_TRY(ix->cand_off.ensure((size_t)(n + 1) * 8));
     DPH_TRY(ix->cand_cnt.ensure((size_t)n * 4));
@@ -371,7 +371,7 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
         DPH_TRY(dph_launch_sgemm_nt_seq(ix->xr.as<float>(), n, ix->C, ix->nlist, ix->d, ix->S.as<float>(), st));   // coarse scores
         DPH_TRY(dph_launch_coarse_select(ix->S.as<float>(), n, ix->nlist, nprobe, ix->key.as<int32_t>(), ix->cd.as<float>(), st));
     }
-    DPH_TRY(dph_launch_lut(ix->xr.as<float>(), n, ix->pq, ix->lut_scan.as<float>(), ix->lut_canon.as<float>(), ix->lutmax.as<float>(),
+    DPH_TRY(dph_launch_lut(ix->xr.as<float>(), n, ix->pq, pair ? nullptr : ix->lut_scan.as<float>(), ix->lut_canon.as<float>(), ix->lutmax.as<float>(),
                            ix->lutmin.as<float>(), ix->lutmaxv.as<float>(), pair ? ix->lutq.as<unsigned short>() : nullptr,
                            pair ? ix->qparams.as<float2>() : nullptr, st));
     if (ix->scan_mode != DPH_SCAN_EXACT) {
@@ -530,8 +530,59 @@ DPH_API int dph_index_reconstruct_batch(dph_index* ix, const int64_t* ids, int64
     return 0;
 }
 
+// ---- fused phrase-window scoring: score[i,l] = <q[i], R^T-unrotated reconstruct(first_id[i] + l)> --------------
+// The reference reconstructs every window vector, multiplies by R and dots with the query (index.py:282-300,338-343,363-368).
+// Here the query is rotated once (xq = A q, sequential-k SGEMM) and dotted with centroid + PQ decode on the fly:
+// <q, A^T v> == <A q, v>.  A label that is not in this shard/index contributes 0 (the reference's zero vector).
+__global__ void __launch_bounds__(96) window_scores_kernel(LocateArgs la, const float* __restrict__ xq, const long long* __restrict__ first_id,
+                                                            int L, const uint8_t* __restrict__ codes, const float* __restrict__ C,
+                                                            const float* __restrict__ pq, float* __restrict__ out) {
+    const long long i = blockIdx.x;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    __shared__ long long s_l, s_prow; __shared__ int s_ok; __shared__ float red[3];
+    const float4* xp = reinterpret_cast<const float4*>(xq + i * DPH_D + t * 8);
+    const float4 x0 = xp[0], x1 = xp[1];
+    for (int w = 0; w < L; w++) {
+        if (t == 0) { long long l = 0, pr = 0; s_ok = locate_label(la, first_id[i] + w, l, pr) ? 1 : 0; s_l = l; s_prow = pr; }
+        __syncthreads();
+        float part = 0.f;
+        if (s_ok) {
+            const long long blk = s_prow >> 5; const int ln = (int)(s_prow & 31);
+            const unsigned char code = codes[blk * DPH_BLK_BYTES + dph_blk_addr(ln, t)];
+            const float4* cb = reinterpret_cast<const float4*>(pq + ((size_t)t * 256 + code) * 8);
+            const float4* ce = reinterpret_cast<const float4*>(C + s_l * DPH_D + t * 8);
+            const float4 a0 = cb[0], a1 = cb[1], c0 = ce[0], c1 = ce[1];
+            part = fmaf(x0.x, a0.x + c0.x, part); part = fmaf(x0.y, a0.y + c0.y, part); part = fmaf(x0.z, a0.z + c0.z, part); part = fmaf(x0.w, a0.w + c0.w, part);
+            part = fmaf(x1.x, a1.x + c1.x, part); part = fmaf(x1.y, a1.y + c1.y, part); part = fmaf(x1.z, a1.z + c1.z, part); part = fmaf(x1.w, a1.w + c1.w, part);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+        if (lane == 0) red[warp] = part;
+        __syncthreads();
+        if (t == 0) out[i * L + w] = (red[0] + red[1]) + red[2];
+        __syncthreads();
+    }
+}
+
 DPH_API int dph_index_window_scores(dph_index* ix, const float* q, const int64_t* first_id, int64_t m, int L, float* out_scores, int mem) {
-    (void)ix; (void)q; (void)first_id; (void)m; (void)L; (void)out_scores; (void)mem;
-    dph_set_error("dph_index_window_scores: not built yet (SURVEY 8f #1)");
-    return 1;
+    DPH_TRY(check_ready(ix, 1));
+    DPH_CHECK(L >= 1 && L <= 64, "window length out of range");
+    DPH_CUDA(cudaSetDevice(ix->device));
+    if (m == 0) return 0;
+    DevBuf tq, tid, tout, txq;
+    const float* dq = q; const int64_t* did = first_id; float* dout = out_scores;
+    if (mem == DPH_MEM_HOST) {
+        DPH_TRY(tq.ensure((size_t)m * ix->d * 4)); DPH_TRY(tid.ensure((size_t)m * 8)); DPH_TRY(tout.ensure((size_t)m * L * 4));
+        DPH_CUDA(cudaMemcpyAsync(tq.p, q, (size_t)m * ix->d * 4, cudaMemcpyHostToDevice, ix->stream));
+        DPH_CUDA(cudaMemcpyAsync(tid.p, first_id, (size_t)m * 8, cudaMemcpyHostToDevice, ix->stream));
+        dq = tq.as<float>(); did = tid.as<int64_t>(); dout = tout.as<float>();
+    }
+    DPH_TRY(txq.ensure((size_t)m * ix->d * 4));
+    DPH_TRY(dph_launch_sgemm_nt_seq(dq, m, ix->A, ix->d, ix->d, txq.as<float>(), ix->stream));          // xq = A q
+    window_scores_kernel<<<(unsigned)m, 96, 0, ix->stream>>>(make_locate(ix), txq.as<float>(), (const long long*)did, L, ix->codes, ix->C, ix->pq, dout);
+    DPH_CUDA(cudaGetLastError());
+    if (mem == DPH_MEM_HOST) DPH_CUDA(cudaMemcpyAsync(out_scores, dout, (size_t)m * L * 4, cudaMemcpyDeviceToHost, ix->stream));
+    DPH_CUDA(cudaStreamSynchronize(ix->stream));
+    tq.release(); tid.release(); tout.release(); txq.release();
+    return 0;
 }

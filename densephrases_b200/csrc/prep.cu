@@ -299,6 +299,7 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ xr, 
         lutmin[q * DPH_M + seg * 32 + j] = lo;
         lutmaxv[q * DPH_M + seg * 32 + j] = hi;
     }
+    if (lut_scan == nullptr) return;          // pair mode scans the quantised table (lutq_kernel) instead
     float* dst = lut_scan + ((size_t)q * 3 + seg) * (256 * 64);
     for (int idx = j; idx < 256 * 64; idx += 256) {
         int row = idx >> 6, w = idx & 63;

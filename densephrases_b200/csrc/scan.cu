@@ -620,6 +620,60 @@ int dph_launch_merge(dph_index* ix, int64_t n, int k, int mode, const int32_t* o
 }
 
 // =================================================================================================
+// pack / merge of the per-shard partial top-k for ONE all-gather:  P[q][i] = { ckey(score, scan position), label }.
+// =================================================================================================
+__global__ void pack_topk_kernel(const float* D, const long long* I, const unsigned* G, long long total, longlong2* P) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    longlong2 v;
+    v.x = I[i] >= 0 ? (long long)dph_ckey(D[i], G[i]) : 0ll;
+    v.y = I[i];
+    P[i] = v;
+}
+__global__ void __launch_bounds__(256) merge_packed_kernel(const longlong2* Pg, int nshards, long long n, int k, float* D, long long* I) {
+    extern __shared__ unsigned long long mp[];      // [p2] keys, then [p2] labels
+    const long long q = blockIdx.x;
+    const int tot = nshards * k, p2 = dph_next_pow2(tot);
+    unsigned long long* keys = mp;
+    for (int i = threadIdx.x; i < p2; i += blockDim.x) {
+        unsigned long long key = 0ull;
+        if (i < tot) key = (unsigned long long)Pg[((long long)(i / k) * n + q) * k + (i % k)].x;
+        keys[i] = key;
+    }
+    __syncthreads();
+    block_bitonic_sort_desc(keys, p2);
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        float d = DPH_NEUTRAL; long long id = -1;
+        const unsigned long long key = keys[i];
+        if (key != 0ull) {
+            d = dph_ckey_score(key);
+            for (int j = 0; j < tot && id < 0; j++) {          // scan positions are unique per query: find the owner (<= nshards*k entries)
+                const longlong2 e = Pg[((long long)(j / k) * n + q) * k + (j % k)];
+                if ((unsigned long long)e.x == key) id = e.y;
+            }
+        }
+        D[q * k + i] = d; I[q * k + i] = id;
+    }
+}
+DPH_API int dph_pack_topk(const float* D, const int64_t* I, const uint32_t* G, int64_t n, int k, int64_t* P, void* cuda_stream) {
+    const long long total = (long long)n * k;
+    if (total == 0) return 0;
+    pack_topk_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(D, (const long long*)I, G, total, (longlong2*)P);
+    DPH_CUDA(cudaGetLastError());
+    return 0;
+}
+DPH_API int dph_merge_shards_packed(const int64_t* Pg, int nshards, int64_t n, int k, float* D, int64_t* I, void* cuda_stream) {
+    if (n == 0) return 0;
+    DPH_CHECK(nshards >= 1 && k >= 1 && (long long)nshards * k <= 8192, "merge_shards: nshards*k must be <= 8192");
+    int p2 = 1; while (p2 < nshards * k) p2 <<= 1;
+    static bool attr = false;
+    if (!attr) { DPH_CUDA(cudaFuncSetAttribute(merge_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8)); attr = true; }
+    merge_packed_kernel<<<(unsigned)n, 256, p2 * 8, (cudaStream_t)cuda_stream>>>((const longlong2*)Pg, nshards, n, k, D, (long long*)I);
+    DPH_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =================================================================================================
 // merge_shards: all-gathered per-shard top-k -> global top-k, order (score desc, scan position asc).
 // =================================================================================================
 __global__ void __launch_bounds__(256) merge_shards_kernel(const float* Dg, const long long* Ig, const unsigned* Gg, int nshards, long long n,

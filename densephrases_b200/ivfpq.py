@@ -217,6 +217,20 @@ class IvfPqIndex:
         return out, found
 
 
+def _window_scores(self, q, first_ids, L):
+    """q [m,768] f32, first_ids [m] int64 (numpy) -> scores [m,L] f32: <q[i], un-rotated reconstruct(first_ids[i] + l)>;
+    labels that are not in the index score 0 (the reference's zero vector, index.py:287-288)."""
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    first_ids = np.ascontiguousarray(first_ids, dtype=np.int64)
+    out = np.empty((len(first_ids), L), dtype=np.float32)
+    L_.check(L_.lib().dph_index_window_scores(self._h, _np_ptr(q), _np_ptr(first_ids), len(first_ids), L, _np_ptr(out), L_.MEM_HOST))
+    return out
+
+
+L_ = L
+IvfPqIndex.window_scores = _window_scores
+
+
 def merge_shards(Dg, Ig, Gg, k):
     """all-gathered [nshards,n,k] torch cuda tensors -> (D, I) [n,k]; order score desc, scan position asc."""
     import torch
@@ -226,4 +240,25 @@ def merge_shards(Dg, Ig, Gg, k):
     I = torch.empty((n, k), dtype=torch.int64, device=Dg.device)
     st = torch.cuda.current_stream(Dg.device).cuda_stream
     L.check(L.lib().dph_merge_shards(Dg.data_ptr(), Ig.data_ptr(), Gg.data_ptr(), nsh, n, k, D.data_ptr(), I.data_ptr(), C.c_void_p(st)))
+    return D, I
+
+
+def pack_topk(D, I, G):
+    """(D f32, I i64, G i32) [n,k] cuda -> P int64 [n,k,2] for a single all-gather."""
+    import torch
+    n, k = D.shape
+    P = torch.empty((n, k, 2), dtype=torch.int64, device=D.device)
+    st = torch.cuda.current_stream(D.device).cuda_stream
+    L.check(L.lib().dph_pack_topk(D.data_ptr(), I.data_ptr(), G.data_ptr(), n, k, P.data_ptr(), C.c_void_p(st)))
+    return P
+
+
+def merge_shards_packed(Pg, k):
+    """all-gathered P [nshards,n,k,2] -> (D, I) [n,k]."""
+    import torch
+    nsh, n = Pg.shape[0], Pg.shape[1]
+    D = torch.empty((n, k), dtype=torch.float32, device=Pg.device)
+    I = torch.empty((n, k), dtype=torch.int64, device=Pg.device)
+    st = torch.cuda.current_stream(Pg.device).cuda_stream
+    L.check(L.lib().dph_merge_shards_packed(Pg.data_ptr(), nsh, n, k, D.data_ptr(), I.data_ptr(), C.c_void_p(st)))
     return D, I

@@ -210,15 +210,21 @@ class MIPS(object):
         span = np.arange(L, dtype=np.int64)
         fwd_labels = s_lab.astype(np.int64)[:, None] + span              # [start, start+L)        (index.py:284)
         bwd_labels = e_lab.astype(np.int64)[:, None] - (L - 1) + span    # (end-L, end]            (index.py:294)
-        vecs, _ = self.reconst_batch(np.concatenate([fwd_labels.ravel(), bwd_labels.ravel()]))   # missing label -> zeros
-        vecs = np.asarray(vecs, dtype=np.float32)
-        fwd, bwd = vecs[:H * L].reshape(H, L, -1), vecs[H * L:].reshape(H, L, -1)
+        fused = (not return_idxs) and hasattr(self.index, 'window_scores')
+        if fused:   # one CUDA call per direction: reconstruct + un-rotate + dot fused (libdph_b200: dph_index_window_scores)
+            end_sc = self.index.window_scores(q_end, fwd_labels[:, 0], L)
+            start_sc = self.index.window_scores(q_start, bwd_labels[:, 0], L)
+        else:
+            vecs, _ = self.reconst_batch(np.concatenate([fwd_labels.ravel(), bwd_labels.ravel()]))   # missing label -> zeros
+            vecs = np.asarray(vecs, dtype=np.float32)
+            fwd, bwd = vecs[:H * L].reshape(H, L, -1), vecs[H * L:].reshape(H, L, -1)
         logger.debug(f'1) {time()-tic:.3f}s: reconstruct vecs')
 
         tic = time()
         cand_end = s_word[:, None] + span                                # end word candidates for each start hit
         ok_end = packed.windows(s_doc, np.broadcast_to(s_word[:, None], cand_end.shape), cand_end, L)
-        end_sc, fwd_unrot = self._unrotated_scores(fwd, q_end)
+        if not fused:
+            end_sc, fwd_unrot = self._unrotated_scores(fwd, q_end)
         score_se = s_sc[:, None] + end_sc + np.where(ok_end, 0.0, _MASKED)
         pick_e = score_se.argmax(1)
         best_end = np.where(ok_end, cand_end, -1)[np.arange(H), pick_e]
@@ -227,7 +233,8 @@ class MIPS(object):
         tic = time()
         cand_start = e_word[:, None] - (L - 1) + span                    # start word candidates for each end hit
         ok_start = packed.windows(e_doc, cand_start, np.broadcast_to(e_word[:, None], cand_start.shape), L)
-        start_sc, bwd_unrot = self._unrotated_scores(bwd, q_start)
+        if not fused:
+            start_sc, bwd_unrot = self._unrotated_scores(bwd, q_start)
         score_es = start_sc + e_sc[:, None] + np.where(ok_start, 0.0, _MASKED)
         pick_s = score_es.argmax(1)
         best_start = np.where(ok_start, cand_start, -1)[np.arange(H), pick_s]

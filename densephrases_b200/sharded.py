@@ -5,7 +5,7 @@ With world_size 1 it degenerates to IvfPqIndex.  This is the call a user (MIPS.s
 import numpy as np
 import torch
 
-from .ivfpq import IvfPqIndex, merge_shards
+from .ivfpq import IvfPqIndex, merge_shards, merge_shards_packed, pack_topk
 
 
 def shard_ranges(list_len, world):
@@ -81,8 +81,11 @@ class ShardedIvfPq:
         keys_g = torch.empty((self.world * n, keys.shape[1]), dtype=torch.int64, device=x.device)
         dist.all_gather_into_tensor(keys_g, keys, group=self.group)
         D, I, G = self.local.search_preassigned(keys_g.view(self.world, n, -1), k)
-        # exchange 2: per-shard partial top-k
-        return gather_and_merge(D, I, G, k, self.world, self.group)
+        # exchange 2: per-shard partial top-k, packed into one buffer
+        P = pack_topk(D, I, G)
+        Pg = torch.empty((self.world * n, k, 2), dtype=torch.int64, device=x.device)
+        dist.all_gather_into_tensor(Pg, P, group=self.group)
+        return merge_shards_packed(Pg.view(self.world, n, k, 2), k)
 
     def search(self, x, k):
         """Host API == faiss index.search (index.py:200): numpy / pinned CPU tensor [n,d] -> numpy (D, I)."""

@@ -97,6 +97,10 @@ int dph_index_search_preassigned(dph_index* ix, const uint64_t* keys_gathered_de
 /* Dg/Ig/Gg [nshards,n,k] (all-gathered, device) -> D/I [n,k] (device).  Order: score desc, scan position asc. */
 int dph_merge_shards(const float* Dg, const int64_t* Ig, const uint32_t* Gg, int nshards, int64_t n, int k, float* D,
                      int64_t* I, void* cuda_stream);
+/* Same exchange as ONE buffer: pack (D, I, G) [n,k] into P [n,k,2] int64 = {candidate key (score, scan position), label};
+ * all-gather P; merge Pg [nshards,n,k,2] -> D/I [n,k]. */
+int dph_pack_topk(const float* D, const int64_t* I, const uint32_t* G, int64_t n, int k, int64_t* P, void* cuda_stream);
+int dph_merge_shards_packed(const int64_t* Pg, int nshards, int64_t n, int k, float* D, int64_t* I, void* cuda_stream);
 /* Per-query flags of the last search (device pointer, int32 [n]): bit0 = fast filter could not prove
  * exactness and the query was re-run through the exact kernel. */
 const int32_t* dph_index_last_flags(const dph_index* ix);

@@ -107,3 +107,26 @@ def test_mips_end_to_end_on_gpu(oracle):
     refs = ref_search(ref, idx_f, doc_groups, query, top_k=10, nprobe=256, aggregate=True, agg_strat='opt1', return_idxs=True,
                       normalize_answer=normalize_answer)
     compare(outs, refs, vec_tol=1e-3)
+
+
+@pytest.mark.gpu
+def test_fused_window_scores_match_reconstruct_path(oracle):
+    """dph_index_window_scores (fused reconstruct + un-rotate + dot) == reconstruct_batch + R matmul + dot; missing labels -> 0."""
+    from densephrases_b200 import IvfPqIndex
+    from densephrases_b200.mips import MIPS, normalize_answer
+    from oracle.mips_ref import ref_search
+    doc_groups, idx_f, (A, pq, Cm, list_len, codes, ids), ref, query = build(oracle, n_docs=25)
+    index = IvfPqIndex.from_arrays(A, Cm, pq, list_len, codes, ids)
+    rng = np.random.default_rng(0)
+    first = np.concatenate([rng.integers(0, ref.ntotal, 40), [-3, ref.ntotal - 2, ref.ntotal + 7]]).astype(np.int64)
+    q = rng.standard_normal((len(first), 768)).astype(np.float32)
+    got = index.window_scores(q, first, 10)
+    lab = (first[:, None] + np.arange(10)[None, :]).ravel()
+    vec, found = ref.reconstruct(lab)
+    want = ((vec.astype(np.float64) @ A.astype(np.float64)).reshape(len(first), 10, 768) * q[:, None, :].astype(np.float64)).sum(2)
+    assert np.abs(got - want).max() < 1e-3 * max(1.0, np.abs(want).max())
+    assert (got.ravel()[found == 0] == 0).all()
+    mips = MIPS.from_components(index, idx_f, doc_groups, cuda=True)
+    outs = mips.search(query, q_texts=['q'] * len(query), top_k=10, aggregate=True, agg_strat='opt1', return_idxs=False)      # fused path
+    refs = ref_search(ref, idx_f, doc_groups, query, top_k=10, nprobe=256, aggregate=True, agg_strat='opt1', normalize_answer=normalize_answer)
+    compare(outs, refs)

@@ -180,6 +180,9 @@ def test_list_range_shards_on_one_device(oracle, nshards):
         assert np.array_equal(shards[0].last_probes(len(x)), ref.search(x, k, nprobe, return_key=True)[2].astype(np.int32))
     Dg, Ig, Gg = (torch.stack([p[i] for p in parts]).contiguous() for i in range(3))
     D, I = merge_shards(Dg, Ig, Gg, k)
+    from densephrases_b200.ivfpq import merge_shards_packed, pack_topk
+    D2, I2 = merge_shards_packed(torch.stack([pack_topk(*p) for p in parts]).contiguous(), k)      # the single-buffer exchange
+    assert torch.equal(D, D2) and torch.equal(I, I2)
     Dr, Ir = ref.search(x, k, nprobe)
     assert_topk_equal(D.cpu().numpy(), I.cpu().numpy(), Dr, Ir, "sharded")
     # a label that lives in another shard reconstructs to zeros + found=0 on this shard; the sum over shards is the vector
