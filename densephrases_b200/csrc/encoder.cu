@@ -177,6 +177,114 @@ __global__ void __launch_bounds__(256) attention_kernel(AttnArgs a) {
     }
 }
 
+// ---- register-tiled attention for S <= 128 (the query path: max_query_length 24/32/64, options.py:38, Makefile:441) ----------------
+// One CTA per (head x 64-row tile, batch row, tower), 256 threads as 16 x 16: thread (ty,tx) owns rows 4ty..4ty+3 and keys
+// tx + 16 c (c < KT) of the score tile, then rows 4ty.. and dims 4tx..4tx+3 of the context tile.  Q and K are staged transposed
+// ([d][row]) so every inner step is two LDS.128 for 16 (scores) / 16 (context) FMAs; the softmax row reduction is a 16-lane
+// shuffle.  Same arithmetic as the reference: scores/8 + (1-mask)*-10000, fp32 softmax, P V.
+template <int KT>
+__global__ void __launch_bounds__(256) attention_tile_kernel(AttnArgs a) {
+    extern __shared__ __align__(16) float asm2_[];
+    constexpr int SP = 16 * KT;                       // padded key count
+    const int S = a.S, h = blockIdx.x % ENC_HEADS, rt = blockIdx.x / ENC_HEADS, b = blockIdx.y, tw = blockIdx.z;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    float* Qt = asm2_;                                // [64 d][68]      rows of this tile
+    float* Kt = Qt + 64 * 68;                         // [64 d][SP + 4]
+    float* Vs = Kt + 64 * (SP + 4);                   // [SP][64]
+    float* Pt = Vs + SP * 64;                         // [SP keys][68]   probabilities, transposed
+    float* mb = Pt + SP * 68;                         // [SP]
+    const float* base = a.qkv[tw] + (long long)b * S * (3 * ENC_H) + h * ENC_DH;
+    const int row0 = rt * 64;
+    for (int i = tid; i < 64 * 64; i += 256) {        // Q tile, transposed
+        const int r = i >> 6, d = i & 63;
+        Qt[d * 68 + r] = (row0 + r < S) ? base[(long long)(row0 + r) * (3 * ENC_H) + d] : 0.f;
+    }
+    for (int i = tid; i < SP * 64; i += 256) {        // K transposed, V as is
+        const int j = i >> 6, d = i & 63;
+        const bool ok = j < S;
+        Kt[d * (SP + 4) + j] = ok ? base[(long long)j * (3 * ENC_H) + ENC_H + d] : 0.f;
+        Vs[j * 64 + d] = ok ? base[(long long)j * (3 * ENC_H) + 2 * ENC_H + d] : 0.f;
+    }
+    for (int j = tid; j < SP; j += 256) mb[j] = (j < S) ? (1.0f - (float)a.mask[(long long)b * S + j]) * -10000.0f : -3.0e38f;
+    __syncthreads();
+    float acc[4][KT];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int c = 0; c < KT; c++) acc[i][c] = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < 64; d++) {
+        const float4 q4 = *reinterpret_cast<const float4*>(Qt + d * 68 + ty * 4);
+        const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+        for (int c = 0; c < KT; c++) {
+            const float kv = Kt[d * (SP + 4) + tx + 16 * c];
+#pragma unroll
+            for (int i = 0; i < 4; i++) acc[i][c] = fmaf(q[i], kv, acc[i][c]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float mx = -3.0e38f;
+#pragma unroll
+        for (int c = 0; c < KT; c++) { acc[i][c] = acc[i][c] * 0.125f + mb[tx + 16 * c]; mx = fmaxf(mx, acc[i][c]); }
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < KT; c++) { const float e = (tx + 16 * c < S) ? expf(acc[i][c] - mx) : 0.f; acc[i][c] = e; sum += e; }
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int c = 0; c < KT; c++) Pt[(tx + 16 * c) * 68 + ty * 4 + i] = acc[i][c] * inv;
+    }
+    __syncthreads();
+    float o[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) o[i][e] = 0.f;
+    for (int j = 0; j < S; j++) {
+        const float4 p4 = *reinterpret_cast<const float4*>(Pt + j * 68 + ty * 4);
+        const float4 v4 = *reinterpret_cast<const float4*>(Vs + j * 64 + tx * 4);
+        const float p[4] = {p4.x, p4.y, p4.z, p4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) o[i][e] = fmaf(p[i], v[e], o[i][e]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int r = row0 + ty * 4 + i;
+        if (r < S) *reinterpret_cast<float4*>(a.ctx[tw] + ((long long)b * S + r) * ENC_H + h * ENC_DH + tx * 4) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+    }
+}
+template <int KT> static int launch_attention_tile(const AttnArgs& aa, int B, cudaStream_t st) {
+    constexpr int SP = 16 * KT;
+    const size_t smem = (size_t)(64 * 68 + 64 * (SP + 4) + SP * 64 + SP * 68 + SP) * 4;
+    static bool attr = false;
+    if (!attr) { DPH_CUDA(cudaFuncSetAttribute(attention_tile_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    attention_tile_kernel<KT><<<dim3(ENC_HEADS * ((aa.S + 63) / 64), (unsigned)B, 2), 256, smem, st>>>(aa);
+    DPH_CUDA(cudaGetLastError());
+    return 0;
+}
+static int launch_attention(const AttnArgs& aa, int B, cudaStream_t st) {
+    const int S = aa.S;
+    if (S <= 16) return launch_attention_tile<1>(aa, B, st);
+    if (S <= 32) return launch_attention_tile<2>(aa, B, st);
+    if (S <= 64) return launch_attention_tile<4>(aa, B, st);
+    if (S <= 96) return launch_attention_tile<6>(aa, B, st);
+    if (S <= 128) return launch_attention_tile<8>(aa, B, st);
+    const int attn_warps = 8;      // long sequences (max_query_length 384 for KILT entity linking): K,V of the head in shared memory
+    const size_t attn_smem = ((size_t)S * 65 + (size_t)S * 64 + S + attn_warps * 64 + (size_t)attn_warps * S) * 4;
+    static bool attr = false;
+    if (!attr) { DPH_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+    attention_kernel<<<dim3(ENC_HEADS, (unsigned)B, 2), attn_warps * 32, attn_smem, st>>>(aa);
+    DPH_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ---- C ABI ---------------------------------------------------------------------------------------------
 DPH_API int dph_encoder_create(dph_encoder** out, int device, int vocab_size, int max_pos, int type_vocab) {
     DPH_CHECK(out && vocab_size > 0 && max_pos > 0 && type_vocab > 0, "bad encoder geometry");
@@ -288,10 +396,6 @@ DPH_API int dph_encoder_embed_query(dph_encoder* e, const int64_t* ids, const in
         embed_ln_kernel<<<dim3((unsigned)T, 2), 256, 0, st>>>(a);
         DPH_CUDA(cudaGetLastError());
     }
-    const int attn_warps = 8;
-    const size_t attn_smem = ((size_t)S * 65 + (size_t)S * 64 + S + attn_warps * 64 + (size_t)attn_warps * S) * 4;
-    static bool attr = false;
-    if (!attr) { DPH_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
     if (e->precise) DPH_TRY(ensure_split_weights(e));
     // one grouped (two-tower) linear layer: out = act(in . W^T + b) + residual; m = which weight of the layer (0 qkv, 1 attn out, 2 ffn in, 3 ffn out)
     auto linear = [&](int l, int m, float* const in[2], const float* const bias[2], float* const resid[2], float* const out[2], int N, int K, int act) -> int {
@@ -322,8 +426,7 @@ DPH_API int dph_encoder_embed_query(dph_encoder* e, const int64_t* ids, const in
         const float* bqkv[2] = {L0.bqkv, L1.bqkv}; const float* bo[2] = {L0.bo, L1.bo}; const float* bi[2] = {L0.bi, L1.bi}; const float* bo2[2] = {L0.bo2, L1.bo2};
         DPH_TRY(linear(l, 0, X, bqkv, nullptr, QKV, 3 * ENC_H, ENC_H, 0));
         AttnArgs aa; aa.qkv[0] = e->qkv[0]; aa.qkv[1] = e->qkv[1]; aa.ctx[0] = e->ctx[0]; aa.ctx[1] = e->ctx[1]; aa.mask = d_mask; aa.S = S;
-        attention_kernel<<<dim3(ENC_HEADS, (unsigned)B, 2), attn_warps * 32, attn_smem, st>>>(aa);
-        DPH_CUDA(cudaGetLastError());
+        DPH_TRY(launch_attention(aa, B, st));
         DPH_TRY(linear(l, 1, CTX, bo, X, A2, ENC_H, ENC_H, 0));                                         // dense + residual
         LnArgs ln1; for (int t = 0; t < 2; t++) { ln1.in[t] = e->a[t]; ln1.out[t] = e->a[t]; } ln1.g[0] = L0.ln1g; ln1.g[1] = L1.ln1g; ln1.b[0] = L0.ln1b; ln1.b[1] = L1.ln1b;
         layernorm_kernel<<<dim3((unsigned)T, 2), 256, 0, st>>>(ln1);
