@@ -286,11 +286,12 @@ def run_ours(args):
     pk, pk_kind = peaks()
     t_scan = sum(scan_ms) / len(scan_ms) / 1000.0
     achieved = (sum(alg_bytes) / len(alg_bytes)) / t_scan / 1e9
+    pair_mode = ix.local.last_used_pair_mode()
     traffic = None
     tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-    pair_mode = ix.local.last_used_pair_mode()
+        tj = json.load(open(tp))
+        traffic = tj.get("dram_bytes_per_launch") if pair_mode else tj.get("single_query_kernel", {}).get("dram_bytes_per_launch")
     roofline = {"kernel": "scan_pair_kernel" if pair_mode else "scan_kernel<FAST>", "gathers": "two queries per gather (pair-packed)" if pair_mode else "one query per gather", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                 "peak_kind": pk_kind, "traffic": traffic, "kernel_ms": 1000.0 * t_scan, "algorithmic_bytes_per_launch": sum(alg_bytes) / len(alg_bytes),
                 "share_of_step": 1000.0 * t_scan / (ms_prof_pass / K), "step_ms_same_pass": ms_prof_pass / K,
@@ -352,7 +353,7 @@ def run_ours(args):
                 "dtype": "f32", "data": "synthetic", "config": config_dict(wl, world, "hbm"),
                 "e2e": {"value": B * K / (ms_e2e / 1000.0), "unit": "queries/s", "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * k * 12,
                         "ms_per_step": ms_e2e / K},
-                "gpu_launches": K * (12 + (1 if world > 1 else 0)), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+                "gpu_launches": K * ((17 if pair_mode else 12) + (3 if world > 1 else 0)), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                 "exact_fallback_queries_last_batch": flags, "encoder": enc_info}
         print(json.dumps(line), flush=True)
     del ix

@@ -243,11 +243,126 @@ int dph_launch_coarse_merge(const unsigned long long* keys, int W, int64_t n, in
     return 0;
 }
 
+// Fast path for rows that fit shared memory (nlist <= 16384 per launch row, i.e. every sharded coarse search and C2):
+// the row is staged once, keys are normalised to (key - row minimum) so the radix passes start at the first bit that
+// actually varies, digits are 11 bits (<= 3 passes), and exact ties at the pivot are resolved by smallest list id.
+// Same result as coarse_select_kernel (score desc, list asc).
+#define CS_MAX_ROW 16384
+#define CS_BINS 2048
+__global__ void __launch_bounds__(256) coarse_select_smem_kernel(const float* __restrict__ S, int nlist, int nprobe,
+                                                                  int* __restrict__ key, float* __restrict__ cd,
+                                                                  unsigned long long* __restrict__ keys64, unsigned list_base) {
+    extern __shared__ unsigned cs_sm[];
+    unsigned* row = cs_sm;                         // [nlist] fkey(score)
+    unsigned* hist = row + ((nlist + 1) & ~1);     // [2048]   (keeps `sel` 8-byte aligned)
+    unsigned long long* sel = reinterpret_cast<unsigned long long*>(hist + CS_BINS);   // [1024]
+    __shared__ unsigned s_min, s_max, s_digit, s_rem, s_cnt, s_ties;
+    const long long q = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* src = S + q * (long long)nlist;
+    unsigned lmin = 0xFFFFFFFFu, lmax = 0u;
+    for (int i = tid; i < nlist; i += 256) { const unsigned u = dph_fkey(__ldg(src + i)); row[i] = u; lmin = min(lmin, u); lmax = max(lmax, u); }
+    if (tid == 0) { s_min = 0xFFFFFFFFu; s_max = 0u; s_cnt = 0; s_ties = 0; }
+    __syncthreads();
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, off)); lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, off)); }
+    if (lane == 0) { atomicMin(&s_min, lmin); atomicMax(&s_max, lmax); }
+    __syncthreads();
+    const int take = nlist < nprobe ? nlist : nprobe;
+    const unsigned base = s_min, range = s_max - s_min;
+    unsigned pivot = 0;                            // normalised pivot: elements with (u - base) > pivot are taken, == pivot are ties
+    unsigned need_ties = 0;
+    if (nlist > nprobe) {
+        int top = 32 - __clz(range | 1u);          // number of significant bits of the normalised keys
+        unsigned prefix = 0, mask = 0, remaining = (unsigned)take;
+        for (int hi = top; hi > 0; hi -= 11) {
+            const int lo = hi - 11 > 0 ? hi - 11 : 0, width = hi - lo;
+            for (int i = tid; i < CS_BINS; i += 256) hist[i] = 0;
+            __syncthreads();
+            for (int i = tid; i < nlist; i += 256) {
+                const unsigned v = row[i] - base;
+                if ((v & mask) == prefix) atomicAdd(&hist[(v >> lo) & ((1u << width) - 1u)], 1u);
+            }
+            __syncthreads();
+            {   // suffix scan over 2048 bins: 8 bins per thread, warp scan, then the 8 warp totals
+                unsigned loc[8], sum = 0;
+#pragma unroll
+                for (int b = 0; b < 8; b++) { loc[b] = hist[tid * 8 + b]; sum += loc[b]; }
+                unsigned incl = sum;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) { unsigned v = __shfl_down_sync(0xffffffffu, incl, off); if (lane + off < 32) incl += v; }
+                __shared__ unsigned wtot[8];
+                if (lane == 0) wtot[warp] = incl;
+                __syncthreads();
+                unsigned higher = 0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) higher += (w > warp) ? wtot[w] : 0u;
+                const unsigned above = higher + incl - sum;          // elements in bins above this thread's bins
+                if (above < remaining && remaining <= above + sum) {
+                    unsigned c = above;
+#pragma unroll
+                    for (int b = 7; b >= 0; b--) {
+                        if (c + loc[b] >= remaining) { s_digit = tid * 8 + b; s_rem = remaining - c; break; }
+                        c += loc[b];
+                    }
+                }
+            }
+            __syncthreads();
+            prefix |= s_digit << lo; mask |= ((1u << width) - 1u) << lo; remaining = s_rem;
+            __syncthreads();
+        }
+        pivot = prefix; need_ties = remaining;
+    }
+    const int p2 = dph_next_pow2(take);
+    for (int i = tid; i < p2; i += 256) sel[i] = 0ull;
+    __syncthreads();
+    // strictly-above elements
+    for (int i = tid; i < nlist; i += 256) {
+        const unsigned v = row[i] - base;
+        if (nlist <= nprobe || v > pivot) { unsigned p = atomicAdd(&s_cnt, 1u); if (p < DPH_MAX_NPROBE) sel[p] = ((unsigned long long)row[i] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i); }
+    }
+    __syncthreads();
+    if (nlist > nprobe) {      // ties at the pivot: the `need_ties` smallest list ids
+        for (int i = tid; i < nlist; i += 256)
+            if (row[i] - base == pivot) atomicAdd(&s_ties, 1u);
+        __syncthreads();
+        const bool all = (s_ties == need_ties);       // the usual case: exactly the needed number of elements sits at the pivot
+        for (int i = tid; i < nlist; i += 256) {
+            if (row[i] - base == pivot) {
+                unsigned rank = 0;
+                if (!all) for (int j = 0; j < i; j++) rank += (row[j] - base == pivot) ? 1u : 0u;    // rare: rank among the ties by list id
+                if (rank < need_ties) { unsigned p = atomicAdd(&s_cnt, 1u); if (p < DPH_MAX_NPROBE) sel[p] = ((unsigned long long)row[i] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i); }
+            }
+        }
+        __syncthreads();
+    }
+    block_bitonic_sort_desc(sel, p2);
+    for (int r = tid; r < nprobe; r += 256) {
+        if (keys64) {
+            unsigned long long k = r < take ? sel[r] : 0ull;
+            if (k) k = (k & 0xFFFFFFFF00000000ull) | (unsigned long long)(0xFFFFFFFFu - ((0xFFFFFFFFu - (unsigned)k) + list_base));
+            keys64[q * nprobe + r] = k;
+        } else if (r < take) {
+            const unsigned long long k = sel[r];
+            key[q * nprobe + r] = (int)(0xFFFFFFFFu - (unsigned)k);
+            cd[q * nprobe + r] = dph_fkey_inv((unsigned)(k >> 32));
+        } else { key[q * nprobe + r] = -1; cd[q * nprobe + r] = DPH_NEUTRAL; }
+    }
+}
+
 int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprobe, int32_t* key, float* cd, cudaStream_t st,
                              unsigned long long* keys64, unsigned list_base) {
     DPH_CHECK(nprobe >= 1 && nprobe <= DPH_MAX_NPROBE, "nprobe out of range [1,1024]");
     DPH_CHECK(nlist < (1ll << 31), "nlist too large");
     if (n == 0) return 0;
+    if (nlist <= CS_MAX_ROW) {
+        const size_t smem = (size_t)((nlist + 1) & ~1) * 4 + CS_BINS * 4 + DPH_MAX_NPROBE * 8;
+        static bool attr = false;
+        if (!attr) { DPH_CUDA(cudaFuncSetAttribute(coarse_select_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_MAX_ROW * 4 + CS_BINS * 4 + DPH_MAX_NPROBE * 8)); attr = true; }
+        coarse_select_smem_kernel<<<(unsigned)n, 256, smem, st>>>(S, (int)nlist, nprobe, key, cd, keys64, list_base);
+        DPH_CUDA(cudaGetLastError());
+        return 0;
+    }
     coarse_select_kernel<<<(unsigned)n, 256, 0, st>>>(S, nlist, nprobe, key, cd, keys64, list_base);
     DPH_CUDA(cudaGetLastError());
     return 0;

@@ -208,3 +208,39 @@ def test_mid_size_skewed_lists_and_large_k(oracle):
         Dr, Ir = ref.search(x, k, 64)
         assert_topk_equal(D, I, Dr, Ir, f"k={k} mode={mode}")
         assert gpu.last_flags(32).sum() == 0
+
+
+def test_coarse_ties_duplicate_centroids(oracle):
+    """Exactly equal coarse scores (duplicated centroids) at the nprobe boundary: the smaller list id is probed (an equal score
+    never evicts in faiss' heap either); probe SETS and final results must match the oracle."""
+    from densephrases_b200 import IvfPqIndex
+    nlist, nprobe = 96, 12
+    lens = np.full(nlist, 200, dtype=np.int64)
+    A, pq = opq_matrix(2), oracle.gen_pq(2)
+    Cm = oracle.gen_centroids(2, 0, nlist)
+    Cm[1::2] = Cm[0::2]                                  # every centroid appears twice
+    codes = np.concatenate([oracle.gen_codes(2, l, 0, 200) for l in range(nlist)])
+    ref = oracle.RefIndex(A, pq, lens, centroids=Cm, codes=codes)
+    x = near_queries(ref, 20, 3)
+    Dr, Ir, keyr = ref.search(x, 10, nprobe, return_key=True)
+    for mode in (3, 2):
+        gpu = IvfPqIndex.from_arrays(A, Cm, pq, lens, codes)
+        gpu.nprobe = nprobe
+        gpu.set_scan_mode(mode)
+        D, I = gpu.search(x, 10)
+        pr = gpu.last_probes(20)
+        assert all(set(pr[i].tolist()) == set(keyr[i].tolist()) for i in range(20))
+        assert_topk_equal(D, I, Dr, Ir, f"coarse ties mode={mode}")
+
+
+def test_large_nlist_uses_generic_coarse_select(oracle):
+    """nlist above the shared-memory fast path (16384) takes the generic radix-select kernel; both must agree with the oracle."""
+    nlist = 20000
+    lens = np.full(nlist, 3, dtype=np.int64)
+    ref, gpu = make_pair(oracle, nlist, lens)
+    gpu.nprobe = 40
+    x = near_queries(ref, 6, 8)
+    D, I = gpu.search(x, 10)
+    Dr, Ir, keyr = ref.search(x, 10, 40, return_key=True)
+    assert np.array_equal(gpu.last_probes(6), keyr.astype(np.int32))
+    assert_topk_equal(D, I, Dr, Ir)
