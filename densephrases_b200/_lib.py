@@ -34,6 +34,7 @@ _SIGS = {
     "dph_index_nprobe": (_i32, [_vp]),
     "dph_index_set_nprobe": (_i32, [_vp, _i32]),
     "dph_index_set_scan_mode": (_i32, [_vp, _i32]),
+    "dph_index_set_coarse_tc": (_i32, [_vp, _i32]),
     "dph_index_get_opq": (_i32, [_vp, _vp, _i32]),
     "dph_index_device_bytes": (_i64, [_vp]),
     "dph_index_set_profile": (_i32, [_vp, _i32]),

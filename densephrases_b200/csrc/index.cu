@@ -117,7 +117,7 @@ DPH_API void dph_index_free(dph_index* ix) {
     for (void* p : ptrs) if (p) cudaFree(p);
     DevBuf* bufs[] = {&ix->xdev, &ix->xr, &ix->S, &ix->key, &ix->cd, &ix->lut_scan, &ix->lut_canon, &ix->lutmax, &ix->segs, &ix->wpre, &ix->qinfo,
                       &ix->cand, &ix->cand_off, &ix->cand_cnt, &ix->gthr, &ix->flags, &ix->work, &ix->Dp, &ix->Ip, &ix->Gp, &ix->Dh, &ix->Ih, &ix->eps, &ix->nseg, &ix->lutmin, &ix->lutmaxv, &ix->lutq, &ix->qparams, &ix->gdense,
-                      &ix->pl_cnt, &ix->pl_fill, &ix->pl_off, &ix->pl_blockpre, &ix->pl_entries, &ix->pairwork};
+                      &ix->pl_cnt, &ix->pl_fill, &ix->pl_off, &ix->pl_blockpre, &ix->pl_entries, &ix->pairwork, &ix->csplit, &ix->xsplit, &ix->candkeys, &ix->cflags};
     for (DevBuf* b : bufs) b->release();
     delete ix;
 }
@@ -131,11 +131,12 @@ static int upload(float** dst, const float* src, size_t count, int mem, dph_inde
     return 0;
 }
 DPH_API int dph_index_set_opq(dph_index* ix, const float* A, int mem) { return upload(&ix->A, A, (size_t)ix->d * ix->d, mem, ix); }
-DPH_API int dph_index_set_centroids(dph_index* ix, const float* C, int mem) { return upload(&ix->C, C, (size_t)ix->nlist * ix->d, mem, ix); }
+DPH_API int dph_index_set_centroids(dph_index* ix, const float* C, int mem) { ix->csplit_lo = -1; return upload(&ix->C, C, (size_t)ix->nlist * ix->d, mem, ix); }
 DPH_API int dph_index_set_pq(dph_index* ix, const float* pq, int mem) { return upload(&ix->pq, pq, (size_t)DPH_M * 256 * DPH_DSUB, mem, ix); }
 
 DPH_API int dph_index_gen_centroids(dph_index* ix, uint64_t seed, float sigma) {
     DPH_CUDA(cudaSetDevice(ix->device));
+    ix->csplit_lo = -1;
     DPH_TRY(dev_alloc(&ix->C, (size_t)ix->nlist * ix->d, ix));
     long long tot = (long long)ix->nlist * ix->d;
     gen_normal_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ix->stream>>>(ix->C, ix->nlist, ix->d, seed, DPH_STREAM_CENTROIDS, sigma / DPH_IH4_STD);
@@ -251,6 +252,7 @@ DPH_API int dph_index_set_nprobe(dph_index* ix, int nprobe) {
     ix->nprobe = nprobe;
     return 0;
 }
+DPH_API int dph_index_set_coarse_tc(dph_index* ix, int on) { ix->coarse_tc = on ? 1 : 0; return 0; }
 DPH_API int dph_index_set_scan_mode(dph_index* ix, int mode) {
     DPH_CHECK(mode >= 0 && mode <= 3, "bad scan mode");
     ix->scan_mode = mode;
@@ -362,14 +364,23 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
     if (stage == 1) {
         const int64_t nl = ix->list_hi - ix->list_lo;
         DPH_TRY(dph_launch_sgemm_nt_seq(x_dev, n, ix->A, ix->d, ix->d, ix->xr.as<float>(), st));                   // OPQ rotation
+        if (ix->coarse_tc) {
+            int rc = dph_coarse_tc(ix, n, ix->list_lo, nl, nprobe, keys64, nullptr, nullptr, st);
+            if (rc == 0) return 0;
+            if (rc != 1) return rc;
+        }
         DPH_TRY(dph_launch_sgemm_nt_seq(ix->xr.as<float>(), n, ix->C + ix->list_lo * ix->d, nl, ix->d, ix->S.as<float>(), st));   // this shard's centroids only
         DPH_TRY(dph_launch_coarse_select(ix->S.as<float>(), n, nl, nprobe, nullptr, nullptr, st, keys64, (unsigned)ix->list_lo));
         return 0;
     }
     if (stage == 0) {
         DPH_TRY(dph_launch_sgemm_nt_seq(x_dev, n, ix->A, ix->d, ix->d, ix->xr.as<float>(), st));                   // OPQ rotation
-        DPH_TRY(dph_launch_sgemm_nt_seq(ix->xr.as<float>(), n, ix->C, ix->nlist, ix->d, ix->S.as<float>(), st));   // coarse scores
-        DPH_TRY(dph_launch_coarse_select(ix->S.as<float>(), n, ix->nlist, nprobe, ix->key.as<int32_t>(), ix->cd.as<float>(), st));
+        int rc = ix->coarse_tc ? dph_coarse_tc(ix, n, 0, ix->nlist, nprobe, nullptr, ix->key.as<int32_t>(), ix->cd.as<float>(), st) : 1;
+        if (rc > 1) return rc;
+        if (rc == 1) {
+            DPH_TRY(dph_launch_sgemm_nt_seq(ix->xr.as<float>(), n, ix->C, ix->nlist, ix->d, ix->S.as<float>(), st));   // coarse scores
+            DPH_TRY(dph_launch_coarse_select(ix->S.as<float>(), n, ix->nlist, nprobe, ix->key.as<int32_t>(), ix->cd.as<float>(), st));
+        }
     }
     DPH_TRY(dph_launch_lut(ix->xr.as<float>(), n, ix->pq, pair ? nullptr : ix->lut_scan.as<float>(), ix->lut_canon.as<float>(), ix->lutmax.as<float>(),
                            ix->lutmin.as<float>(), ix->lutmaxv.as<float>(), pair ? ix->lutq.as<unsigned short>() : nullptr,

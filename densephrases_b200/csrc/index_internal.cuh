@@ -59,7 +59,10 @@ struct dph_index {
     // per-batch workspace
     DevBuf xdev, xr, S, key, cd, lut_scan, lut_canon, lutmax, segs, wpre, qinfo, cand, cand_off, cand_cnt, gthr, flags,
         work, Dp, Ip, Gp, Dh, Ih, eps, nseg,
-        lutmin, lutmaxv, lutq, qparams, gdense, pl_cnt, pl_fill, pl_off, pl_blockpre, pl_entries, pairwork;
+        lutmin, lutmaxv, lutq, qparams, gdense, pl_cnt, pl_fill, pl_off, pl_blockpre, pl_entries, pairwork,
+        csplit, xsplit, candkeys, cflags;
+    int64_t csplit_lo = -1, csplit_nl = -1;
+    int coarse_tc = 1;                 // tensor-core coarse quantizer with exact re-rank (0: always the SIMT sequential-k GEMM)
     int64_t last_n = 0;
     bool last_pair = false;
     int64_t last_coarse_n = -1;
@@ -71,7 +74,8 @@ struct dph_index {
 // ---- prep.cu ----
 int dph_launch_sgemm_nt_seq(const float* X, int64_t n, const float* W, int64_t m, int K, float* out, cudaStream_t st);
 int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprobe, int32_t* key, float* cd, cudaStream_t st,
-                             unsigned long long* keys64 = nullptr, unsigned list_base = 0);
+                             unsigned long long* keys64 = nullptr, unsigned list_base = 0, const int* only_rows = nullptr);
+int dph_coarse_tc(dph_index* ix, int64_t n, int64_t lo, int64_t nl, int nprobe, unsigned long long* keys64, int32_t* key, float* cd, cudaStream_t st);
 int dph_launch_coarse_merge(const unsigned long long* keys, int W, int64_t n, int nprobe, int32_t* key, float* cd, cudaStream_t st);
 int dph_launch_lut(const float* xr, int64_t n, const float* pq, float* lut_scan, float* lut_canon, float* lutmax, float* lutmin, float* lutmaxv,
                    unsigned short* lutq, float2* qparams, cudaStream_t st);

@@ -178,7 +178,8 @@ int dph_launch_sgemm_nt_seq(const float* X, int64_t n, const float* W, int64_t m
 // =================================================================================================
 __global__ void __launch_bounds__(256) coarse_select_kernel(const float* __restrict__ S, long long nlist, int nprobe,
                                                              int* __restrict__ key, float* __restrict__ cd,
-                                                             unsigned long long* __restrict__ keys64, unsigned list_base) {
+                                                             unsigned long long* __restrict__ keys64, unsigned list_base, const int* __restrict__ only_rows) {
+    if (only_rows && only_rows[blockIdx.x] == 0) return;
     __shared__ SelectScratch sc;
     __shared__ unsigned long long sel[DPH_MAX_NPROBE];
     __shared__ int cnt;
@@ -251,7 +252,8 @@ int dph_launch_coarse_merge(const unsigned long long* keys, int W, int64_t n, in
 #define CS_BINS 2048
 __global__ void __launch_bounds__(256) coarse_select_smem_kernel(const float* __restrict__ S, int nlist, int nprobe,
                                                                   int* __restrict__ key, float* __restrict__ cd,
-                                                                  unsigned long long* __restrict__ keys64, unsigned list_base) {
+                                                                  unsigned long long* __restrict__ keys64, unsigned list_base, const int* __restrict__ only_rows) {
+    if (only_rows && only_rows[blockIdx.x] == 0) return;
     extern __shared__ unsigned cs_sm[];
     unsigned* row = cs_sm;                         // [nlist] fkey(score)
     unsigned* hist = row + ((nlist + 1) & ~1);     // [2048]   (keeps `sel` 8-byte aligned)
@@ -351,7 +353,7 @@ __global__ void __launch_bounds__(256) coarse_select_smem_kernel(const float* __
 }
 
 int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprobe, int32_t* key, float* cd, cudaStream_t st,
-                             unsigned long long* keys64, unsigned list_base) {
+                             unsigned long long* keys64, unsigned list_base, const int* only_rows) {
     DPH_CHECK(nprobe >= 1 && nprobe <= DPH_MAX_NPROBE, "nprobe out of range [1,1024]");
     DPH_CHECK(nlist < (1ll << 31), "nlist too large");
     if (n == 0) return 0;
@@ -359,11 +361,11 @@ int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprob
         const size_t smem = (size_t)((nlist + 1) & ~1) * 4 + CS_BINS * 4 + DPH_MAX_NPROBE * 8;
         static bool attr = false;
         if (!attr) { DPH_CUDA(cudaFuncSetAttribute(coarse_select_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_MAX_ROW * 4 + CS_BINS * 4 + DPH_MAX_NPROBE * 8)); attr = true; }
-        coarse_select_smem_kernel<<<(unsigned)n, 256, smem, st>>>(S, (int)nlist, nprobe, key, cd, keys64, list_base);
+        coarse_select_smem_kernel<<<(unsigned)n, 256, smem, st>>>(S, (int)nlist, nprobe, key, cd, keys64, list_base, only_rows);
         DPH_CUDA(cudaGetLastError());
         return 0;
     }
-    coarse_select_kernel<<<(unsigned)n, 256, 0, st>>>(S, nlist, nprobe, key, cd, keys64, list_base);
+    coarse_select_kernel<<<(unsigned)n, 256, 0, st>>>(S, nlist, nprobe, key, cd, keys64, list_base, only_rows);
     DPH_CUDA(cudaGetLastError());
     return 0;
 }

@@ -105,6 +105,9 @@ class IvfPqIndex:
     def last_used_pair_mode(self):
         return bool(L.lib().dph_index_last_used_pair_mode(self._h))
 
+    def set_coarse_tc(self, on):
+        L.check(L.lib().dph_index_set_coarse_tc(self._h, int(bool(on))))
+
     def set_stream(self, cuda_stream_ptr):
         L.check(L.lib().dph_index_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 

@@ -68,6 +68,9 @@ int64_t dph_index_nlist(const dph_index* ix);
 int dph_index_nprobe(const dph_index* ix);
 int dph_index_set_nprobe(dph_index* ix, int nprobe);
 int dph_index_set_scan_mode(dph_index* ix, int mode);
+/* Coarse quantizer on the tensor cores (3xTF32 candidate pass + exact sequential-FMA re-rank + proof; bit-identical probes).
+ * 1 (default): used when the shape allows (lists % 128 == 0, batch >= 32, nprobe + margin <= 1024); 0: always the exact SIMT GEMM. */
+int dph_index_set_coarse_tc(dph_index* ix, int on);
 int dph_index_get_opq(const dph_index* ix, float* A_out, int mem);
 int64_t dph_index_device_bytes(const dph_index* ix);
 /* Measurement hook: when on, CUDA events bracket the scan kernel of each search (last chunk); last_scan_ms waits

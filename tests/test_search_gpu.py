@@ -244,3 +244,49 @@ def test_large_nlist_uses_generic_coarse_select(oracle):
     Dr, Ir, keyr = ref.search(x, 10, 40, return_key=True)
     assert np.array_equal(gpu.last_probes(6), keyr.astype(np.int32))
     assert_topk_equal(D, I, Dr, Ir)
+
+
+@pytest.mark.parametrize("nprobe", [8, 256])
+def test_tensor_core_coarse_is_bit_identical(oracle, nprobe):
+    """Coarse quantizer on tcgen05 (3xTF32 candidates + exact re-rank + proof) == SIMT sequential-k path == oracle (probes AND scores)."""
+    nlist = 1024
+    lens = np.full(nlist, 40, dtype=np.int64)
+    ref, gpu = make_pair(oracle, nlist, lens)
+    gpu.nprobe = nprobe
+    x = np.concatenate([near_queries(ref, 60, 5), 0.5 * np.random.default_rng(2).standard_normal((36, 768)).astype(np.float32)])
+    out = {}
+    for tc in (1, 0):
+        gpu.set_coarse_tc(tc)
+        D, I = gpu.search(x, 10)
+        out[tc] = (gpu.last_probes(len(x)).copy(), gpu.last_coarse(len(x)).copy(), D, I)
+    Dr, Ir, keyr = ref.search(x, 10, nprobe, return_key=True)
+    cdr, _ = ref.coarse(ref.rotate(x), nprobe)
+    for tc in (1, 0):
+        assert np.array_equal(out[tc][0], keyr.astype(np.int32)), f"probes differ (tc={tc})"
+        assert np.array_equal(out[tc][1].view(np.int32), cdr.view(np.int32)), f"coarse scores differ (tc={tc})"
+        assert_topk_equal(out[tc][2], out[tc][3], Dr, Ir, f"tc={tc}")
+
+
+def test_tensor_core_coarse_repair_path(oracle):
+    """Near-identical centroids: candidate scores sit inside the error bound, the proof fails, and every query takes the repair path
+    (exact scores for all lists) -- results must still equal the oracle."""
+    from densephrases_b200 import IvfPqIndex
+    nlist, nprobe = 256, 16
+    rng = np.random.default_rng(4)
+    lens = np.full(nlist, 30, dtype=np.int64)
+    A, pq = opq_matrix(4), oracle.gen_pq(4)
+    Cm = (oracle.gen_centroids(4, 0, 1) + 1e-6 * rng.standard_normal((nlist, 768))).astype(np.float32)
+    codes = np.concatenate([oracle.gen_codes(4, l, 0, 30) for l in range(nlist)])
+    ref = oracle.RefIndex(A, pq, lens, centroids=Cm, codes=codes)
+    gpu = IvfPqIndex.from_arrays(A, Cm, pq, lens, codes)
+    gpu.nprobe = nprobe
+    x = near_queries(ref, 48, 6)
+    out = {}
+    for tc in (1, 0):        # both paths are canonical (score desc, list asc): they must agree exactly, ties included
+        gpu.set_coarse_tc(tc)
+        D, I = gpu.search(x, 10)
+        out[tc] = (gpu.last_probes(48).copy(), gpu.last_coarse(48).copy(), D, I)
+    assert np.array_equal(out[1][0], out[0][0]) and np.array_equal(out[1][1].view(np.int32), out[0][1].view(np.int32))
+    assert np.array_equal(out[1][2].view(np.int32), out[0][2].view(np.int32)) and np.array_equal(out[1][3], out[0][3])
+    cdr, _ = ref.coarse(ref.rotate(x), nprobe)
+    assert np.array_equal(out[1][1].view(np.int32), cdr.view(np.int32))     # the exact coarse scores equal the oracle's bit for bit
