@@ -123,33 +123,39 @@ __global__ void cnorm_max_kernel(const float* C, long long nl, float* out) {
 int dph_coarse_tc(dph_index* ix, int64_t n, int64_t lo, int64_t nl, int nprobe, unsigned long long* keys64, int32_t* key, float* cd, cudaStream_t st) {
     const int margin = nprobe / 4 > 32 ? nprobe / 4 : 32;
     const int ncand = (int)std::min<int64_t>(nprobe + margin, nl);
-    // measured on B200 (tools/bench_c4_shard.py): pays for small probe counts (C4 nprobe 32: 0.48 -> 0.28 ms per 1024 queries);
+    // measured on B200 (tools/bench_shard.py): pays for small probe counts (C4 nprobe 32: 0.48 -> 0.28 ms per 1024 queries);
     // at nprobe 256 the exact re-rank of 320 candidates costs what the tensor cores save, so the SIMT GEMM is kept there.
-    if (nl % 128 != 0 || ncand > 160 || n < 32 || nl <= 4 * ncand) return 1;
+    // With many lists per candidate (C5: 131 072 lists per shard, 320 candidates) the GEMM dominates again and the tensor cores win.
+    const bool few_candidates = ncand <= 160 && nl > 4 * (int64_t)ncand;
+    const bool many_lists = nl >= 32 * (int64_t)ncand;
+    if (ncand > DPH_MAX_NPROBE || n < 32 || !(few_candidates || many_lists)) return 1;
+    const int64_t nlp = (nl + 127) / 128 * 128;          // GEMM N must be a multiple of the 128-wide tile: zero-padded centroid rows
+    if ((size_t)n * nlp * 4 > ix->S.cap) return 1;
     const float* Cl = ix->C + lo * DPH_D;
     if (!ix->csplit.p || ix->csplit_lo != lo || ix->csplit_nl != nl) {          // (hi, lo) TF32 split of the shard's centroids + max norm, once
-        DPH_TRY(ix->csplit.ensure((size_t)nl * DPH_D * 8 + 16));
+        DPH_TRY(ix->csplit.ensure((size_t)nlp * DPH_D * 8 + 16));
         float* hi = ix->csplit.as<float>();
-        DPH_TRY(dph_launch_split_tf32(Cl, hi, hi + nl * DPH_D, nl * DPH_D, st));
-        float* nm = hi + 2 * nl * DPH_D;
+        DPH_CUDA(cudaMemsetAsync(hi, 0, (size_t)nlp * DPH_D * 8, st));
+        DPH_TRY(dph_launch_split_tf32(Cl, hi, hi + nlp * DPH_D, nl * DPH_D, st));
+        float* nm = hi + 2 * nlp * DPH_D;
         DPH_CUDA(cudaMemsetAsync(nm, 0, 4, st));
         cnorm_max_kernel<<<(unsigned)((nl + 7) / 8), 256, 0, st>>>(Cl, nl, nm);
         DPH_CUDA(cudaGetLastError());
         ix->csplit_lo = lo; ix->csplit_nl = nl;
     }
-    float* chi = ix->csplit.as<float>(); float* clo = chi + nl * DPH_D; float* cnorm = chi + 2 * nl * DPH_D;
+    float* chi = ix->csplit.as<float>(); float* clo = chi + nlp * DPH_D; float* cnorm = chi + 2 * nlp * DPH_D;
     DPH_TRY(ix->xsplit.ensure((size_t)n * DPH_D * 8));
     DPH_TRY(ix->candkeys.ensure((size_t)n * ncand * 8));
     DPH_TRY(ix->cflags.ensure((size_t)n * 4));
     float* xhi = ix->xsplit.as<float>(); float* xlo = xhi + n * DPH_D;
     DPH_TRY(dph_launch_split_tf32(ix->xr.as<float>(), xhi, xlo, n * DPH_D, st));
     const float* A1[1] = {xhi}; const float* W1[1] = {chi}; const float* A2[1] = {xlo}; const float* W2[1] = {clo}; float* O1[1] = {ix->S.as<float>()};
-    DPH_TRY(dph_launch_gemm_tf32(1, A1, W1, nullptr, nullptr, O1, (int)n, (int)nl, DPH_D, 0, st, A2, W2));
-    DPH_TRY(dph_launch_coarse_select(ix->S.as<float>(), n, nl, ncand, nullptr, nullptr, st, ix->candkeys.as<unsigned long long>(), 0u));
+    DPH_TRY(dph_launch_gemm_tf32(1, A1, W1, nullptr, nullptr, O1, (int)n, (int)nlp, DPH_D, 0, st, A2, W2));
+    DPH_TRY(dph_launch_coarse_select(ix->S.as<float>(), n, nl, ncand, nullptr, nullptr, st, ix->candkeys.as<unsigned long long>(), 0u, nullptr, nlp));
     CoarseTcArgs a;
     a.xr = ix->xr.as<float>(); a.C = Cl; a.Sapprox = ix->S.as<float>(); a.nl = nl; a.ncand = ncand; a.nprobe = nprobe; a.list_base = (unsigned)lo;
     a.cand_keys = ix->candkeys.as<unsigned long long>(); a.cnorm_max = cnorm; a.keys64 = keys64; a.key = key; a.cd = cd;
-    a.flags = ix->cflags.as<int>(); a.S_exact = ix->S.as<float>();
+    a.flags = ix->cflags.as<int>(); a.S_exact = ix->S.as<float>();       // repaired rows are rewritten with stride nl (the approximate scores are dead by then)
     coarse_tc_finish_kernel<<<(unsigned)n, 256, 0, st>>>(a);
     coarse_tc_repair_kernel<<<(unsigned)n, 256, 0, st>>>(a);
     DPH_CUDA(cudaGetLastError());

@@ -178,13 +178,14 @@ int dph_launch_sgemm_nt_seq(const float* X, int64_t n, const float* W, int64_t m
 // =================================================================================================
 __global__ void __launch_bounds__(256) coarse_select_kernel(const float* __restrict__ S, long long nlist, int nprobe,
                                                              int* __restrict__ key, float* __restrict__ cd,
-                                                             unsigned long long* __restrict__ keys64, unsigned list_base, const int* __restrict__ only_rows) {
+                                                             unsigned long long* __restrict__ keys64, unsigned list_base, const int* __restrict__ only_rows,
+                                                             long long ld) {
     if (only_rows && only_rows[blockIdx.x] == 0) return;
     __shared__ SelectScratch sc;
     __shared__ unsigned long long sel[DPH_MAX_NPROBE];
     __shared__ int cnt;
     const long long q = blockIdx.x;
-    const float* row = S + q * nlist;
+    const float* row = S + q * ld;
     const int tid = threadIdx.x;
     const int take = (int)(nlist < nprobe ? nlist : nprobe);
     auto get = [&](int i) { return ((unsigned long long)dph_fkey(__ldg(row + i)) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i); };
@@ -252,7 +253,8 @@ int dph_launch_coarse_merge(const unsigned long long* keys, int W, int64_t n, in
 #define CS_BINS 2048
 __global__ void __launch_bounds__(256) coarse_select_smem_kernel(const float* __restrict__ S, int nlist, int nprobe,
                                                                   int* __restrict__ key, float* __restrict__ cd,
-                                                                  unsigned long long* __restrict__ keys64, unsigned list_base, const int* __restrict__ only_rows) {
+                                                                  unsigned long long* __restrict__ keys64, unsigned list_base, const int* __restrict__ only_rows,
+                                                                  long long ld) {
     if (only_rows && only_rows[blockIdx.x] == 0) return;
     extern __shared__ unsigned cs_sm[];
     unsigned* row = cs_sm;                         // [nlist] fkey(score)
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(256) coarse_select_smem_kernel(const float* __
     __shared__ unsigned s_min, s_max, s_digit, s_rem, s_cnt, s_ties;
     const long long q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* src = S + q * (long long)nlist;
+    const float* src = S + q * ld;
     unsigned lmin = 0xFFFFFFFFu, lmax = 0u;
     for (int i = tid; i < nlist; i += 256) { const unsigned u = dph_fkey(__ldg(src + i)); row[i] = u; lmin = min(lmin, u); lmax = max(lmax, u); }
     if (tid == 0) { s_min = 0xFFFFFFFFu; s_max = 0u; s_cnt = 0; s_ties = 0; }
@@ -353,7 +355,8 @@ __global__ void __launch_bounds__(256) coarse_select_smem_kernel(const float* __
 }
 
 int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprobe, int32_t* key, float* cd, cudaStream_t st,
-                             unsigned long long* keys64, unsigned list_base, const int* only_rows) {
+                             unsigned long long* keys64, unsigned list_base, const int* only_rows, int64_t ld) {
+    if (ld <= 0) ld = nlist;
     DPH_CHECK(nprobe >= 1 && nprobe <= DPH_MAX_NPROBE, "nprobe out of range [1,1024]");
     DPH_CHECK(nlist < (1ll << 31), "nlist too large");
     if (n == 0) return 0;
@@ -361,11 +364,11 @@ int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprob
         const size_t smem = (size_t)((nlist + 1) & ~1) * 4 + CS_BINS * 4 + DPH_MAX_NPROBE * 8;
         static bool attr = false;
         if (!attr) { DPH_CUDA(cudaFuncSetAttribute(coarse_select_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_MAX_ROW * 4 + CS_BINS * 4 + DPH_MAX_NPROBE * 8)); attr = true; }
-        coarse_select_smem_kernel<<<(unsigned)n, 256, smem, st>>>(S, (int)nlist, nprobe, key, cd, keys64, list_base, only_rows);
+        coarse_select_smem_kernel<<<(unsigned)n, 256, smem, st>>>(S, (int)nlist, nprobe, key, cd, keys64, list_base, only_rows, ld);
         DPH_CUDA(cudaGetLastError());
         return 0;
     }
-    coarse_select_kernel<<<(unsigned)n, 256, 0, st>>>(S, nlist, nprobe, key, cd, keys64, list_base, only_rows);
+    coarse_select_kernel<<<(unsigned)n, 256, 0, st>>>(S, nlist, nprobe, key, cd, keys64, list_base, only_rows, ld);
     DPH_CUDA(cudaGetLastError());
     return 0;
 }

@@ -2,7 +2,7 @@
 by building shard 0 only (125M phrases, 12 GB) and timing the rank-local work of a sharded search:
     coarse_local (this shard's 8192 centroids)  +  search_preassigned (LUT, plan, scan of this shard's probed lists, merge)
 (the two NCCL all-gathers, ~2 x 20 us, are not included).  Projected 8-GPU QPS = 1024 / rank step time.
-python tools/bench_c4_shard.py [nprobe ...]"""
+python tools/bench_shard.py [nprobe ...]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -10,12 +10,18 @@ import bench
 from densephrases_b200 import IvfPqIndex
 from densephrases_b200.sharded import shard_ranges
 
-N, NLIST, WORLD, B, K = 1_000_000_000, 65536, 8, 1024, 10
+CONFIGS = {"c4": (1_000_000_000, 65536, 8, 1024, 10),       # BASELINE.json configs[3]
+           "c5": (580_000_000, 1_048_576, 8, 128, 10)}       # configs[4]: multi_wiki-scale dump, IVF1048576, eval batch 64 questions = 128 vectors
+cfg = "c4"
+if len(sys.argv) > 1 and sys.argv[1] in CONFIGS:
+    cfg = sys.argv.pop(1)
+N, NLIST, WORLD, B, K = CONFIGS[cfg]
 lens = bench.uniform_lens(N, NLIST)
 lo, hi = shard_ranges(lens, WORLD)[0]
 ix = IvfPqIndex(NLIST)
 ix.set_opq(bench.opq_matrix(1234)); ix.gen_centroids(1234); ix.gen_pq(1234); ix.set_shard(lo, hi); ix.set_lists_synthetic(lens, 1234)
 torch.cuda.synchronize()
+print(f"config {cfg}: N={N} nlist={NLIST} batch={B}")
 print(f"shard 0: lists [{lo},{hi}), {ix.ntotal_local/1e6:.1f} M phrases, {ix.device_bytes/1e9:.1f} GB on device", flush=True)
 g = torch.Generator(device="cuda").manual_seed(4321)
 X = [0.5 * torch.randn((B, 768), generator=g, device="cuda") for _ in range(6)]
