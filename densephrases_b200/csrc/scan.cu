@@ -547,6 +547,7 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeArgs a) {
     const unsigned long long* E = a.cand + a.cand_off[q];
     long long cap = a.cand_off[q + 1] - a.cand_off[q];
     int n = a.cand_cnt[q];
+    const bool overflow = n > cap;          // cannot happen with the plan's capacity bound; if it ever does the query goes to the exact kernel
     if (n > cap) n = (int)cap;
     const DphSeg* segs = a.segs + q * a.nprobe;
     const int nsg = a.nseg[q];
@@ -555,7 +556,7 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeArgs a) {
     __syncthreads();
     auto get = [&](int i) { return E[i]; };
     unsigned long long pivot = 0ull;   // gather keys >= pivot
-    int flag = 0;
+    int flag = overflow ? 1 : 0;
     if (a.mode == DPH_SCAN_FAST) {
         const float eps2 = 2.0f * a.eps[q];
         const unsigned gt = a.gthr[q];
