@@ -40,6 +40,26 @@ def gather_and_merge(D, I, G, k, world, group=None, merge_fn=merge_shards):
     return merge_fn(Dg.view(world, n, k), Ig.view(world, n, k), Gg.view(world, n, k), k)
 
 
+def sharded_search(x, k, world, group, coarse_local, search_preassigned, pack, merge_packed):
+    """The two-exchange protocol of one sharded search, independent of where the local work runs (CUDA in the product, the CPU
+    oracle in tests/test_sharded_cpu.py over gloo):
+        keys   = coarse_local(x)                      [n, nprobe] int64   this shard's best lists (score key << 32 | ~list id)
+        keys_g = all_gather(keys)                     [W, n, nprobe]      exchange 1
+        D,I,G  = search_preassigned(keys_g, k)        per-shard partial top-k over the GLOBAL probe set
+        P_g    = all_gather(pack(D, I, G))            [W, n, k, 2]        exchange 2
+        return merge_packed(P_g, k)                   identical on every rank"""
+    import torch.distributed as dist
+    n = x.shape[0]
+    keys = coarse_local(x)
+    keys_g = torch.empty((world * n, keys.shape[1]), dtype=torch.int64, device=keys.device)
+    dist.all_gather_into_tensor(keys_g, keys.contiguous(), group=group)
+    D, I, G = search_preassigned(keys_g.view(world, n, -1), k)
+    P = pack(D, I, G)
+    Pg = torch.empty((world * n, k, 2), dtype=torch.int64, device=P.device)
+    dist.all_gather_into_tensor(Pg, P.contiguous(), group=group)
+    return merge_packed(Pg.view(world, n, k, 2), k)
+
+
 class ShardedIvfPq:
     def __init__(self, nlist, rank=0, world=1, device=0, group=None):
         self.rank, self.world, self.device, self.group = rank, world, device, group
@@ -71,21 +91,11 @@ class ShardedIvfPq:
         """x torch cuda [n,d] (same on every rank) -> (D, I) torch cuda [n,k] (same on every rank)."""
         if self.world == 1:
             return self.local.search(x, k)
-        import torch.distributed as dist
         n = x.shape[0]
         if n > 4096:        # one chunk per collective round
             parts = [self.search_device(x[i:i + 4096], k) for i in range(0, n, 4096)]
             return torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
-        # exchange 1: every rank scores only its own centroids; all-gather the per-shard best-nprobe keys
-        keys = self.local.coarse_local(x)
-        keys_g = torch.empty((self.world * n, keys.shape[1]), dtype=torch.int64, device=x.device)
-        dist.all_gather_into_tensor(keys_g, keys, group=self.group)
-        D, I, G = self.local.search_preassigned(keys_g.view(self.world, n, -1), k)
-        # exchange 2: per-shard partial top-k, packed into one buffer
-        P = pack_topk(D, I, G)
-        Pg = torch.empty((self.world * n, k, 2), dtype=torch.int64, device=x.device)
-        dist.all_gather_into_tensor(Pg, P, group=self.group)
-        return merge_shards_packed(Pg.view(self.world, n, k, 2), k)
+        return sharded_search(x, k, self.world, self.group, self.local.coarse_local, self.local.search_preassigned, pack_topk, merge_shards_packed)
 
     def search(self, x, k):
         """Host API == faiss index.search (index.py:200): numpy / pinned CPU tensor [n,d] -> numpy (D, I)."""

@@ -39,6 +39,92 @@ def numpy_merge(Dg, Ig, Gg, k):
     return torch.from_numpy(D), torch.from_numpy(I)
 
 
+def _fkey(f):
+    b = np.asarray(f, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    return np.where(b & 0x80000000, (~b) & 0xFFFFFFFF, b | 0x80000000)
+
+
+def _fkey_inv(k):
+    k = np.asarray(k, dtype=np.uint64)
+    b = np.where(k & 0x80000000, k & 0x7FFFFFFF, (~k) & 0xFFFFFFFF).astype(np.uint32)
+    return b.view(np.float32)
+
+
+def _worker2(rank, world, port, out):
+    """Both exchanges of densephrases_b200.sharded.sharded_search over gloo, local work done by the oracle."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from densephrases_b200.sharded import shard_ranges, sharded_search
+    from oracle import ivfpq_ref as R
+    seed, nlist, nprobe, k = 9, 40, 10, 10
+    lens = np.random.default_rng(seed).integers(0, 300, nlist).astype(np.int64)
+    ix = R.RefIndex(opq_matrix(seed), R.gen_pq(seed), lens, centroids=R.gen_centroids(seed, 0, nlist), seed=seed)
+    x = near_queries(ix, 7, 3)
+    Dfull, Ifull, keyfull = ix.search(x, k, nprobe, return_key=True)
+    lo, hi = shard_ranges(lens, world)[rank]
+    xr = ix.rotate(x)
+    state = {}
+
+    def coarse_local(xt):
+        S = R.np_matmul_nt_seq(xr, ix.centroids()[lo:hi])                  # this shard's centroids only (same sequential-FMA scores)
+        keys = np.zeros((len(x), nprobe), dtype=np.uint64)
+        for q in range(len(x)):
+            order = sorted(range(hi - lo), key=lambda j: (-float(S[q, j]), j))[:nprobe]
+            for r, j in enumerate(order):
+                keys[q, r] = (_fkey(S[q, j]) << np.uint64(32)) | np.uint64(0xFFFFFFFF - (j + lo))
+        return torch.from_numpy(keys.view(np.int64))
+
+    def search_preassigned(keys_g, kk):
+        kg = keys_g.numpy().view(np.uint64)                                  # [W, n, nprobe]
+        key = np.full((len(x), nprobe), -1, dtype=np.int64)
+        for q in range(len(x)):
+            allk = sorted((int(v) for v in kg[:, q, :].ravel() if v != 0), reverse=True)[:nprobe]
+            key[q, :len(allk)] = [0xFFFFFFFF - (v & 0xFFFFFFFF) for v in allk]
+        state["key"] = key
+        D, I = ix.search_preassigned(xr, np.where((key >= lo) & (key < hi), key, -1), kk)
+        G = np.zeros_like(I)
+        for q in range(len(x)):
+            starts = np.concatenate([[0], np.cumsum([lens[l] if l >= 0 else 0 for l in key[q]])])
+            for r in range(kk):
+                if I[q, r] >= 0:
+                    l, off = ix.locate(np.array([I[q, r]]))
+                    G[q, r] = starts[list(key[q]).index(int(l[0]))] + int(off[0])
+        return torch.from_numpy(D), torch.from_numpy(I), torch.from_numpy(G.astype(np.int32))
+
+    def pack(D, I, G):
+        ck = (_fkey(D.numpy()) << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - (G.numpy().astype(np.int64) & 0xFFFFFFFF).astype(np.uint64))
+        P = np.stack([np.where(I.numpy() >= 0, ck, 0).view(np.int64), I.numpy()], axis=-1)
+        return torch.from_numpy(np.ascontiguousarray(P))
+
+    def merge_packed(Pg, kk):
+        Pn = Pg.numpy()
+        D = np.full((len(x), kk), np.float32(-3.4028234663852886e38), dtype=np.float32)
+        I = np.full((len(x), kk), -1, dtype=np.int64)
+        for q in range(len(x)):
+            ent = sorted(((int(np.uint64(Pn[s, q, r, 0])), int(Pn[s, q, r, 1])) for s in range(Pn.shape[0]) for r in range(kk) if Pn[s, q, r, 0] != 0),
+                         reverse=True)[:kk]
+            for i, (ckey, lab) in enumerate(ent):
+                D[q, i], I[q, i] = _fkey_inv(ckey >> 32), lab
+        return torch.from_numpy(D), torch.from_numpy(I)
+
+    Dm, Im = sharded_search(torch.from_numpy(x), k, world, None, coarse_local, search_preassigned, pack, merge_packed)
+    if rank == 0:
+        np.savez(out, D=Dm.numpy(), I=Im.numpy(), Dfull=Dfull, Ifull=Ifull, key=state["key"], keyfull=keyfull)
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_two_exchange_protocol(tmp_path, oracle):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "merged2.npz")
+    mp.spawn(_worker2, args=(2, port, out), nprocs=2, join=True)
+    g = np.load(out)
+    assert np.array_equal(g["key"], g["keyfull"])                       # sharded coarse quantizer == unsharded probe selection
+    assert_topk_equal(g["D"], g["I"], g["Dfull"], g["Ifull"], "two-exchange sharded search vs unsharded")
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
