@@ -175,7 +175,7 @@ def run_reference(args):
             "config": config_dict(wl, args.gpus, "cpu"),
             "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -355,12 +355,34 @@ def run_ours(args):
                         "ms_per_step": ms_e2e / K},
                 "gpu_launches": K * ((17 if pair_mode else 12) + (3 if world > 1 else 0)), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                 "exact_fallback_queries_last_batch": flags, "encoder": enc_info}
-        print(json.dumps(line), flush=True)
+        emit(line)
     del ix
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout; NCCL prints a version banner there (seen on the GPU box).  Route fd 1 to stderr for
+    the whole run and keep the real stdout for the final line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -377,6 +399,7 @@ def main():
     args.warmup = max(args.warmup, 3)
     if args.steps is None:
         args.steps = 10 if args.impl == "reference" else 100
+    quiet_stdout()
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 
 
