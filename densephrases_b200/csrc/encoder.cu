@@ -4,7 +4,6 @@
 // every GEMM is one launch of the tcgen05 TF32 kernel (gemm_tf32.cu) with blockIdx.z = tower.
 #include "common.cuh"
 #include "../../include/dph_b200.h"
-#include <vector>
 
 #define ENC_H 768
 #define ENC_HEADS 12

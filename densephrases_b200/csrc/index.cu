@@ -2,7 +2,6 @@
 // C ABI declared in include/dph_b200.h (each entry point cites the reference call it replaces).
 #include "index_internal.cuh"
 #include <algorithm>
-#include <mutex>
 #include <numeric>
 #include <string.h>
 

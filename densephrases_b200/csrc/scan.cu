@@ -8,18 +8,20 @@
 // per SM (the per-query LUT fills shared memory); inside a CTA each warp owns one 32-vector block per round,
 // lane l <-> vector l.
 //
-// FAST mode (the product path).  Shared-memory gathers, not HBM, co-limit this scan (one 4-byte LUT gather
-// per code byte).  The code blocks are stored lane-rotated (common.cuh: dph_blk_addr) and the LUT is stored as
-// three [256][64] tables (32 sub-quantizers + 31 wrap copies per row), so that at step t lane l reads word
-// (l + t%32) of row `code byte` of table t/32: the 32 lanes always hit 32 different banks -> every LDS is one
-// conflict-free wavefront regardless of the code values.  One PRMT builds the address (code<<8 | lane*4), so a
-// lookup is PRMT + LDS + FADD.  The rotated summation order differs from faiss' m-ascending order by at most
-// eps (plan kernel), so the scores are used as a FILTER: each CTA keeps its best k+32 by filter score, the merge
-// kernel re-scores the survivors in canonical order (bit-exact with the oracle) and PROVES that nothing that
-// was dropped could have been in the top-k (T_k - max drop threshold > 2 eps); otherwise the query is flagged
-// and re-run through EXACT mode.
+// FAST (one query per gather, fp32 LUT).  Shared-memory gathers, not HBM, co-limit this scan (one 4-byte LUT gather per code
+// byte).  The code blocks are stored lane-rotated (common.cuh: dph_blk_addr) and the LUT is stored as three [256][64] tables
+// (32 sub-quantizers + 31 wrap copies per row), so that at step t lane l reads word (l + t%32) of row `code byte` of table t/32:
+// the 32 lanes always hit 32 different banks -> every LDS is one conflict-free wavefront regardless of the code values.  One
+// PRMT builds the address (code<<8 | lane*4), so a lookup is PRMT + LDS + FADD.  The rotated summation order differs from faiss'
+// m-ascending order by at most eps (plan kernel), so the scores are used as a FILTER: each CTA keeps its best k+slack by filter
+// score, the merge kernel re-scores the survivors in canonical order (bit-exact with the oracle) and PROVES that nothing that was
+// dropped could have been in the top-k (T_k - max drop threshold > 2 eps); otherwise the query is flagged and re-run through
+// EXACT mode.
 //
-// EXACT mode: canonical m-ascending fp32 sum for every code (bank conflicts and all) -- fallback/cross-check.
+// PAIR (scan_pair_kernel, further down): two queries that probe the same list share every gather through int16-packed quantised
+// LUTs -- the default whenever lists are shared by the batch (the reference's nprobe = 256).
+//
+// EXACT: canonical m-ascending fp32 sum for every code (bank conflicts and all) -- fallback/cross-check.
 #include "index_internal.cuh"
 #include "select.cuh"
 
@@ -51,8 +53,6 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
 __device__ __forceinline__ void l2_prefetch_block(const void* p) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "n"(DPH_BLK_BYTES) : "memory");
 }
-
-struct BlockMeta { const uint4* ptr; int j0; int len; unsigned gstart; float dis0; };
 
 extern __shared__ __align__(1024) unsigned char dph_smem[];
 // The dynamic shared memory window of a kernel without static shared memory starts at this shared-space address on
