@@ -91,13 +91,46 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(EmbedArgs a) {
     for (int i = 0; i < 3; i++) v[i] = (w[t + 256 * i] + y[t + 256 * i]) + p[t + 256 * i];   // inputs_embeds + token_type, + position (HF order)
     ln_row_256(v, a.g[tw], a.b[tw], a.out[tw] + tok * ENC_H, red);
 }
-struct LnArgs { const float* in[2]; const float* g[2]; const float* b[2]; float* out[2]; };
+struct LnArgs { const float* in[2]; const float* g[2]; const float* b[2]; float* out[2]; long long rows; long long in_stride, out_stride; };
+// One warp per row, 24 elements per lane as six float4: no shared memory, no block barrier; two-pass mean / variance like
+// torch.nn.LayerNorm.  in/out row strides allow normalising only the [CLS] rows of the last layer.
 __global__ void __launch_bounds__(256) layernorm_kernel(LnArgs a) {
-    __shared__ float red[8];
-    const long long tok = blockIdx.x; const int tw = blockIdx.y, t = threadIdx.x;
-    const float* x = a.in[tw] + tok * ENC_H;
-    float v[3] = {x[t], x[t + 256], x[t + 512]};
-    ln_row_256(v, a.g[tw], a.b[tw], a.out[tw] + tok * ENC_H, red);
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int tw = blockIdx.y, lane = threadIdx.x & 31;
+    if (row >= a.rows) return;
+    const float4* x = reinterpret_cast<const float4*>(a.in[tw] + row * a.in_stride);
+    float4 v[6];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; i++) { v[i] = x[lane + 32 * i]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    const float mean = s * (1.0f / ENC_H);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) q += __shfl_xor_sync(0xffffffffu, q, off);
+    const float rstd = rsqrtf(q * (1.0f / ENC_H) + 1e-12f);
+    const float4* g = reinterpret_cast<const float4*>(a.g[tw]);
+    const float4* b = reinterpret_cast<const float4*>(a.b[tw]);
+    float4* o = reinterpret_cast<float4*>(a.out[tw] + row * a.out_stride);
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        const float4 gg = g[lane + 32 * i], bb = b[lane + 32 * i];
+        o[lane + 32 * i] = make_float4(v[i].x * rstd * gg.x + bb.x, v[i].y * rstd * gg.y + bb.y, v[i].z * rstd * gg.z + bb.z, v[i].w * rstd * gg.w + bb.w);
+    }
+}
+// gather rows b*S of [B*S, 768] into a dense [B, 768] buffer (the [CLS] rows the last layer's output actually needs)
+__global__ void gather_cls_kernel(const float* in0, const float* in1, float* out0, float* out1, int S, long long B) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * (ENC_H / 4)) return;
+    const long long b = i / (ENC_H / 4); const int c = (int)(i % (ENC_H / 4));
+    const float* in = blockIdx.y ? in1 : in0; float* out = blockIdx.y ? out1 : out0;
+    reinterpret_cast<float4*>(out)[b * (ENC_H / 4) + c] = reinterpret_cast<const float4*>(in)[b * S * (ENC_H / 4) + c];
 }
 
 // ---- self attention: one CTA per (head, batch row, tower); K (padded rows) and V of the head in shared memory; a warp per
@@ -397,7 +430,8 @@ DPH_API int dph_encoder_embed_query(dph_encoder* e, const int64_t* ids, const in
     }
     if (e->precise) DPH_TRY(ensure_split_weights(e));
     // one grouped (two-tower) linear layer: out = act(in . W^T + b) + residual; m = which weight of the layer (0 qkv, 1 attn out, 2 ffn in, 3 ffn out)
-    auto linear = [&](int l, int m, float* const in[2], const float* const bias[2], float* const resid[2], float* const out[2], int N, int K, int act) -> int {
+    auto linear = [&](int l, int m, float* const in[2], const float* const bias[2], float* const resid[2], float* const out[2], int N, int K, int act,
+                      long long rows) -> int {
         const LayerW &L0 = e->tw[0].L[l], &L1 = e->tw[1].L[l];
         const float* Wfull[2];
         switch (m) { case 0: Wfull[0] = L0.Wqkv; Wfull[1] = L1.Wqkv; break; case 1: Wfull[0] = L0.Wo; Wfull[1] = L1.Wo; break;
@@ -405,15 +439,15 @@ DPH_API int dph_encoder_embed_query(dph_encoder* e, const int64_t* ids, const in
         const float* R[2] = {resid ? resid[0] : nullptr, resid ? resid[1] : nullptr};
         if (!e->precise) {
             const float* A[2] = {in[0], in[1]};
-            return dph_launch_gemm_tf32(2, A, Wfull, bias, resid ? R : nullptr, out, (int)T, N, K, act, st, nullptr, nullptr);
+            return dph_launch_gemm_tf32(2, A, Wfull, bias, resid ? R : nullptr, out, (int)rows, N, K, act, st, nullptr, nullptr);
         }
         const float *Whi[2], *Wlo[2];
         for (int t = 0; t < 2; t++) {
             split_ptrs(e, t, l, m, &Whi[t], &Wlo[t]);
-            DPH_TRY(dph_launch_split_tf32(in[t], e->act_hi[t], e->act_lo[t], (long long)T * K, st));
+            DPH_TRY(dph_launch_split_tf32(in[t], e->act_hi[t], e->act_lo[t], rows * K, st));
         }
         const float* Ahi[2] = {e->act_hi[0], e->act_hi[1]}; const float* Alo[2] = {e->act_lo[0], e->act_lo[1]};
-        return dph_launch_gemm_tf32(2, Ahi, Whi, bias, resid ? R : nullptr, out, (int)T, N, K, act, st, Alo, Wlo);
+        return dph_launch_gemm_tf32(2, Ahi, Whi, bias, resid ? R : nullptr, out, (int)rows, N, K, act, st, Alo, Wlo);
     };
     for (int l = 0; l < ENC_LAYERS; l++) {
         const LayerW &L0 = e->tw[0].L[l], &L1 = e->tw[1].L[l];
@@ -423,24 +457,46 @@ DPH_API int dph_encoder_embed_query(dph_encoder* e, const int64_t* ids, const in
         float* A2[2] = {e->a[0], e->a[1]};
         float* FF[2] = {e->ffn[0], e->ffn[1]};
         const float* bqkv[2] = {L0.bqkv, L1.bqkv}; const float* bo[2] = {L0.bo, L1.bo}; const float* bi[2] = {L0.bi, L1.bi}; const float* bo2[2] = {L0.bo2, L1.bo2};
-        DPH_TRY(linear(l, 0, X, bqkv, nullptr, QKV, 3 * ENC_H, ENC_H, 0));
+        DPH_TRY(linear(l, 0, X, bqkv, nullptr, QKV, 3 * ENC_H, ENC_H, 0, T));
         AttnArgs aa; aa.qkv[0] = e->qkv[0]; aa.qkv[1] = e->qkv[1]; aa.ctx[0] = e->ctx[0]; aa.ctx[1] = e->ctx[1]; aa.mask = d_mask; aa.S = S;
         DPH_TRY(launch_attention(aa, B, st));
-        DPH_TRY(linear(l, 1, CTX, bo, X, A2, ENC_H, ENC_H, 0));                                         // dense + residual
+        // Only position 0 of the LAST layer is returned (encoder.py:116-117): after its attention, everything (attention output
+        // projection, both LayerNorms, the FFN) runs on the B [CLS] rows instead of all B*S tokens.
+        const bool last = (l == ENC_LAYERS - 1) && S >= 2;      // (S == 1: the scratch aliasing below needs T >= 2B rows)
+        long long rows = T;
+        if (last) {
+            rows = B;
+            const unsigned gb = (unsigned)((B * (ENC_H / 4) + 255) / 256);
+            gather_cls_kernel<<<dim3(gb, 2), 256, 0, st>>>(e->ctx[0], e->ctx[1], e->ffn[0], e->ffn[1], S, B);                         // ctx rows  -> ffn[:B]  (scratch)
+            gather_cls_kernel<<<dim3(gb, 2), 256, 0, st>>>(e->x[0], e->x[1], e->ffn[0] + (size_t)B * ENC_H, e->ffn[1] + (size_t)B * ENC_H, S, B);   // residual rows
+            DPH_CUDA(cudaGetLastError());
+            CTX[0] = e->ffn[0]; CTX[1] = e->ffn[1];
+            X[0] = e->ffn[0] + (size_t)B * ENC_H; X[1] = e->ffn[1] + (size_t)B * ENC_H;
+            FF[0] = e->qkv[0]; FF[1] = e->qkv[1];                                                                                     // qkv is dead after attention: [B, 3072] fits
+        }
+        DPH_TRY(linear(l, 1, CTX, bo, X, A2, ENC_H, ENC_H, 0, rows));                                   // dense + residual
         LnArgs ln1; for (int t = 0; t < 2; t++) { ln1.in[t] = e->a[t]; ln1.out[t] = e->a[t]; } ln1.g[0] = L0.ln1g; ln1.g[1] = L1.ln1g; ln1.b[0] = L0.ln1b; ln1.b[1] = L1.ln1b;
-        layernorm_kernel<<<dim3((unsigned)T, 2), 256, 0, st>>>(ln1);
+        ln1.rows = rows; ln1.in_stride = ENC_H; ln1.out_stride = ENC_H;
+        layernorm_kernel<<<dim3((unsigned)((rows + 7) / 8), 2), 256, 0, st>>>(ln1);
         DPH_CUDA(cudaGetLastError());
-        DPH_TRY(linear(l, 2, A2, bi, nullptr, FF, ENC_FF, ENC_H, 1));                                    // intermediate + erf-GELU
-        DPH_TRY(linear(l, 3, FF, bo2, A2, X, ENC_H, ENC_FF, 0));                                         // output dense + residual
-        LnArgs ln2; for (int t = 0; t < 2; t++) { ln2.in[t] = e->x[t]; ln2.out[t] = e->x[t]; } ln2.g[0] = L0.ln2g; ln2.g[1] = L1.ln2g; ln2.b[0] = L0.ln2b; ln2.b[1] = L1.ln2b;
-        layernorm_kernel<<<dim3((unsigned)T, 2), 256, 0, st>>>(ln2);
+        DPH_TRY(linear(l, 2, A2, bi, nullptr, FF, ENC_FF, ENC_H, 1, rows));                              // intermediate + erf-GELU
+        float* XO[2] = {last ? e->ctx[0] : e->x[0], last ? e->ctx[1] : e->x[1]};                         // last layer: dense [B,768] result in ctx
+        DPH_TRY(linear(l, 3, FF, bo2, A2, XO, ENC_H, ENC_FF, 0, rows));                                  // output dense + residual
+        LnArgs ln2; for (int t = 0; t < 2; t++) { ln2.in[t] = XO[t]; ln2.out[t] = XO[t]; } ln2.g[0] = L0.ln2g; ln2.g[1] = L1.ln2g; ln2.b[0] = L0.ln2b; ln2.b[1] = L1.ln2b;
+        ln2.rows = rows; ln2.in_stride = ENC_H; ln2.out_stride = ENC_H;
+        layernorm_kernel<<<dim3((unsigned)((rows + 7) / 8), 2), 256, 0, st>>>(ln2);
         DPH_CUDA(cudaGetLastError());
     }
     // hidden state at position 0 of every sequence ([:, :1, :], encoder.py:116-117)
     float* ds = mem == DPH_MEM_HOST ? e->out_s : start_out;
     float* de = mem == DPH_MEM_HOST ? e->out_e : end_out;
-    DPH_CUDA(cudaMemcpy2DAsync(ds, ENC_H * 4, e->x[0], (size_t)S * ENC_H * 4, ENC_H * 4, B, cudaMemcpyDeviceToDevice, st));
-    DPH_CUDA(cudaMemcpy2DAsync(de, ENC_H * 4, e->x[1], (size_t)S * ENC_H * 4, ENC_H * 4, B, cudaMemcpyDeviceToDevice, st));
+    if (S >= 2) {
+        DPH_CUDA(cudaMemcpyAsync(ds, e->ctx[0], (size_t)B * ENC_H * 4, cudaMemcpyDeviceToDevice, st));
+        DPH_CUDA(cudaMemcpyAsync(de, e->ctx[1], (size_t)B * ENC_H * 4, cudaMemcpyDeviceToDevice, st));
+    } else {
+        DPH_CUDA(cudaMemcpyAsync(ds, e->x[0], (size_t)B * ENC_H * 4, cudaMemcpyDeviceToDevice, st));
+        DPH_CUDA(cudaMemcpyAsync(de, e->x[1], (size_t)B * ENC_H * 4, cudaMemcpyDeviceToDevice, st));
+    }
     if (mem == DPH_MEM_HOST) {
         DPH_CUDA(cudaMemcpyAsync(start_out, ds, (size_t)B * ENC_H * 4, cudaMemcpyDeviceToHost, st));
         DPH_CUDA(cudaMemcpyAsync(end_out, de, (size_t)B * ENC_H * 4, cudaMemcpyDeviceToHost, st));
