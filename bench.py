@@ -289,13 +289,16 @@ def run_ours(args):
     pair_mode = ix.local.last_used_pair_mode()
     traffic = None
     tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
+    limiter = None
     if os.path.exists(tp):
         tj = json.load(open(tp))
         traffic = tj.get("dram_bytes_per_launch") if pair_mode else tj.get("single_query_kernel", {}).get("dram_bytes_per_launch")
+        if pair_mode and tj.get("lsu_data_pipe_pct"):      # ncu: the pair kernel's own limiter is the LSU data pipe, not DRAM
+            limiter = {"pipe": "lsu data pipe (shared-memory gathers + code loads)", "pct_of_peak": tj["lsu_data_pipe_pct"], "source": tj.get("source")}
     roofline = {"kernel": "scan_pair_kernel" if pair_mode else "scan_kernel<FAST>", "gathers": "two queries per gather (pair-packed)" if pair_mode else "one query per gather", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                 "peak_kind": pk_kind, "traffic": traffic, "kernel_ms": 1000.0 * t_scan, "algorithmic_bytes_per_launch": sum(alg_bytes) / len(alg_bytes),
                 "share_of_step": 1000.0 * t_scan / (ms_prof_pass / K), "step_ms_same_pass": ms_prof_pass / K,
-                "how": "CUDA events around the kernel inside a back-to-back K-step loop on the launching stream"}
+                "how": "CUDA events around the kernel inside a back-to-back K-step loop on the launching stream", "limiter": limiter}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on a bounded sample of the same workload ----
     cpu = None

@@ -104,7 +104,11 @@ struct __align__(16) DphSeg {
 struct DphWork {       // device scalars written by the plan kernel
     long long total_blocks;
 };
-struct DphPairWork {   // pair mode: total (list, item, block) work units and the per-CTA share
-    long long total_blocks;
-    long long per;
+struct DphPairWork {   // pair mode: the work queue of (list, block segment, item) units the scan CTAs pull from
+    long long total_blocks;         // sum over items of the list's blocks
+    long long per;                  // blocks per segment (a list longer than this is cut into several units per item)
+    int total_units;
+    int next_unit;                  // queue head, advanced with atomicAdd by the scan CTAs; reset by the plan
 };
+#define DPH_PAIR_SEG_MIN 128        // shortest segment worth rebuilding the packed 192 KB LUT for
+#define DPH_PAIR_UNITS_PER_CTA 16   // lists are cut only when the batch has fewer than this many whole-list units per CTA

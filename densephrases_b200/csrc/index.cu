@@ -116,7 +116,7 @@ DPH_API void dph_index_free(dph_index* ix) {
     for (void* p : ptrs) if (p) cudaFree(p);
     DevBuf* bufs[] = {&ix->xdev, &ix->xr, &ix->S, &ix->key, &ix->cd, &ix->lut_scan, &ix->lut_canon, &ix->lutmax, &ix->segs, &ix->wpre, &ix->qinfo,
                       &ix->cand, &ix->cand_off, &ix->cand_cnt, &ix->gthr, &ix->flags, &ix->work, &ix->Dp, &ix->Ip, &ix->Gp, &ix->Dh, &ix->Ih, &ix->eps, &ix->nseg, &ix->lutmin, &ix->lutmaxv, &ix->lutq, &ix->qparams, &ix->gdense,
-                      &ix->pl_cnt, &ix->pl_fill, &ix->pl_off, &ix->pl_blockpre, &ix->pl_entries, &ix->pairwork, &ix->csplit, &ix->xsplit, &ix->candkeys, &ix->cflags};
+                      &ix->pl_cnt, &ix->pl_fill, &ix->pl_off, &ix->pl_blockpre, &ix->pl_entries, &ix->pl_unitpre, &ix->pl_units, &ix->pairwork, &ix->csplit, &ix->xsplit, &ix->candkeys, &ix->cflags};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < DPH_PROF_RING; i++) { if (ix->ev0[i]) cudaEventDestroy(ix->ev0[i]); if (ix->ev1[i]) cudaEventDestroy(ix->ev1[i]); }
     delete ix;
@@ -338,7 +338,7 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
     if (keep_pair > 1536 - DPH_SCAN_THREADS || ix->scan_mode == DPH_SCAN_SINGLE) pair = false;
     const int keep_fast = pair ? keep_pair : keep_single;
     if (!pair) DPH_TRY(ix->lut_scan.ensure((size_t)n * DPH_LUT_SCAN_FLOATS * 4));
-    DPH_TRY(ix->cand.ensure(((size_t)(2 * grid + 2 * n + 2) + (pair ? (size_t)(3 * n * nprobe + 3 * grid + n + 16) : 0)) * keep_max * 8));
+    DPH_TRY(ix->cand.ensure(((size_t)(2 * grid + 2 * n + 2) + (pair ? (size_t)(n * nprobe + 2 * DPH_PAIR_UNITS_PER_CTA * grid + 2 * n + 16) : 0)) * keep_max * 8));
     DPH_TRY(ix->cand_off.ensure((size_t)(n + 1) * 8));
     DPH_TRY(ix->cand_cnt.ensure((size_t)n * 4));
     DPH_TRY(ix->gthr.ensure((size_t)n * 4));
@@ -355,6 +355,9 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
         DPH_TRY(ix->pl_off.ensure((size_t)(ix->nlist + 1) * 4));
         DPH_TRY(ix->pl_blockpre.ensure((size_t)(ix->nlist + 1) * 8));
         DPH_TRY(ix->pl_entries.ensure((size_t)n * nprobe * 4));
+        DPH_TRY(ix->pl_unitpre.ensure((size_t)(ix->nlist + 1) * 4));
+        // units <= sum_l items_l * (blocks_l / seg + 1) <= total_blocks / seg + items <= UNITS_PER_CTA * grid + n * nprobe
+        DPH_TRY(ix->pl_units.ensure((size_t)(n * nprobe + DPH_PAIR_UNITS_PER_CTA * grid + 16) * 8));
         DPH_TRY(ix->pairwork.ensure(sizeof(DphPairWork)));
     }
     ix->last_n = n;

@@ -59,7 +59,7 @@ struct dph_index {
     // per-batch workspace
     DevBuf xdev, xr, S, key, cd, lut_scan, lut_canon, lutmax, segs, wpre, qinfo, cand, cand_off, cand_cnt, gthr, flags,
         work, Dp, Ip, Gp, Dh, Ih, eps, nseg,
-        lutmin, lutmaxv, lutq, qparams, gdense, pl_cnt, pl_fill, pl_off, pl_blockpre, pl_entries, pairwork,
+        lutmin, lutmaxv, lutq, qparams, gdense, pl_cnt, pl_fill, pl_off, pl_blockpre, pl_entries, pl_unitpre, pl_units, pairwork,
         csplit, xsplit, candkeys, cflags;
     int64_t csplit_lo = -1, csplit_nl = -1;
     int coarse_tc = 1;                 // tensor-core coarse quantizer with exact re-rank (0: always the SIMT sequential-k GEMM)

@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(256) plan_segs_kernel(PlanArgs a) {
 struct PlanScanArgs {
     const unsigned* qblocks; long long n; int keep; int grid;
     long long* qpre; long long* cand_off; int* cand_cnt; unsigned* gthr; DphWork* work;
-    const DphPairWork* pairwork; const int* nseg;     // pair mode (nullable): a query is flushed once per (CTA, item) visit
+    const DphPairWork* pairwork; const int* nseg;     // pair mode (nullable): a query is flushed once per (list, segment) unit it is part of
 };
 __global__ void __launch_bounds__(1024) plan_scan_kernel(PlanScanArgs a) {
     __shared__ long long wsum[32];
@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(PlanScanArgs a) {
             long long qb = (long long)a.qblocks[q];
             if (qb > 0) {
                 long long parts = qb / per + 2;
-                if (a.pairwork) parts = 3ll * a.nseg[q] + qb / per + 1;
+                if (a.pairwork) parts = (long long)a.nseg[q] + qb / per + 1;        // sum over its lists of ceil(blocks / segment)
                 else if (parts > a.grid) parts = a.grid;
                 v = parts * a.keep;
             }
@@ -622,11 +622,14 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(PlanScanArgs a) {
 
 // =================================================================================================
 // pair plan: invert (query -> probed lists) into (list -> probing queries), pair the probes of each list two by two into
-// work items, and linearise (list, item, block) for the pair-packed scan kernel.
+// work items, and emit the work queue of the pair-packed scan kernel: units (list, block segment, item), items of the same
+// list segment ADJACENT in the queue.  The scan CTAs pull units in queue order, so the items of a list are scanned at the
+// same time by different CTAs and all but the first reader of a code block hit L2 instead of HBM.
 // =================================================================================================
 struct PairPlanArgs {
     const int* key; long long nq_probes; int nprobe; const int* list_len; long long list_lo, list_hi, nlist; int grid;
     int* cnt; int* fill; int* off; long long* blockpre; unsigned* entries; DphPairWork* work;
+    int* unitpre; unsigned long long* units;
 };
 __global__ void pair_count_kernel(PairPlanArgs a) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -672,11 +675,57 @@ __global__ void __launch_bounds__(1024) pair_scan_kernel(PairPlanArgs a) {
         if (tid == 1023) { ca = ea + va; cb = eb + vb; }
         __syncthreads();
     }
+    __shared__ long long segb_s;
     if (tid == 0) {
         a.off[a.list_hi] = (int)ca; a.blockpre[a.list_hi] = cb;
+        long long segb = (cb + (long long)a.grid * DPH_PAIR_UNITS_PER_CTA - 1) / ((long long)a.grid * DPH_PAIR_UNITS_PER_CTA);
+        if (segb < DPH_PAIR_SEG_MIN) segb = DPH_PAIR_SEG_MIN;
         a.work->total_blocks = cb;
-        a.work->per = cb / a.grid > 0 ? cb / a.grid : 1;
+        a.work->per = segb;
+        segb_s = segb; ca = 0;
     }
+    __syncthreads();
+    // second pass: units per list = items x segments -> unitpre (exclusive prefix)
+    const long long segb = segb_s;
+    for (long long base = a.list_lo; base < a.list_hi; base += 1024) {
+        const long long l = base + tid;
+        long long va = 0;
+        if (l < a.list_hi) {
+            const long long nb = (a.list_len[l] + 31) >> 5;
+            va = (long long)((a.cnt[l] + 1) >> 1) * ((nb + segb - 1) / segb);
+        }
+        long long ia = va;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { long long t1 = __shfl_up_sync(0xffffffffu, ia, off); if (lane >= off) ia += t1; }
+        if (lane == 31) wsa[warp] = ia;
+        __syncthreads();
+        if (warp == 0) {
+            long long w1 = wsa[lane], i1 = w1;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { long long t1 = __shfl_up_sync(0xffffffffu, i1, off); if (lane >= off) i1 += t1; }
+            wsa[lane] = i1 - w1;
+        }
+        __syncthreads();
+        const long long ea = ca + wsa[warp] + ia - va;
+        if (l < a.list_hi) a.unitpre[l] = (int)ea;
+        __syncthreads();
+        if (tid == 1023) ca = ea + va;
+        __syncthreads();
+    }
+    if (tid == 0) { a.work->total_units = (int)ca; a.work->next_unit = 0; }
+}
+// one thread per list: unit = list | item << 32 | segment << 48, ordered (segment, item) inside the list
+__global__ void pair_units_kernel(PairPlanArgs a) {
+    const long long l = a.list_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= a.list_hi) return;
+    const int items = (a.cnt[l] + 1) >> 1;
+    if (items == 0) return;
+    const long long segb = a.work->per, nb = (a.list_len[l] + 31) >> 5;
+    const int nsegs = (int)((nb + segb - 1) / segb);
+    unsigned long long* u = a.units + a.unitpre[l];
+    for (int s = 0; s < nsegs; s++)
+        for (int it = 0; it < items; it++)
+            *u++ = (unsigned long long)l | ((unsigned long long)it << 32) | ((unsigned long long)s << 48);
 }
 __global__ void pair_fill_kernel(PairPlanArgs a) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -703,13 +752,14 @@ int dph_launch_plan(dph_index* ix, int64_t n, int k, int keep, int grid, const i
         p.key = ix->key.as<int>(); p.nq_probes = n * ix->nprobe; p.nprobe = ix->nprobe; p.list_len = ix->list_len; p.list_lo = ix->list_lo;
         p.list_hi = ix->list_hi; p.nlist = ix->nlist; p.grid = grid; p.cnt = ix->pl_cnt.as<int>(); p.fill = ix->pl_fill.as<int>();
         p.off = ix->pl_off.as<int>(); p.blockpre = ix->pl_blockpre.as<long long>(); p.entries = ix->pl_entries.as<unsigned>();
-        p.work = ix->pairwork.as<DphPairWork>();
+        p.work = ix->pairwork.as<DphPairWork>(); p.unitpre = ix->pl_unitpre.as<int>(); p.units = ix->pl_units.as<unsigned long long>();
         DPH_CUDA(cudaMemsetAsync(p.cnt, 0, (size_t)ix->nlist * 4, st));
         DPH_CUDA(cudaMemsetAsync(p.fill, 0, (size_t)ix->nlist * 4, st));
         const unsigned nb = (unsigned)((p.nq_probes + 255) / 256);
         pair_count_kernel<<<nb, 256, 0, st>>>(p);
         pair_scan_kernel<<<1, 1024, 0, st>>>(p);
         pair_fill_kernel<<<nb, 256, 0, st>>>(p);
+        if (ix->list_hi > ix->list_lo) pair_units_kernel<<<(unsigned)((ix->list_hi - ix->list_lo + 255) / 256), 256, 0, st>>>(p);
         DPH_CUDA(cudaGetLastError());
     }
     PlanScanArgs b;

@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(NT, 1) scan_kernel(ScanArgs a) {
 // =================================================================================================
 struct PairScanArgs {
     const uint8_t* codes; const long long* blk_off; const int* list_len;
-    const int* pl_cnt; const int* pl_off; const long long* blockpre; const unsigned* entries; const DphPairWork* work;
+    const int* pl_cnt; const int* pl_off; const unsigned long long* units; const unsigned* entries; const DphPairWork* work; int* next_unit;
     const unsigned short* lutq; const float2* qparams; const float* cd; const unsigned* gdense;
     unsigned* gthr; unsigned long long* cand; const long long* cand_off; int* cand_cnt;
     long long list_lo, list_hi; int nprobe; int keep;
@@ -290,7 +290,7 @@ struct PairScanArgs {
 struct PairShared {
     unsigned long long cbuf[2][PCAP];
     SelectScratch sc;
-    int cnt[2]; unsigned thr[2]; int base[2]; int ndone; int ndone_snap;
+    int cnt[2]; unsigned thr[2]; int base[2]; int ndone; int ndone_snap; int unit;
 };
 template <int IMM> __device__ __forceinline__ unsigned lds_imm_u32(unsigned addr) {
     unsigned v;
@@ -345,23 +345,24 @@ __global__ void __launch_bounds__(NT, 1) scan_pair_kernel(PairScanArgs a) {
     unsigned char* const smem = dph_smem;
     PairShared* sh = reinterpret_cast<PairShared*>(smem + SMEM_LUT_FAST);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long T = a.work->total_blocks;
-    const long long G = gridDim.x, c = blockIdx.x;
-    const long long g0 = T * c / G, g1 = T * (c + 1) / G;
-    if (g0 >= g1) return;
-    long long lo = a.list_lo, hi = a.list_hi;                  // last l with blockpre[l] <= g0
-    while (hi - lo > 1) { long long mid = (lo + hi) >> 1; if (a.blockpre[mid] <= g0) lo = mid; else hi = mid; }
-    long long l = lo, g = g0;
+    const int total_units = a.work->total_units;
+    const unsigned segb = (unsigned)a.work->per;
     const unsigned ywin = (((unsigned)__cvta_generic_to_shared(dph_smem)) & 0xFF000000u) | ((unsigned)lane * 4u);
 
-    while (g < g1) {
-        while (a.blockpre[l + 1] <= g) l++;
+    while (true) {
+        // pull the next unit of the queue: consecutive units are the items of one list segment, so they run at the same time on
+        // different CTAs and share the segment's code blocks through L2
+        if (tid == 0) sh->unit = atomicAdd(a.next_unit, 1);
+        __syncthreads();
+        const int u = sh->unit;
+        if (u >= total_units) break;
+        const unsigned long long ud = a.units[u];
+        const long long l = (long long)(ud & 0xFFFFFFFFull);
+        const int it = (int)((ud >> 32) & 0xFFFFull);
         const int len = a.list_len[l];
-        const long long nb = (len + 31) >> 5;
-        const long long rel = g - a.blockpre[l];
-        const int it = (int)(rel / nb);
-        const unsigned bi0 = (unsigned)(rel % nb);
-        const unsigned bend = (unsigned)((nb - bi0 < g1 - g) ? nb : bi0 + (g1 - g));
+        const unsigned nb = (unsigned)((len + 31) >> 5);
+        const unsigned bi0 = (unsigned)(ud >> 48) * segb;
+        const unsigned bend = (nb - bi0 < segb) ? nb : bi0 + segb;
         const int e0 = a.pl_off[l] + 2 * it;
         const bool has_b = (2 * it + 1) < a.pl_cnt[l];
         const unsigned ea = a.entries[e0], eb = has_b ? a.entries[e0 + 1] : ea;
@@ -464,7 +465,6 @@ __global__ void __launch_bounds__(NT, 1) scan_pair_kernel(PairScanArgs a) {
             for (int i = tid; i < cnt; i += NT)
                 if (basep + i < cap) a.cand[off + basep + i] = sh->cbuf[s2i][i];
         }
-        g += (long long)(bend - bi0);
     }
 }
 
@@ -510,8 +510,8 @@ int dph_launch_scan_pair(dph_index* ix, int64_t n, int keep, int grid, cudaStrea
     DPH_TRY(dph_scan_setup_attrs());
     PairScanArgs a;
     a.codes = ix->codes; a.blk_off = (const long long*)ix->blk_off; a.list_len = ix->list_len; a.pl_cnt = ix->pl_cnt.as<int>();
-    a.pl_off = ix->pl_off.as<int>(); a.blockpre = ix->pl_blockpre.as<long long>(); a.entries = ix->pl_entries.as<unsigned>();
-    a.work = ix->pairwork.as<DphPairWork>(); a.lutq = ix->lutq.as<unsigned short>(); a.qparams = ix->qparams.as<float2>();
+    a.pl_off = ix->pl_off.as<int>(); a.units = ix->pl_units.as<unsigned long long>(); a.entries = ix->pl_entries.as<unsigned>();
+    a.work = ix->pairwork.as<DphPairWork>(); a.next_unit = &ix->pairwork.as<DphPairWork>()->next_unit; a.lutq = ix->lutq.as<unsigned short>(); a.qparams = ix->qparams.as<float2>();
     a.cd = ix->cd.as<float>(); a.gdense = ix->gdense.as<unsigned>(); a.gthr = ix->gthr.as<unsigned>();
     a.cand = ix->cand.as<unsigned long long>(); a.cand_off = ix->cand_off.as<long long>(); a.cand_cnt = ix->cand_cnt.as<int>();
     a.list_lo = ix->list_lo; a.list_hi = ix->list_hi; a.nprobe = ix->nprobe; a.keep = keep;
