@@ -15,6 +15,7 @@
 int dph_launch_gemm_tf32(int group, const float* const* A, const float* const* W, const float* const* bias, const float* const* residual,
                          float* const* out, int M, int N, int K, int act, cudaStream_t st, const float* const* A_lo, const float* const* W_lo);
 int dph_launch_split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t st);
+int dph_launch_attention_tc(const float* const qkv[2], float* const ctx[2], const long long* mask, int B, int S, long long T, cudaStream_t st);   // attention_tc.cu
 
 struct LayerW { const float *Wqkv, *bqkv, *Wo, *bo, *ln1g, *ln1b, *Wi, *bi, *Wo2, *bo2, *ln2g, *ln2b; };
 struct TowerW { const float *word, *pos, *type, *embg, *embb; LayerW L[ENC_LAYERS]; };
@@ -26,6 +27,7 @@ struct dph_encoder {
     TowerW tw[2];
     // 3xTF32 mode: (hi, lo) copies of the four GEMM weight matrices of every layer, made lazily on the first precise forward
     int precise = 0;
+    int attention_tc = 1;                        // S <= 64 and not precise: attention on the tensor cores (attention_tc.cu); 0: SIMT fp32 kernels below
     float* wsplit[2] = {nullptr, nullptr};       // per tower: for each layer [Wqkv_hi, Wqkv_lo, Wo_hi, Wo_lo, Wi_hi, Wi_lo, Wo2_hi, Wo2_lo]
     float *act_hi[2] = {}, *act_lo[2] = {};      // split copy of the current GEMM input activation (up to T x 3072)
     // workspace for T tokens
@@ -343,6 +345,27 @@ DPH_API void dph_encoder_free(dph_encoder* e) {
 }
 DPH_API int dph_encoder_set_stream(dph_encoder* e, void* s) { e->stream = (cudaStream_t)s; return 0; }
 DPH_API int dph_encoder_set_precision(dph_encoder* e, int precise) { e->precise = precise ? 1 : 0; return 0; }
+DPH_API int dph_encoder_set_attention(dph_encoder* e, int tensor_core) { e->attention_tc = tensor_core ? 1 : 0; return 0; }
+
+// C ABI (test / standalone use): one BERT self-attention over a [B*S, 2304] QKV activation (device pointers) -> ctx [B*S, 768].
+DPH_API int dph_attention_bert(const float* qkv, const int64_t* mask, int B, int S, float* ctx, int tensor_core, void* cuda_stream) {
+    DPH_CHECK(qkv && mask && ctx && B >= 1 && S >= 1 && S <= ENC_MAX_S, "attention: bad arguments");
+    DPH_CHECK(!tensor_core || S <= 64, "tensor-core attention handles S <= 64");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    float* scratch = nullptr;                            // the launchers run two towers: the second one repeats the first into scratch
+    DPH_CUDA(cudaMalloc((void**)&scratch, (size_t)B * S * ENC_H * 4));
+    int rc;
+    if (tensor_core) {
+        const float* q2[2] = {qkv, qkv}; float* c2[2] = {ctx, scratch};
+        rc = dph_launch_attention_tc(q2, c2, (const long long*)mask, B, S, (long long)B * S, st);
+    } else {
+        AttnArgs aa; aa.qkv[0] = qkv; aa.qkv[1] = qkv; aa.ctx[0] = ctx; aa.ctx[1] = scratch; aa.mask = (const long long*)mask; aa.S = S;
+        rc = launch_attention(aa, B, st);
+    }
+    cudaStreamSynchronize(st);
+    cudaFree(scratch);
+    return rc;
+}
 
 static const int64_t kGemmW[4] = {(int64_t)3 * ENC_H * ENC_H, (int64_t)ENC_H * ENC_H, (int64_t)ENC_FF * ENC_H, (int64_t)ENC_H * ENC_FF};
 static int64_t split_layer_floats() { return 2 * (kGemmW[0] + kGemmW[1] + kGemmW[2] + kGemmW[3]); }
@@ -459,7 +482,12 @@ DPH_API int dph_encoder_embed_query(dph_encoder* e, const int64_t* ids, const in
         const float* bqkv[2] = {L0.bqkv, L1.bqkv}; const float* bo[2] = {L0.bo, L1.bo}; const float* bi[2] = {L0.bi, L1.bi}; const float* bo2[2] = {L0.bo2, L1.bo2};
         DPH_TRY(linear(l, 0, X, bqkv, nullptr, QKV, 3 * ENC_H, ENC_H, 0, T));
         AttnArgs aa; aa.qkv[0] = e->qkv[0]; aa.qkv[1] = e->qkv[1]; aa.ctx[0] = e->ctx[0]; aa.ctx[1] = e->ctx[1]; aa.mask = d_mask; aa.S = S;
-        DPH_TRY(launch_attention(aa, B, st));
+        if (e->attention_tc && !e->precise && S <= 64) {
+            const float* q2[2] = {e->qkv[0], e->qkv[1]}; float* c2[2] = {e->ctx[0], e->ctx[1]};
+            DPH_TRY(dph_launch_attention_tc(q2, c2, d_mask, B, S, T, st));
+        } else {
+            DPH_TRY(launch_attention(aa, B, st));
+        }
         // Only position 0 of the LAST layer is returned (encoder.py:116-117): after its attention, everything (attention output
         // projection, both LayerNorms, the FFN) runs on the B [CLS] rows instead of all B*S tokens.
         const bool last = (l == ENC_LAYERS - 1) && S >= 2;      // (S == 1: the scratch aliasing below needs T >= 2B rows)

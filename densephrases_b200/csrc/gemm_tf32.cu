@@ -10,9 +10,8 @@
 // allocator, warps 4-7 = epilogue (tcgen05.ld 32x32b -> bias / erf-GELU / residual -> 128-byte row segments to global).
 // ~97 KB of shared memory and 128 TMEM columns per CTA -> two CTAs per SM, so one tile's epilogue overlaps the
 // neighbour's main loop.  blockIdx.z selects the problem of a group (the two towers run as one launch).
-#include "common.cuh"
+#include "umma.cuh"
 #include "../../include/dph_b200.h"
-#include <cuda.h>
 
 #define GM_BM 128
 #define GM_BN 128
@@ -28,45 +27,6 @@ struct GemmArgs {
     const float* bias[GM_MAX_GROUP]; const float* residual[GM_MAX_GROUP]; float* out[GM_MAX_GROUP];
     int M, N, K, act;     // act: 0 none, 1 erf-GELU
 };
-
-// ---- PTX wrappers ----------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc, unsigned idesc, unsigned accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(unsigned bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor, sm_100 version 1).
-__device__ __forceinline__ unsigned long long make_sw128_desc(unsigned smem_addr) {
-    unsigned long long d = 0;
-    d |= (unsigned long long)((smem_addr & 0x3FFFF) >> 4);        // start address, bits [0,14)
-    d |= (unsigned long long)1 << 16;                            // leading byte offset (ignored for swizzled K-major), bits [16,30)
-    d |= (unsigned long long)(1024 >> 4) << 32;                  // stride byte offset, bits [32,46)
-    d |= (unsigned long long)1 << 46;                            // descriptor version (Blackwell)
-    d |= (unsigned long long)2 << 61;                            // layout type SWIZZLE_128B
-    return d;
-}
 
 template <int SPLIT>
 __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) gemm_tf32_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs args) {
@@ -157,16 +117,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) gemm_tf32_kernel(const __g
         for (int c = 0; c < GM_BN / 32; c++) {
             unsigned v[32];
             const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(c * 32);
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-                  "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-                  "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tmem_ld32(taddr, v);
             const int col0 = n_blk * GM_BN + c * 32;
             if (row < args.M) {
 #pragma unroll
@@ -195,29 +146,31 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) gemm_tf32_kernel(const __g
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static PFN_encodeTiled g_encode = nullptr;
-static int get_encode() {
-    if (g_encode) return 0;
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    DPH_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-    DPH_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
-    g_encode = (PFN_encodeTiled)fn;
+static dph_PFN_encodeTiled g_encode = nullptr;
+int dph_tensormap_encoder(dph_PFN_encodeTiled* out) {
+    if (!g_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        DPH_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        DPH_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+        g_encode = (dph_PFN_encodeTiled)fn;
+    }
+    if (out) *out = g_encode;
     return 0;
 }
-// rows x K fp32 row-major matrix -> tensor map with a [GM_BK x 128] box, 128-byte swizzle, zero fill out of bounds
-static int make_map(CUtensorMap* map, const float* ptr, long long rows, int K) {
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-    cuuint32_t box[2] = {GM_BK, 128};
+int dph_make_map_f32(CUtensorMap* map, const float* ptr, long long rows, long long cols, long long ld, int box_rows) {
+    DPH_TRY(dph_tensormap_encoder(nullptr));
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DPH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
     return 0;
 }
+// rows x K fp32 row-major matrix -> tensor map with a [GM_BK x 128] box
+static int make_map(CUtensorMap* map, const float* ptr, long long rows, int K) { return dph_make_map_f32(map, ptr, rows, K, K, 128); }
 
 // x -> (hi, lo): hi = round-to-nearest TF32 of x, lo = round-to-nearest TF32 of (x - hi)  (both exact TF32 values)
 __global__ void split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo, long long n4) {
@@ -250,7 +203,6 @@ int dph_launch_gemm_tf32(int group, const float* const* A, const float* const* W
                          float* const* out, int M, int N, int K, int act, cudaStream_t st, const float* const* A_lo, const float* const* W_lo) {
     DPH_CHECK(group >= 1 && group <= GM_MAX_GROUP, "gemm group size");
     DPH_CHECK(N % GM_BN == 0 && K % GM_BK == 0 && M >= 1, "gemm_tf32 needs N % 128 == 0 and K % 32 == 0");
-    DPH_TRY(get_encode());
     const bool split = A_lo != nullptr && W_lo != nullptr;
     const int smem_fast = GM_STAGES * 2 * GM_TILE_BYTES + 1024, smem_split = GM_STAGES * 4 * GM_TILE_BYTES + 1024;
     static bool attr = false;

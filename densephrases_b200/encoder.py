@@ -72,6 +72,10 @@ class Encoder(object):
         self.precise = bool(precise)
         L.check(L.lib().dph_encoder_set_precision(self._h, int(self.precise)))
 
+    def set_attention(self, tensor_core=True):
+        """True (default): tensor-core attention for S <= 64 in the 1xTF32 mode; False: fp32 SIMT attention always."""
+        L.check(L.lib().dph_encoder_set_attention(self._h, int(bool(tensor_core))))
+
     # -- torch.nn.Module-style surface the callers touch (embed_utils.py:393, single_utils.py:116) --
     def eval(self):
         self.training = False

@@ -140,6 +140,12 @@ int dph_encoder_load_tower(dph_encoder* e, int tower, const float* blob, int mem
 /* 0 (default): GEMMs as one TF32 MMA per product -- what torch 1.9 (the reference's pin) does for fp32 matmuls on Ampere+;
  * 1: 3xTF32 split GEMMs, fp32-accurate (matches the reference's CPU/fp32 path to ~1e-5). */
 int dph_encoder_set_precision(dph_encoder* e, int precise);
+/* 1 (default): self-attention of sequences with S <= 64 on the tensor cores (TF32 operands, fp32 accumulation and softmax) unless
+ * precise is set; 0: always the fp32 SIMT attention kernels. */
+int dph_encoder_set_attention(dph_encoder* e, int tensor_core);
+/* One BERT-base self-attention (12 heads x 64; HF BertSelfAttention as used by encoder.py:101-118) on device buffers:
+ * qkv fp32 [B*S, 2304] = (Q | K | V), mask int64 [B,S] -> ctx fp32 [B*S, 768].  tensor_core = 1 needs S <= 64. */
+int dph_attention_bert(const float* qkv, const int64_t* attention_mask, int B, int S, float* ctx, int tensor_core, void* cuda_stream);
 /* input_ids / attention_mask / token_type_ids int64 [B,S] (S <= 384); start_out / end_out fp32 [B,768] = hidden state at
  * position 0 of each tower (the reference returns them as [B,1,768]). */
 int dph_encoder_embed_query(dph_encoder* e, const int64_t* input_ids, const int64_t* attention_mask, const int64_t* token_type_ids,

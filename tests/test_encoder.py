@@ -95,3 +95,45 @@ def test_cuda_encoder_3xtf32_is_fp32_accurate():
     enc.set_precision(False)
     s2, _ = enc(input_ids_=ids, attention_mask_=mask, token_type_ids_=tt, return_query=True)
     assert (s2.cpu() - start).abs().max().item() > ds
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,S", [(5, 64), (3, 24), (2, 8), (7, 37)])
+def test_tensor_core_attention_matches_simt_attention(B, S):
+    """attention_tc.cu (tcgen05 TF32 QK^T and PV, S <= 64, padded / ragged masks) against the fp32 SIMT attention kernels inside the
+    same encoder: the only difference is TF32 rounding of Q, K, P, V operands -> [CLS] vectors within 2e-2, cosine > 0.9999."""
+    from densephrases_b200.encoder import BertGeometry, Encoder, random_state_dict, synthetic_query_batch
+    geo = BertGeometry(vocab_size=2000)
+    enc = Encoder(geo, state_dict=random_state_dict(geo, 3))
+    ids, mask, tt = synthetic_query_batch(B, S, geo.vocab_size, 5)
+    enc.set_attention(True)
+    s1, e1 = enc(input_ids_=ids, attention_mask_=mask, token_type_ids_=tt, return_query=True)
+    enc.set_attention(False)
+    s0, e0 = enc(input_ids_=ids, attention_mask_=mask, token_type_ids_=tt, return_query=True)
+    d = max((s1 - s0).abs().max().item(), (e1 - e0).abs().max().item())
+    print(f"B={B} S={S}: tensor-core vs SIMT attention max|diff| {d:.2e}")
+    assert torch.isfinite(s1).all() and torch.isfinite(e1).all()
+    assert d < 2e-2 and cos(s1, s0).min() > 0.9999 and cos(e1, e0).min() > 0.9999
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tensor_core,tol", [(0, 2e-5), (1, 1e-2)])
+@pytest.mark.parametrize("B,S", [(3, 64), (4, 20)])
+def test_attention_kernels_against_torch(B, S, tensor_core, tol):
+    """One BERT self-attention (12 heads x 64) through the C ABI against torch fp32: softmax(QK^T/8 + (1-mask)*-1e4) V."""
+    from densephrases_b200 import _lib as L
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(S)
+    qkv = torch.randn((B * S, 2304), generator=g, device="cuda")
+    mask = torch.ones((B, S), dtype=torch.int64, device="cuda")
+    for b in range(B):
+        mask[b, S - b * 3:] = 0
+    ctx = torch.zeros((B * S, 768), device="cuda")
+    L.check(L.lib().dph_attention_bert(qkv.data_ptr(), mask.data_ptr(), B, S, ctx.data_ptr(), tensor_core, None))
+    torch.cuda.synchronize()
+    q, k, v = (qkv[:, i * 768:(i + 1) * 768].reshape(B, S, 12, 64).permute(0, 2, 1, 3) for i in range(3))
+    sc = q @ k.transpose(-1, -2) / 8.0 + ((1.0 - mask.float()) * -10000.0)[:, None, None, :]
+    ref = (torch.softmax(sc, dim=-1) @ v).permute(0, 2, 1, 3).reshape(B * S, 768)
+    d = (ctx - ref).abs().max().item()
+    print(f"attention B={B} S={S} tensor_core={tensor_core}: max|diff| {d:.2e}")
+    assert d < tol
