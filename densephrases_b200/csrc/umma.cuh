@@ -22,6 +22,15 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+// multicast variant: the box lands at the same CTA-relative offset (and signals the same barrier offset) in every CTA of cta_mask
+__device__ __forceinline__ void tma_load_2d_mc(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar, unsigned short cta_mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc, unsigned idesc, unsigned accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -30,6 +39,10 @@ __device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long ad
 }
 __device__ __forceinline__ void umma_commit(unsigned bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the barrier at this CTA-relative offset in every CTA of cta_mask once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_mc(unsigned bar, unsigned short cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask) : "memory");
 }
 // K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor, sm_100 version 1).
 __device__ __forceinline__ unsigned long long make_sw128_desc(unsigned smem_addr) {

@@ -160,6 +160,11 @@ int dph_sgemm_nt_seq(const float* X, int64_t n, const float* W, int64_t m, int64
  * N % 128 == 0, K % 32 == 0.  == torch.nn.functional.linear (HF BertSelfAttention/BertOutput/BertIntermediate). */
 int dph_gemm_tf32_nt(const float* A, const float* W, const float* bias, const float* residual, float* out, int64_t M, int64_t N,
                      int64_t K, int act, int precise /* 0: 1xTF32, 1: 3xTF32 split (fp32-accurate) */, void* cuda_stream);
+/* Scheduling of the 1xTF32 GEMMs (process-wide; every mode issues the same MMAs in the same order -> bit-identical results):
+ * 0: one 128x128 tile per CTA, two CTAs per SM;  1: the same as 2-CTA thread-block clusters sharing the A tile through TMA
+ * multicast (N/128 even);  2 (default): persistent CTAs walking 128x256 tiles with double-buffered TMEM accumulators and eight
+ * epilogue warps (N % 256 == 0, else mode 0). */
+int dph_gemm_tf32_set_mode(int mode);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+DEFAULT_MODE = 2      # the library default of dph_gemm_tf32_set_mode
 
 
 def run_gemm(A, W, bias, resid, act, precise=0):
@@ -60,3 +61,26 @@ def test_gemm_tf32_matches_torch_fp32(M, N, K, variant):
     out2 = run_gemm(A2.contiguous(), W2.contiguous(), None, None, 0)
     ref2 = (A2.double() @ W2.double().T)
     assert (out2.double() - ref2).abs().max() < 1e-3 * max(1.0, ref2.abs().max().item() * 1e-3)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("M,N,K", [(4096, 768, 768), (333, 2304, 768), (64, 3072, 768), (1000, 256, 3072), (20000, 768, 96)])
+def test_gemm_schedules_are_bit_identical(M, N, K, mode):
+    """mode 1 (2-CTA clusters sharing the A tile by TMA multicast) and mode 2 (persistent 128x256 tiles, double-buffered TMEM)
+    issue the same MMAs per output element in the same order as mode 0 (one 128x128 tile per CTA)."""
+    import torch
+    from densephrases_b200 import _lib as L
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn((M, K), generator=g, device="cuda")
+    W = torch.randn((N, K), generator=g, device="cuda") * 0.05
+    bias = torch.randn((N,), generator=g, device="cuda")
+    resid = torch.randn((M, N), generator=g, device="cuda")
+    try:
+        L.check(L.lib().dph_gemm_tf32_set_mode(0))
+        base = run_gemm(A, W, bias, resid, 1)
+        L.check(L.lib().dph_gemm_tf32_set_mode(mode))
+        other = run_gemm(A, W, bias, resid, 1)
+    finally:
+        L.check(L.lib().dph_gemm_tf32_set_mode(DEFAULT_MODE))
+    assert torch.isfinite(other).all()
+    assert torch.equal(base, other), f"max|diff| {(base - other).abs().max().item():.3e}"
