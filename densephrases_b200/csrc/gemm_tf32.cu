@@ -163,12 +163,12 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) gemm_tf32_kernel(const __g
 // run together share A and B tiles in L2).  Bigger tiles raise the arithmetic intensity of the operand stream from 32 to 43 flop
 // per L2 byte -- the chip-wide L2 -> SM throughput (~12 TB/s) is what bounds fp32-operand tiles, not the tensor pipe -- and the
 // roles never stop: warp 0 keeps the 4-stage TMA ring (48 KB per stage) full across tile boundaries, warp 1 issues
-// tcgen05.mma 128x256x8 into one of TWO 256-column TMEM accumulators, warps 4-11 drain the other one (two warps per TMEM lane quarter, half the columns each) (tcgen05.ld -> bias / GELU /
+// tcgen05.mma 128x256x8 into one of TWO 256-column TMEM accumulators, warps 4-15 drain the other one (three warps per TMEM lane quarter, 32-column chunks 0-2 / 3-5 / 6-7) (tcgen05.ld -> bias / GELU /
 // residual -> global), so a tile's epilogue overlaps the next tile's main loop.  Barriers: full/empty per stage, and per
-// accumulator tfull (MMA -> epilogue, tcgen05.commit) / tempty (epilogue -> MMA, one arrive per epilogue warp, 8 in all).
+// accumulator tfull (MMA -> epilogue, tcgen05.commit) / tempty (epilogue -> MMA, one arrive per epilogue warp, 12 in all).
 #define GP_BN 256
 #define GP_STAGES 4
-#define GP_EPI_WARPS 8
+#define GP_EPI_WARPS 12
 #define GP_THREADS (128 + 32 * GP_EPI_WARPS)
 #define GP_A_BYTES (GM_BM * GM_BK * 4)          // 16 KB
 #define GP_B_BYTES (GP_BN * GM_BK * 4)          // 32 KB
@@ -247,8 +247,9 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gemm_tf32_persist_kernel(const 
             }
         }
     } else if (warp >= 4) {
-        const int q = warp & 3;                              // TMEM lane quarter; warps 4-7 take columns 0..127 of a tile, warps 8-11 columns 128..255
-        const int c_lo = (warp >= 8) ? 4 : 0;
+        const int q = warp & 3;                              // TMEM lane quarter; three warps share a quarter: 32-column chunks 0-2 / 3-5 / 6-7 of a tile
+        const int eg = (warp >> 2) - 1;                      // 0: warps 4-7, 1: warps 8-11, 2: warps 12-15
+        const int c_lo = eg * 3, c_hi = (eg == 2) ? 8 : c_lo + 3;
         unsigned i = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, i++) {
             const int g = t / per_group, r = t - g * per_group, m_blk = r / tiles_n, n_blk = r - m_blk * tiles_n;
@@ -260,10 +261,10 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gemm_tf32_persist_kernel(const 
             const float* resid = args.residual[g];
             float* out = args.out[g];
 #pragma unroll 1
-            for (int c = c_lo; c < c_lo + 4; c++) {
+            for (int c = c_lo; c < c_hi; c++) {
                 unsigned v[32];
                 tmem_ld32(tmem_base + ((unsigned)(q * 32) << 16) + buf * GP_BN + (unsigned)(c * 32), v);
-                if (c == c_lo + 3) {                                // this warp's share is read: hand it back before the last stores
+                if (c == c_hi - 1) {                                // this warp's share is read: hand it back before the last stores
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
@@ -350,7 +351,7 @@ int dph_launch_split_tf32(const float* x, float* hi, float* lo, long long n, cud
 
 // how 1xTF32 GEMMs are scheduled: 0 one 128x128 tile per CTA (2 CTAs/SM); 1 the same as 2-CTA clusters sharing the A tile by TMA
 // multicast (needs an even number of N tiles); 2 persistent 128x256 tiles with double-buffered TMEM (needs N % 256 == 0)
-static int g_gemm_mode = 2;      // measured on the encoder forward (B=64, S=64): mode 0 5.44 ms, mode 1 5.65 ms, mode 2 4.53 ms
+static int g_gemm_mode = 2;      // measured on the encoder forward (B=64, S=64): mode 0 5.44 ms, mode 1 5.65 ms, mode 2 4.41 ms
 static int g_num_sms = 0;
 DPH_API int dph_gemm_tf32_set_mode(int mode) { DPH_CHECK(mode >= 0 && mode <= 2, "gemm mode 0..2"); g_gemm_mode = mode; return 0; }
 

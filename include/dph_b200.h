@@ -162,7 +162,7 @@ int dph_gemm_tf32_nt(const float* A, const float* W, const float* bias, const fl
                      int64_t K, int act, int precise /* 0: 1xTF32, 1: 3xTF32 split (fp32-accurate) */, void* cuda_stream);
 /* Scheduling of the 1xTF32 GEMMs (process-wide; every mode issues the same MMAs in the same order -> bit-identical results):
  * 0: one 128x128 tile per CTA, two CTAs per SM;  1: the same as 2-CTA thread-block clusters sharing the A tile through TMA
- * multicast (N/128 even);  2 (default): persistent CTAs walking 128x256 tiles with double-buffered TMEM accumulators and eight
+ * multicast (N/128 even);  2 (default): persistent CTAs walking 128x256 tiles with double-buffered TMEM accumulators and twelve
  * epilogue warps (N % 256 == 0, else mode 0). */
 int dph_gemm_tf32_set_mode(int mode);
 
