@@ -13,8 +13,10 @@ train_query.get_top_phrases :187-201) work on top of it.  The internals are writ
   per-label dict lookups in get_idxs   (:124-141)      grouped fancy indexing
   spaCy sentencizer                    (:65-66,178)    rule-based stand-in (spaCy is not in this image)
 
-On-disk containers: faiss / h5py / blosc are unavailable here, so `MIPS(...)` reads `index.dph.npz`, `idx2id.npz`,
-`meta_dph.pkl` placed next to the reference's file names (FAISS-file reader = SURVEY.md 8f #2, next);
+On-disk artefacts: `MIPS(...)` takes the reference's paths.  It prefers this repo's containers when they sit next to them
+(`index.dph.npz`, `idx2id.npz`, `meta_dph.pkl`) and otherwise parses the reference's own files -- `index.faiss` (+ the
+`.ivfdata` payload of a merged index), `idx2id.hdf5`, `meta_compressed.pkl` with its blosc blobs -- with the pure-Python
+readers of densephrases_b200/artifacts.py (no faiss / h5py / blosc; see that module's STATUS note).
 `MIPS.from_components` wraps in-memory objects.
 """
 import logging
@@ -22,7 +24,6 @@ import os
 import pickle
 import re
 import string
-import zlib
 from time import time
 
 import numpy as np
@@ -79,17 +80,27 @@ class _PackedDocs(object):
 class MIPS(object):
     def __init__(self, phrase_dump_dir, index_path, idx2id_path, cuda=False, logging_level=logging.INFO):
         from .ivfpq import IvfPqIndex
+        from . import artifacts
         container = os.path.join(os.path.dirname(index_path), 'index.dph.npz')
-        if not os.path.exists(container):
-            raise RuntimeError(f'{container} not found (converted form of {index_path}); reading index.faiss directly is the next '
-                               f'scope row -- FAISS itself is not used on this path')
-        logger.info(f'Reading {container}')
-        z = np.load(container)
-        index = IvfPqIndex.from_arrays(z['A'], z['centroids'], z['pq'], z['list_len'], z['codes'], z['ids'] if 'ids' in z.files else None)
-        meta_path = os.path.join(phrase_dump_dir[:phrase_dump_dir.index('/phrase')], 'meta_dph.pkl')
+        if os.path.exists(container):
+            logger.info(f'Reading {container}')
+            z = np.load(container)
+            parts = {k: z[k] for k in z.files}
+        elif os.path.exists(index_path):
+            logger.info(f'Reading {index_path} (FAISS container, parsed natively)')
+            parts = artifacts.read_faiss_index(index_path, ondisk_same_dir=True)          # faiss.IO_FLAG_ONDISK_SAME_DIR, index.py:30
+            if not parts['by_residual'] or parts['metric'] != 0 or parts['quantizer_metric'] != 0:
+                raise RuntimeError('only the inner-product, by-residual IVF-PQ index of build_phrase_index.py:113-116 is supported')
+        else:
+            raise RuntimeError(f'neither {container} nor {index_path} found')
+        index = IvfPqIndex.from_arrays(parts['A'], parts['centroids'], parts['pq'], parts['list_len'], parts['codes'], parts.get('ids'))
+        dump_root = phrase_dump_dir[:phrase_dump_dir.index('/phrase')] if '/phrase' in phrase_dump_dir else phrase_dump_dir
         doc_groups = None
-        if os.path.exists(meta_path) and 'PQ' in index_path:           # in-RAM metadata only with PQ indexes (index.py:69-74)
-            doc_groups = pickle.load(open(meta_path, 'rb'))
+        if 'PQ' in index_path:                                          # in-RAM metadata only with PQ indexes (index.py:69-74)
+            for name in ('meta_dph.pkl', 'meta_compressed.pkl'):
+                if os.path.exists(os.path.join(dump_root, name)):
+                    doc_groups = artifacts.read_meta(os.path.join(dump_root, name))
+                    break
         self.phrase_dump_dir = phrase_dump_dir
         self._attach(index, self.load_idx_f(idx2id_path), doc_groups, index_path, cuda, logging_level)
 
@@ -122,8 +133,13 @@ class MIPS(object):
 
     # ---- loading helpers -------------------------------------------------------------------------------
     def load_idx_f(self, idx2id_path):
-        """{offset_key: {'doc': int32[], 'word': int32[]}} like index.py:78-88; stored here as npz members '<offset>/<type>'."""
-        z = np.load(os.path.splitext(idx2id_path)[0] + '.npz')
+        """{offset_key: {'doc': int32[], 'word': int32[]}} like index.py:78-88; read from `idx2id.npz` (members '<offset>/<type>')
+        when it exists next to idx2id_path, else from the HDF5 file itself."""
+        npz = os.path.splitext(idx2id_path)[0] + '.npz'
+        if not os.path.exists(npz):
+            from . import artifacts
+            return artifacts.read_idx2id(idx2id_path)
+        z = np.load(npz)
         table = {}
         for member in z.files:
             key, kind = member.split('/')
@@ -131,18 +147,19 @@ class MIPS(object):
         return table
 
     def decompress_meta(self, doc_idx):
-        """Per-document metadata record (index.py:106-122).  Array fields may be stored raw or zlib-compressed with a
-        'dtypes' entry (the reference's blosc blobs, compress_metadata.py:32-53)."""
+        """Per-document metadata record (index.py:106-122).  Array fields may be stored raw, zlib-compressed (this repo's
+        converter) or as the reference's blosc frames (compress_metadata.py:32-53), the latter two with a 'dtypes' entry."""
+        from .artifacts import decode_meta_field
         rec = self.doc_groups[doc_idx]
         dt = rec.get('dtypes', {})
 
         def field(name):
             v = rec[name]
-            return np.frombuffer(zlib.decompress(v), dt[name]) if isinstance(v, (bytes, bytearray)) else np.asarray(v)
+            return decode_meta_field(v, dt[name]) if isinstance(v, (bytes, bytearray)) else np.asarray(v)
 
         ctx = rec['context']
         if isinstance(ctx, (bytes, bytearray)):
-            ctx = zlib.decompress(ctx).decode('utf-8')
+            ctx = decode_meta_field(ctx).decode('utf-8')
         return {'word2char_start': field('word2char_start'), 'word2char_end': field('word2char_end'), 'f2o_start': field('f2o_start'),
                 'context': ctx, 'title': rec['title'], 'offset': -2, 'scale': 20}
 

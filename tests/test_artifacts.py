@@ -1,0 +1,159 @@
+"""Readers for the reference's on-disk artefacts (densephrases_b200/artifacts.py): index.faiss, idx2id.hdf5, meta_compressed.pkl.
+faiss / h5py / blosc do not exist in the build container, so these tests pin the readers against the writers of the same module
+(both restate the published formats) and against hand-assembled byte strings for the fixed parts of each header."""
+import os
+import pickle
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+from densephrases_b200 import artifacts as A
+
+
+def small_index(rng, nlist=7, lens=(3, 0, 5, 1, 0, 0, 2)):
+    ll = np.array(lens, dtype=np.int64)
+    return dict(A=rng.standard_normal((768, 768)).astype(np.float32), centroids=rng.standard_normal((nlist, 768)).astype(np.float32),
+                pq=rng.standard_normal((96, 256, 8)).astype(np.float32), list_len=ll,
+                codes=rng.integers(0, 256, (int(ll.sum()), 96), dtype=np.uint8), ids=rng.permutation(10 ** 6)[:int(ll.sum())].astype(np.int64) + 3 * 10 ** 9)
+
+
+@pytest.mark.parametrize("variant", ["ilar_full", "ilar_sparse", "ilod"])
+def test_faiss_index_round_trip(tmp_path, variant):
+    rng = np.random.default_rng(1)
+    ix = small_index(rng) if variant != "ilar_sparse" else small_index(rng, 9, (0, 0, 4, 0, 0, 0, 0, 2, 0))
+    p = str(tmp_path / "index.faiss")
+    A.write_faiss_index(p, nprobe=256, ondisk_payload="merged_index.ivfdata" if variant == "ilod" else None, **ix)
+    raw = open(p, "rb").read()
+    assert raw[:4] == b"IxPT" and struct.unpack_from("<i", raw, 4)[0] == 768            # fourcc, then d of the index header
+    assert (b"sprs" in raw) == (variant == "ilar_sparse") and (b"ilod" in raw) == (variant == "ilod")
+    got = A.read_faiss_index(p)
+    for k, v in ix.items():
+        assert np.array_equal(got[k], v), k
+    assert got["nprobe"] == 256 and got["ntotal"] == int(ix["list_len"].sum()) and got["by_residual"] and got["metric"] == 0
+    if variant == "ilod":                                                              # payload is looked up NEXT TO the index file (index.py:30)
+        os.rename(tmp_path / "merged_index.ivfdata", tmp_path / "moved.ivfdata")
+        with pytest.raises(FileNotFoundError):
+            A.read_faiss_index(p)
+
+
+def test_faiss_reader_fails_loudly(tmp_path):
+    p = tmp_path / "bad.faiss"
+    p.write_bytes(b"IxSQ" + b"\0" * 64)
+    with pytest.raises(ValueError, match="IxSQ"):
+        A.read_faiss_index(str(p))
+    rng = np.random.default_rng(2)
+    good = tmp_path / "index.faiss"
+    A.write_faiss_index(str(good), **small_index(rng))
+    (tmp_path / "cut.faiss").write_bytes(good.read_bytes()[:-100])
+    with pytest.raises(ValueError, match="truncated"):
+        A.read_faiss_index(str(tmp_path / "cut.faiss"))
+
+
+@pytest.mark.parametrize("typesize,shuffle,split,n", [(1, True, False, 5000), (8, True, True, 100000), (8, True, False, 100000), (4, False, True, 33333),
+                                                      (8, True, True, 50), (1, False, False, 0), (2, True, True, 70001)])
+def test_blosc_frames(typesize, shuffle, split, n):
+    rng = np.random.default_rng(n + typesize)
+    data = rng.integers(0, 4, n, dtype=np.uint8).tobytes()
+    frame = A.blosc_compress(data, typesize=typesize, shuffle=shuffle, split=split)
+    ver, verlz, flags, ts, nbytes, blocksize, cbytes = struct.unpack_from("<BBBBIII", frame, 0)
+    assert (ver, ts, nbytes, cbytes) == (2, typesize, n, len(frame))
+    assert A.blosc_decompress(frame) == data
+    if n > 1000:
+        assert len(frame) < n                     # really compressed
+        with pytest.raises(ValueError):
+            A.blosc_decompress(frame[:-7] + b"\0" * 7)
+    with pytest.raises(ValueError, match="not supported"):
+        A.blosc_decompress(bytes([2, 1, (1 << 5) | 1, 1]) + struct.pack("<III", 1000, 1000, 300) + b"\0" * 284)     # lz4 frame
+
+
+def test_meta_fields_in_all_three_encodings(tmp_path):
+    w = np.arange(0, 900, 3, dtype=np.int32)
+    ctx = "Łódź is a city. " * 40
+    rec_ref = {"word2char_start": A.blosc_compress(w.tobytes(), typesize=1), "context": A.blosc_compress(ctx.encode("utf-8"), typesize=8, split=True),
+               "dtypes": {"word2char_start": w.dtype}, "title": ["T"]}
+    p = tmp_path / "meta_compressed.pkl"
+    pickle.dump({"0": rec_ref}, open(p, "wb"))
+    rec = A.read_meta(str(p))["0"]
+    assert np.array_equal(A.decode_meta_field(rec["word2char_start"], rec["dtypes"]["word2char_start"]), w)
+    assert A.decode_meta_field(rec["context"]).decode("utf-8") == ctx
+    assert np.array_equal(A.decode_meta_field(zlib.compress(w.tobytes()), w.dtype), w)           # this repo's converter
+    assert np.array_equal(A.decode_meta_field(w, w.dtype), w)                                    # raw
+
+
+def same(a, b):
+    if isinstance(a, dict):
+        return set(a) == set(b) and all(same(a[k], b[k]) for k in a)
+    return a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b)
+
+
+def test_hdf5_round_trip_and_superblock(tmp_path):
+    rng = np.random.default_rng(3)
+    tree = {str(i * 10 ** 9): {"doc": rng.integers(0, 5000, 1000 + i).astype(np.int32), "word": rng.integers(0, 300, 1000 + i).astype(np.int32)}
+            for i in range(40)}                                                                  # 40 links -> 5 symbol nodes under the root B-tree
+    p = str(tmp_path / "idx2id.hdf5")
+    A.write_hdf5(p, tree)
+    raw = open(p, "rb").read()
+    assert raw[:8] == b"\x89HDF\r\n\x1a\n" and raw[8] == 0 and raw[13] == 8 and raw[14] == 8
+    assert struct.unpack_from("<Q", raw, 40)[0] == len(raw)                                     # end-of-file address
+    assert raw.count(b"SNOD") >= 5 + 40 and raw.count(b"HEAP") == 41
+    assert same(tree, A.read_idx2id(p))
+    tree["misc"] = {"f": rng.standard_normal((3, 5)).astype(np.float32), "be": np.arange(10, dtype=">i8"), "empty": np.zeros(0, np.int32),
+                    "deep": {"x": np.arange(4, dtype=np.uint8)}, "tab": rng.integers(-9, 9, (37, 11)).astype(np.int16)}
+    A.write_hdf5(p, tree, chunks={"tab": (16, 4)})                                               # chunked + shuffle + deflate
+    got = A.read_hdf5(p)
+    assert same(tree, got)
+    body = bytearray(open(p, "rb").read())                                                       # user block: superblock at 512, base address 512
+    struct.pack_into("<Q", body, 24, 512)
+    (tmp_path / "user.hdf5").write_bytes(b"\0" * 512 + bytes(body))
+    assert same(tree, A.read_hdf5(str(tmp_path / "user.hdf5")))
+    with pytest.raises(ValueError, match="not an HDF5"):
+        (tmp_path / "junk").write_bytes(b"junk" * 300)
+        A.read_hdf5(str(tmp_path / "junk"))
+
+
+def test_mips_loads_the_reference_file_layout(tmp_path, monkeypatch):
+    """MIPS(phrase_dump_dir, index_path, idx2id_path) over index.faiss (merged, on-disk lists) + idx2id.hdf5 + meta_compressed.pkl,
+    with the device index replaced by a recorder (CPU test): the arrays handed to IvfPqIndex.from_arrays are the file's."""
+    from densephrases_b200 import ivfpq, mips
+    from densephrases_b200.synthetic import make_corpus, make_phrase_index_arrays
+    rng = np.random.default_rng(4)
+    doc_groups, idx_f, ntotal = make_corpus(6, 1)
+    list_len, codes, ids = make_phrase_index_arrays(ntotal, 8, 1)
+    ix = dict(A=np.linalg.qr(rng.standard_normal((768, 768)))[0].astype(np.float32), centroids=rng.standard_normal((8, 768)).astype(np.float32),
+              pq=rng.standard_normal((96, 256, 8)).astype(np.float32), list_len=list_len, codes=codes, ids=ids)
+    dump = tmp_path / "dump"
+    (dump / "phrase").mkdir(parents=True)
+    (dump / "start" / "8_flat_OPQ96").mkdir(parents=True)
+    index_path = str(dump / "start" / "8_flat_OPQ96" / "index.faiss")
+    A.write_faiss_index(index_path, nprobe=1, ondisk_payload="merged_index.ivfdata", **ix)
+    A.write_hdf5(str(dump / "start" / "8_flat_OPQ96" / "idx2id.hdf5"), {k: {t: np.asarray(v[t]) for t in ("doc", "word")} for k, v in idx_f.items()})
+    packed = {}
+    for k, g in doc_groups.items():
+        packed[k] = {f: A.blosc_compress(np.asarray(g[f]).tobytes(), typesize=1) for f in ("word2char_start", "word2char_end", "f2o_start")}
+        packed[k].update(context=A.blosc_compress(g["context"].encode("utf-8")), title=g["title"],
+                         dtypes={f: np.asarray(g[f]).dtype for f in ("word2char_start", "word2char_end", "f2o_start")})
+    pickle.dump(packed, open(dump / "meta_compressed.pkl", "wb"))
+
+    class Recorder:
+        d, nprobe = 768, 1
+
+        def __init__(self, *arrays):
+            self.arrays = arrays
+            self.ntotal = int(np.sum(arrays[3]))
+
+        def opq_matrix(self):
+            return self.arrays[0]
+
+        reconstruct_batch = None
+
+    monkeypatch.setattr(ivfpq.IvfPqIndex, "from_arrays", staticmethod(lambda *a: Recorder(*a)))
+    m = mips.MIPS(str(dump / "phrase"), index_path, str(dump / "start" / "8_flat_OPQ96" / "idx2id.hdf5"), cuda=False)
+    for got, want in zip(m.index.arrays, (ix["A"], ix["centroids"], ix["pq"], list_len, codes, ids)):
+        assert np.array_equal(got, want)
+    assert m.index.nprobe == 256 and m.is_pq and same({k: {t: np.asarray(v[t]) for t in ("doc", "word")} for k, v in idx_f.items()}, m.idx_f)
+    k0 = sorted(doc_groups)[0]
+    meta = m.decompress_meta(k0)
+    assert meta["context"] == doc_groups[k0]["context"] and np.array_equal(meta["f2o_start"], doc_groups[k0]["f2o_start"])
+    assert np.allclose(m.R.numpy(), ix["A"])
