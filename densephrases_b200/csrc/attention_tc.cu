@@ -35,7 +35,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 
 __global__ void __launch_bounds__(128, 2) attention_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcArgs a) {
     extern __shared__ __align__(1024) unsigned char atsm[];
-    // the dynamic window is 1024-byte aligned by the launch (checked on the host side through the swizzle-atom requirement)
+    // swizzle atoms need 1024-byte alignment: the window is rounded up here (the launch reserves 1 KB of slack)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int hp = blockIdx.x, b = blockIdx.y, tw = blockIdx.z;
     const int S = a.S, h0 = hp * 2;
@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(128, 2) attention_tc_kernel(const __grid_const
 // qkv[t]: [T, 2304] fp32 (Q | K | V, heads contiguous inside each), ctx[t]: [T, 768]; mask int64 [B, S]; S <= 64, 12 heads.
 int dph_launch_attention_tc(const float* const qkv[2], float* const ctx[2], const long long* mask, int B, int S, long long T, cudaStream_t st) {
     DPH_CHECK(S >= 1 && S <= 64 && B >= 1 && T >= (long long)B * S, "attention_tc: S must be 1..64");
-    static bool attr = false;
-    if (!attr) { DPH_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES)); attr = true; }
+    static DphPerDeviceOnce once;
+    if (once.first()) { DPH_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES)); }
     AttnTcMaps maps;
     AttnTcArgs a;
     for (int t = 0; t < 2; t++) {

@@ -36,6 +36,20 @@ void dph_set_error(const std::string& msg);
         if (r__) return r__;     \
     } while (0)
 
+// Once-per-device latch for cudaFuncSetAttribute: function attributes live in the per-device context, so a process that drives
+// several GPUs has to raise the dynamic shared-memory limit on each of them.
+struct DphPerDeviceOnce {
+    bool done[64] = {};
+    bool first() {
+        int d = 0;
+        cudaGetDevice(&d);
+        d &= 63;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+
 // ---- counter-based generator: bit-identical to oracle/ivfpq_ref.c (mix64 / rnd64 / approx_normal) ----
 __host__ __device__ __forceinline__ uint64_t dph_mix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;

@@ -297,8 +297,8 @@ __global__ void __launch_bounds__(256) attention_tile_kernel(AttnArgs a) {
 template <int KT> static int launch_attention_tile(const AttnArgs& aa, int B, cudaStream_t st) {
     constexpr int SP = 16 * KT;
     const size_t smem = (size_t)(64 * 68 + 64 * (SP + 4) + SP * 64 + SP * 68 + SP) * 4;
-    static bool attr = false;
-    if (!attr) { DPH_CUDA(cudaFuncSetAttribute(attention_tile_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    static DphPerDeviceOnce once;
+    if (once.first()) { DPH_CUDA(cudaFuncSetAttribute(attention_tile_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
     attention_tile_kernel<KT><<<dim3(ENC_HEADS * ((aa.S + 63) / 64), (unsigned)B, 2), 256, smem, st>>>(aa);
     DPH_CUDA(cudaGetLastError());
     return 0;
@@ -312,8 +312,8 @@ static int launch_attention(const AttnArgs& aa, int B, cudaStream_t st) {
     if (S <= 128) return launch_attention_tile<8>(aa, B, st);
     const int attn_warps = 8;      // long sequences (max_query_length 384 for KILT entity linking): K,V of the head in shared memory
     const size_t attn_smem = ((size_t)S * 65 + (size_t)S * 64 + S + attn_warps * 64 + (size_t)attn_warps * S) * 4;
-    static bool attr = false;
-    if (!attr) { DPH_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+    static DphPerDeviceOnce once;
+    if (once.first()) { DPH_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); }
     attention_kernel<<<dim3(ENC_HEADS, (unsigned)B, 2), attn_warps * 32, attn_smem, st>>>(aa);
     DPH_CUDA(cudaGetLastError());
     return 0;

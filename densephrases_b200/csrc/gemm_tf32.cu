@@ -352,7 +352,6 @@ int dph_launch_split_tf32(const float* x, float* hi, float* lo, long long n, cud
 // how 1xTF32 GEMMs are scheduled: 0 one 128x128 tile per CTA (2 CTAs/SM); 1 the same as 2-CTA clusters sharing the A tile by TMA
 // multicast (needs an even number of N tiles); 2 persistent 128x256 tiles with double-buffered TMEM (needs N % 256 == 0)
 static int g_gemm_mode = 2;      // measured on the encoder forward (B=64, S=64): mode 0 5.44 ms, mode 1 5.65 ms, mode 2 4.41 ms
-static int g_num_sms = 0;
 DPH_API int dph_gemm_tf32_set_mode(int mode) { DPH_CHECK(mode >= 0 && mode <= 2, "gemm mode 0..2"); g_gemm_mode = mode; return 0; }
 
 // Grouped launch used by the encoder: problems share M, N, K and the epilogue; pointers are device pointers.
@@ -363,23 +362,20 @@ int dph_launch_gemm_tf32(int group, const float* const* A, const float* const* W
     DPH_CHECK(N % GM_BN == 0 && K % GM_BK == 0 && M >= 1, "gemm_tf32 needs N % 128 == 0 and K % 32 == 0");
     const bool split = A_lo != nullptr && W_lo != nullptr;
     const int smem_fast = GM_STAGES * 2 * GM_TILE_BYTES + 1024, smem_split = GM_STAGES * 4 * GM_TILE_BYTES + 1024;
-    static bool attr = false;
-    if (!attr) {
+    static DphPerDeviceOnce once;
+    if (once.first()) {
         DPH_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fast));
         DPH_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fast));
         DPH_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_split));
-        attr = true;
     }
     const bool cluster = !split && g_gemm_mode == 1 && ((N / GM_BN) % 2 == 0);
     if (!split && g_gemm_mode == 2 && N % GP_BN == 0) {
         const int smem_p = GP_STAGES * GP_STAGE_BYTES + 1024;
-        static bool attr_p = false;
-        if (!attr_p) {
-            DPH_CUDA(cudaFuncSetAttribute(gemm_tf32_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
-            int dev = 0; DPH_CUDA(cudaGetDevice(&dev));
-            DPH_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-            attr_p = true;
-        }
+        static DphPerDeviceOnce once_p;
+        if (once_p.first()) DPH_CUDA(cudaFuncSetAttribute(gemm_tf32_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
+        int dev = 0, num_sms = 0;
+        DPH_CUDA(cudaGetDevice(&dev));
+        DPH_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         GemmMapsP mp;
         GemmArgs ap;
         for (int g = 0; g < GM_MAX_GROUP; g++) {
@@ -392,7 +388,7 @@ int dph_launch_gemm_tf32(int group, const float* const* A, const float* const* W
         }
         ap.M = M; ap.N = N; ap.K = K; ap.act = act;
         const int tiles_m = (M + GM_BM - 1) / GM_BM, tiles_n = N / GP_BN, total = group * tiles_m * tiles_n;
-        gemm_tf32_persist_kernel<<<total < g_num_sms ? total : g_num_sms, GP_THREADS, smem_p, st>>>(mp, ap, tiles_m, tiles_n, total);
+        gemm_tf32_persist_kernel<<<total < num_sms ? total : num_sms, GP_THREADS, smem_p, st>>>(mp, ap, tiles_m, tiles_n, total);
         DPH_CUDA(cudaGetLastError());
         return 0;
     }

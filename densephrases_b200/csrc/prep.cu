@@ -238,8 +238,8 @@ int dph_launch_coarse_merge(const unsigned long long* keys, int W, int64_t n, in
     DPH_CHECK((long long)W * nprobe <= 8192, "coarse merge: world * nprobe must be <= 8192");
     if (n == 0) return 0;
     int p2 = 1; while (p2 < W * nprobe) p2 <<= 1;
-    static bool attr = false;
-    if (!attr) { DPH_CUDA(cudaFuncSetAttribute(coarse_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8)); attr = true; }
+    static DphPerDeviceOnce once;
+    if (once.first()) { DPH_CUDA(cudaFuncSetAttribute(coarse_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8)); }
     coarse_merge_kernel<<<(unsigned)n, 256, p2 * 8, st>>>(keys, W, n, nprobe, key, cd);
     DPH_CUDA(cudaGetLastError());
     return 0;
@@ -362,8 +362,8 @@ int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprob
     if (n == 0) return 0;
     if (nlist <= CS_MAX_ROW) {
         const size_t smem = (size_t)((nlist + 1) & ~1) * 4 + CS_BINS * 4 + DPH_MAX_NPROBE * 8;
-        static bool attr = false;
-        if (!attr) { DPH_CUDA(cudaFuncSetAttribute(coarse_select_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_MAX_ROW * 4 + CS_BINS * 4 + DPH_MAX_NPROBE * 8)); attr = true; }
+        static DphPerDeviceOnce once;
+        if (once.first()) { DPH_CUDA(cudaFuncSetAttribute(coarse_select_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_MAX_ROW * 4 + CS_BINS * 4 + DPH_MAX_NPROBE * 8)); }
         coarse_select_smem_kernel<<<(unsigned)n, 256, smem, st>>>(S, (int)nlist, nprobe, key, cd, keys64, list_base, only_rows, ld);
         DPH_CUDA(cudaGetLastError());
         return 0;

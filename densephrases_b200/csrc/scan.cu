@@ -470,9 +470,9 @@ __global__ void __launch_bounds__(NT, 1) scan_pair_kernel(PairScanArgs a) {
 
 __global__ void smem_base_probe_kernel(unsigned* out) { *out = (unsigned)__cvta_generic_to_shared(dph_smem) & 0x00FFFFFFu; }
 
-static bool g_attrs_set = false;
 int dph_scan_setup_attrs() {
-    if (g_attrs_set) return 0;
+    static DphPerDeviceOnce once;
+    if (!once.first()) return 0;
     {
         unsigned* d = nullptr; unsigned h = 0;
         DPH_CUDA(cudaMalloc((void**)&d, 4));
@@ -484,7 +484,6 @@ int dph_scan_setup_attrs() {
     DPH_CUDA(cudaFuncSetAttribute(scan_kernel<DPH_SCAN_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LUT_FAST + (int)sizeof(ScanShared)));
     DPH_CUDA(cudaFuncSetAttribute(scan_kernel<DPH_SCAN_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LUT_EXACT + (int)sizeof(ScanShared)));
     DPH_CUDA(cudaFuncSetAttribute(scan_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LUT_FAST + (int)sizeof(PairShared)));
-    g_attrs_set = true;
     return 0;
 }
 
@@ -667,8 +666,8 @@ DPH_API int dph_merge_shards_packed(const int64_t* Pg, int nshards, int64_t n, i
     if (n == 0) return 0;
     DPH_CHECK(nshards >= 1 && k >= 1 && (long long)nshards * k <= 8192, "merge_shards: nshards*k must be <= 8192");
     int p2 = 1; while (p2 < nshards * k) p2 <<= 1;
-    static bool attr = false;
-    if (!attr) { DPH_CUDA(cudaFuncSetAttribute(merge_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8)); attr = true; }
+    static DphPerDeviceOnce once;
+    if (once.first()) { DPH_CUDA(cudaFuncSetAttribute(merge_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8)); }
     merge_packed_kernel<<<(unsigned)n, 256, p2 * 8, (cudaStream_t)cuda_stream>>>((const longlong2*)Pg, nshards, n, k, D, (long long*)I);
     DPH_CUDA(cudaGetLastError());
     return 0;
