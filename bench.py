@@ -359,7 +359,7 @@ def run_ours(args):
                 "dtype": "f32", "data": "synthetic", "config": config_dict(wl, world, "hbm"),
                 "e2e": {"value": B * K / (ms_e2e / 1000.0), "unit": "queries/s", "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * k * 12,
                         "ms_per_step": ms_e2e / K},
-                "gpu_launches": K * ((17 if pair_mode else 12) + (3 if world > 1 else 0)), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+                "gpu_launches": K * ((18 if pair_mode else 12) + (3 if world > 1 else 0)), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                 "exact_fallback_queries_last_batch": flags, "encoder": enc_info}
         emit(line)
     del ix
