@@ -3,7 +3,11 @@
 (index.dph.npz + idx2id.npz + meta_dph.pkl).  Run this ONCE on a machine that still has the reference's dependencies
 (faiss, h5py, blosc -- requirements.txt of princeton-nlp/DensePhrases); the B200 serving path itself needs none of them.
 
-    python tools/convert_reference_artifacts.py $SAVE_DIR/densephrases-multi_wiki-20181220/dump start/1048576_flat_OPQ96
+    python tools/convert_reference_artifacts.py $SAVE_DIR/densephrases-multi_wiki-20181220/dump start/1048576_flat_OPQ96 [--verify]
+
+--verify additionally parses the same three files with the library-free readers of densephrases_b200/artifacts.py and checks that
+they return exactly what faiss / h5py / blosc returned: that is the cross-check those readers still need (they were written without
+access to the libraries or to any file produced by them).
 
 It only uses public faiss Python API calls (the same ones densephrases/index.py:30-32,52 and build_phrase_index.py use);
 it cannot be exercised in the offline build image (no faiss there), so treat it as a recipe: untested against a real release."""
@@ -64,11 +68,41 @@ def convert_meta(pkl_path, out_path):
     pickle.dump(dst, open(out_path, "wb"))
 
 
+def verify(dump_dir, index_dir):
+    """Native readers (densephrases_b200/artifacts.py) against what the libraries produced above."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from densephrases_b200 import artifacts
+    want = np.load(os.path.join(index_dir, "index.dph.npz"))
+    got = artifacts.read_faiss_index(os.path.join(index_dir, "index.faiss"))
+    for k in ("A", "centroids", "pq", "list_len", "codes", "ids"):
+        assert np.array_equal(got[k], want[k]), f"index.faiss: {k} differs between faiss and the native reader"
+    want = np.load(os.path.join(index_dir, "idx2id.npz"))
+    got = artifacts.read_idx2id(os.path.join(index_dir, "idx2id.hdf5"))
+    assert sorted(f"{k}/{t}" for k in got for t in got[k]) == sorted(want.files), "idx2id.hdf5: group names differ"
+    for member in want.files:
+        key, kind = member.split("/")
+        assert np.array_equal(got[key][kind], want[member]), f"idx2id.hdf5: {member} differs"
+    meta = os.path.join(dump_dir, "meta_compressed.pkl")
+    if os.path.exists(meta):
+        import blosc
+        src = pickle.load(open(meta, "rb"))
+        for n, (doc_id, g) in enumerate(src.items()):
+            for name in ("word2char_start", "word2char_end", "f2o_start", "context"):
+                assert artifacts.blosc_decompress(g[name]) == blosc.decompress(g[name]), f"meta_compressed.pkl: {doc_id}/{name} differs"
+            if n >= 2000:
+                break
+    print("native readers agree with faiss / h5py / blosc")
+
+
 if __name__ == "__main__":
-    dump_dir, index_name = sys.argv[1], sys.argv[2]
+    do_verify = "--verify" in sys.argv
+    args = [a for a in sys.argv[1:] if a != "--verify"]
+    dump_dir, index_name = args[0], args[1]
     index_dir = os.path.join(dump_dir, index_name)
     convert_index(os.path.join(index_dir, "index.faiss"), os.path.join(index_dir, "index.dph.npz"))
     convert_idx2id(os.path.join(index_dir, "idx2id.hdf5"), os.path.join(index_dir, "idx2id.npz"))
     meta = os.path.join(dump_dir, "meta_compressed.pkl")
     if os.path.exists(meta):
         convert_meta(meta, os.path.join(dump_dir, "meta_dph.pkl"))
+    if do_verify:
+        verify(dump_dir, index_dir)
