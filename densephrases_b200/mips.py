@@ -29,6 +29,8 @@ from time import time
 import numpy as np
 import torch
 
+from .artifacts import decode_meta_field
+
 logger = logging.getLogger(__name__)
 _PUNCT = set(string.punctuation)
 _ARTICLES = re.compile(r'\b(a|an|the)\b')
@@ -149,7 +151,6 @@ class MIPS(object):
     def decompress_meta(self, doc_idx):
         """Per-document metadata record (index.py:106-122).  Array fields may be stored raw, zlib-compressed (this repo's
         converter) or as the reference's blosc frames (compress_metadata.py:32-53), the latter two with a 'dtypes' entry."""
-        from .artifacts import decode_meta_field
         rec = self.doc_groups[doc_idx]
         dt = rec.get('dtypes', {})
 
