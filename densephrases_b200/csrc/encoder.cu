@@ -402,26 +402,29 @@ DPH_API int dph_encoder_load_tower(dph_encoder* e, int tower, const float* blob,
     if (e->wsplit[tower]) { cudaFree(e->wsplit[tower]); e->wsplit[tower] = nullptr; }
     return 0;
 }
+// free + null + allocate, so that a failed allocation never leaves a dangling pointer behind for dph_encoder_free
+static int regrow(void** p, size_t bytes) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    DPH_CUDA(cudaMalloc(p, bytes));
+    return 0;
+}
 static int ensure_ws(dph_encoder* e, int64_t T, int64_t B) {
     if (T > e->cap_tokens) {
+        e->cap_tokens = 0;                                   // stays 0 if anything below fails: the next call starts over
         for (int t = 0; t < 2; t++) {
-            float** ps[] = {&e->x[t], &e->qkv[t], &e->ctx[t], &e->a[t], &e->ffn[t]};
-            size_t sz[] = {(size_t)T * ENC_H, (size_t)T * 3 * ENC_H, (size_t)T * ENC_H, (size_t)T * ENC_H, (size_t)T * ENC_FF};
-            for (int i = 0; i < 5; i++) { if (*ps[i]) cudaFree(*ps[i]); DPH_CUDA(cudaMalloc((void**)ps[i], sz[i] * 4)); }
-            if (e->act_hi[t]) cudaFree(e->act_hi[t]);
-            if (e->act_lo[t]) cudaFree(e->act_lo[t]);
-            DPH_CUDA(cudaMalloc((void**)&e->act_hi[t], (size_t)T * ENC_FF * 4));
-            DPH_CUDA(cudaMalloc((void**)&e->act_lo[t], (size_t)T * ENC_FF * 4));
+            float** ps[] = {&e->x[t], &e->qkv[t], &e->ctx[t], &e->a[t], &e->ffn[t], &e->act_hi[t], &e->act_lo[t]};
+            size_t sz[] = {(size_t)T * ENC_H, (size_t)T * 3 * ENC_H, (size_t)T * ENC_H, (size_t)T * ENC_H, (size_t)T * ENC_FF, (size_t)T * ENC_FF,
+                           (size_t)T * ENC_FF};
+            for (int i = 0; i < 7; i++) DPH_TRY(regrow((void**)ps[i], sz[i] * 4));
         }
         long long** ip[] = {&e->ids, &e->mask, &e->tt};
-        for (auto p : ip) { if (*p) cudaFree(*p); DPH_CUDA(cudaMalloc((void**)p, (size_t)T * 8)); }
+        for (auto p : ip) DPH_TRY(regrow((void**)p, (size_t)T * 8));
         e->cap_tokens = T;
     }
     if (B > e->cap_b) {
-        if (e->out_s) cudaFree(e->out_s);
-        if (e->out_e) cudaFree(e->out_e);
-        DPH_CUDA(cudaMalloc((void**)&e->out_s, (size_t)B * ENC_H * 4));
-        DPH_CUDA(cudaMalloc((void**)&e->out_e, (size_t)B * ENC_H * 4));
+        e->cap_b = 0;
+        DPH_TRY(regrow((void**)&e->out_s, (size_t)B * ENC_H * 4));
+        DPH_TRY(regrow((void**)&e->out_e, (size_t)B * ENC_H * 4));
         e->cap_b = B;
     }
     return 0;
