@@ -1,7 +1,8 @@
 """WordPiece tokenisation of questions into the `[CLS] q [SEP] [PAD]...` features the query towers consume
 (reference: squad_utils.py question-only path :117-141,401-431,594-608 via HF BertTokenizer.encode_plus, padded to
 max_query_length, token_type_ids all 0).  CPU work, kept (not accelerated), written from the published BERT algorithm:
-whitespace+punctuation basic tokenisation, then greedy longest-match-first WordPiece.
+text cleaning + whitespace / CJK / punctuation basic tokenisation, then greedy longest-match-first WordPiece; pinned token for
+token against transformers.BertTokenizer on a shared vocabulary (tests/test_api.py::test_tokenizer_matches_transformers_bert_tokenizer).
 No vocabulary file is reachable offline; `WordPieceTokenizer.from_pretrained_or_synthetic` loads `vocab.txt` when a
 directory has one and otherwise builds a deterministic synthetic cased vocabulary of the SpanBERT size (28 996)."""
 import os
@@ -18,9 +19,35 @@ def _is_punct(ch):
     return unicodedata.category(ch).startswith('P')
 
 
+def _is_whitespace(ch):
+    return ch in ' \t\n\r' or unicodedata.category(ch) == 'Zs'
+
+
+def _is_control(ch):
+    return ch not in '\t\n\r' and unicodedata.category(ch).startswith('C')
+
+
+def _is_cjk(cp):
+    return ((0x4E00 <= cp <= 0x9FFF) or (0x3400 <= cp <= 0x4DBF) or (0x20000 <= cp <= 0x2A6DF) or (0x2A700 <= cp <= 0x2B73F) or
+            (0x2B740 <= cp <= 0x2B81F) or (0x2B820 <= cp <= 0x2CEAF) or (0xF900 <= cp <= 0xFAFF) or (0x2F800 <= cp <= 0x2FA1F))
+
+
 def basic_tokenize(text, do_lower_case=False):
+    """BERT BasicTokenizer: drop NUL / U+FFFD / control characters, every Unicode space -> ' ', CJK ideographs become words of
+    their own, whitespace split, (lower-case + strip accents), split at punctuation."""
+    cleaned = []
+    for ch in text:
+        cp = ord(ch)
+        if cp == 0 or cp == 0xFFFD or _is_control(ch):
+            continue
+        if _is_whitespace(ch):
+            cleaned.append(' ')
+        elif _is_cjk(cp):
+            cleaned.append(' ' + ch + ' ')
+        else:
+            cleaned.append(ch)
     out = []
-    for tok in text.strip().split():
+    for tok in ''.join(cleaned).split():
         if do_lower_case:
             tok = ''.join(c for c in unicodedata.normalize('NFD', tok.lower()) if unicodedata.category(c) != 'Mn')
         cur = ''

@@ -90,3 +90,33 @@ def test_densephrases_search_and_evaluate_end_to_end(oracle, tmp_path):
     args.test_path, args.top_k, args.aggregate = str(p), 5, True
     res = evaluate(args, mips=mips, query_encoder=model.model, tokenizer=model.tokenizer)
     assert res["exact_match_top1"] == 1.0 and res["exact_match_top5"] == 1.0
+
+
+@pytest.mark.parametrize("lower", [False, True])
+def test_tokenizer_matches_transformers_bert_tokenizer(tmp_path, lower):
+    """Row 8a-a3 pinned against the library the reference calls: same WordPiece sequence as transformers.BertTokenizer (the slow,
+    pure-Python tokenizer; squad_utils.py:119-135 feeds it whitespace-split question tokens) on a shared vocabulary, for random
+    strings with punctuation, accents, CJK, control / zero-width characters and over-long words; and the same padded features."""
+    transformers = pytest.importorskip("transformers")
+    import random
+    from densephrases_b200.tokenization import WordPieceTokenizer
+    words = ["river", "##s", "the", "Who", "who", "sign", "##ed", "treaty", "city", "##ing", "é", "##é", "naïve", "naive", "cafe", "中", "over", "##flow"]
+    seed_tok = WordPieceTokenizer.from_pretrained_or_synthetic(None, extra_words=words)
+    inv = sorted(seed_tok.vocab.items(), key=lambda kv: kv[1])
+    lines = [f"[unused{i}]" for i in range(inv[-1][1] + 1)]
+    for tok, i in inv:
+        lines[i] = tok
+    (tmp_path / "vocab.txt").write_text("\n".join(lines) + "\n", encoding="utf-8")
+    hf = transformers.BertTokenizer(str(tmp_path / "vocab.txt"), do_lower_case=lower)
+    mine = WordPieceTokenizer.from_pretrained_or_synthetic(str(tmp_path), do_lower_case=lower)
+    rng = random.Random(7)
+    alphabet = list("abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789") + list(" .,;:!?'\"()[]{}-_/\\@#$%^&*+=<>|~`") + \
+        ["é", "ï", "中", "文", "\t", "\n", " ", "​", "\x00", "\x07", "ß", "—", "’", "“", "€", " river ", " rivers ", " signed ", " overflowing "]
+    cases = ["Which rivers?", "Who signed the treaty of naïve café?", "a" * 150 + " b", "中文river", "hello world​zero", "x\x00y\x07z", ""]
+    cases += ["".join(rng.choice(alphabet) for _ in range(rng.randint(0, 40))) for _ in range(1500)]
+    for s in cases:
+        assert mine.tokenize(s) == hf.tokenize(s), repr(s)
+    for s in cases[:200]:
+        enc = hf(s, max_length=16, padding="max_length", truncation=True)
+        ids, mask, tt, toks = mine.encode_question(s, 16)
+        assert ids == enc["input_ids"] and mask == enc["attention_mask"] and tt == enc["token_type_ids"], repr(s)
