@@ -2,7 +2,10 @@
 (/root/reference/densephrases/index.py:220-448: search_phrase + aggregate_results) over the oracle IVF-PQ index,
 written the way the reference runs it (one reconstruct per id, one validity test per candidate, python sorting) so the
 batched product implementation (densephrases_b200/mips.py) can be compared result-by-result.
-PARITY UNPINNED: the reference has no fixtures for this path; this restatement follows its source line by line."""
+PINNED against the reference itself: tests/golden/mips_search.json holds the outputs of the UNMODIFIED reference `MIPS.search`
+(run in the build container by tests/golden/make_mips_golden.py over the same synthetic corpus and oracle index);
+tests/test_mips.py::test_phrase_stage_matches_reference_golden checks this restatement and the product mirror against it.
+(The IVF-PQ search underneath stays "parity unpinned" at the FAISS boundary, see oracle/ivfpq_ref.c.)"""
 import numpy as np
 
 

@@ -120,3 +120,18 @@ def test_tokenizer_matches_transformers_bert_tokenizer(tmp_path, lower):
         enc = hf(s, max_length=16, padding="max_length", truncation=True)
         ids, mask, tt, toks = mine.encode_question(s, 16)
         assert ids == enc["input_ids"] and mask == enc["attention_mask"] and tt == enc["token_type_ids"], repr(s)
+
+
+def test_metrics_match_reference_golden():
+    """normalize_answer / f1 / EM / DrQA matchers against outputs of the unmodified reference functions
+    (tests/golden/metrics.json, written by tests/golden/make_metrics_golden.py from eval_utils.py:9-86)."""
+    from densephrases_b200 import runtime as R
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "metrics.json")))
+    for c in g["pairs"]:
+        p, t = c["prediction"], c["truth"]
+        assert R.normalize_answer(p) == c["norm_p"] and R.exact_match_score(p, t) == c["em"] and R.drqa_exact_match_score(p, t) == c["drqa_em"]
+        assert [float(v) for v in R.f1_score(p, t)] == c["f1"] and R.drqa_normalize(p) == c["drqa_norm"]
+    for c in g["regex"]:
+        assert R.drqa_regex_match_score(c["prediction"], c["pattern"]) == c["match"], c
+    for c in g["max_over"]:
+        assert bool(R.drqa_metric_max_over_ground_truths(R.drqa_exact_match_score, c["prediction"], c["truths"])) == c["em"]

@@ -130,3 +130,32 @@ def test_fused_window_scores_match_reconstruct_path(oracle):
     outs = mips.search(query, q_texts=['q'] * len(query), top_k=10, aggregate=True, agg_strat='opt1', return_idxs=False)      # fused path
     refs = ref_search(ref, idx_f, doc_groups, query, top_k=10, nprobe=256, aggregate=True, agg_strat='opt1', normalize_answer=normalize_answer)
     compare(outs, refs)
+
+
+@pytest.mark.parametrize("which", ["restatement", "mips"])
+def test_phrase_stage_matches_reference_golden(oracle, which):
+    """tests/golden/mips_search.json holds what the UNMODIFIED reference `MIPS.search` (index.py:124-141,189-482) returned for
+    this corpus / index / query batch (generator: tests/golden/make_mips_golden.py, run in the build container).  Both the
+    item-by-item restatement used as the GPU-box oracle (oracle/mips_ref.py) and the batched MIPS mirror reproduce it."""
+    import json
+    import os
+    from densephrases_b200.mips import MIPS, normalize_answer
+    from oracle.mips_ref import ref_search
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "mips_search.json")))
+    doc_groups, idx_f, _, ref, query = build(oracle)
+    for cfg in gold["configs"]:
+        kw = dict(top_k=gold["top_k"], aggregate=cfg["aggregate"], agg_strat=cfg["agg_strat"], return_idxs=True)
+        if which == "restatement":
+            outs = ref_search(ref, idx_f, doc_groups, query, nprobe=gold["nprobe"], normalize_answer=normalize_answer, **kw)
+        else:
+            mips = MIPS.from_components(OracleIndexAdapter(ref), idx_f, doc_groups, cuda=False)
+            mips.index.nprobe = gold["nprobe"]
+            outs = mips.search(query, q_texts=["q"] * len(query), **kw)
+        assert len(outs) == len(cfg["results"])
+        for got, want in zip(outs, cfg["results"]):
+            assert len(got) == len(want), (cfg["agg_strat"], len(got), len(want))
+            for g, w in zip(got, want):
+                for key in ("context", "title", "doc_idx", "start_pos", "end_pos", "start_idx", "end_idx", "answer"):
+                    assert g[key] == w[key], (cfg["agg_strat"], key, g[key], w[key])
+                assert abs(g["score"] - w["score"]) <= 1e-3 * max(1.0, abs(w["score"]))
+                assert abs(float(np.sum(g["start_vec"])) - w["start_vec_sum"]) < 5e-2 and abs(float(np.sum(g["end_vec"])) - w["end_vec_sum"]) < 5e-2
