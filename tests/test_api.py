@@ -135,3 +135,55 @@ def test_metrics_match_reference_golden():
         assert R.drqa_regex_match_score(c["prediction"], c["pattern"]) == c["match"], c
     for c in g["max_over"]:
         assert bool(R.drqa_metric_max_over_ground_truths(R.drqa_exact_match_score, c["prediction"], c["truths"])) == c["em"]
+
+
+def test_unmodified_reference_evaluate_runs_on_the_facade(tmp_path):
+    """The reference's own `eval_phrase_retrieval.evaluate` (:49-91) + `evaluate_results` (:94-204), UNMODIFIED, executed over this
+    repo's drop-in surface: `Options`, `load_qa_pairs`, `get_query2vec` (+ tokenizer) and the metric functions come from the
+    `densephrases` facade; only the phrase index and the encoder are CPU stand-ins with the documented call signatures.  Its
+    numbers equal densephrases_b200.runtime.evaluate on the same inputs (the reference reports percentages)."""
+    ref = "/root/reference/eval_phrase_retrieval.py"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not present (GPU box)")
+    import importlib.util
+    import torch
+    from densephrases import Options
+    from densephrases_b200 import runtime as R
+    from densephrases_b200.tokenization import WordPieceTokenizer
+    spec = importlib.util.spec_from_file_location("ref_eval_phrase_retrieval_run", ref)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    qa = [("which river crosses the city", ["the Seine", "Seine"]), ("who signed the treaty", ["Louis XIV"]), ("what year", ["1648", "in 1648"]),
+          ("where", ["Paris"]), ("what is the a an the", ["yes"])]
+    json.dump({"data": [{"id": str(i), "question": q, "answers": a} for i, (q, a) in enumerate(qa)]}, open(tmp_path / "test.json", "w"))
+    o = Options()
+    o.add_model_options(); o.add_index_options(); o.add_retrieval_options(); o.add_data_options()
+    args = o.parse(["--test_path", str(tmp_path / "test.json"), "--load_dir", str(tmp_path), "--top_k", "3", "--eval_batch_size", "2", "--save_pred"])
+    canned = {"which river crosses the city": ["Seine", "Loire"], "who signed the treaty": ["Louis XV", "Louis XIV", "x"], "what year": [],
+              "where": ["paris.", "Lyon"], "what is the a an the": ["no", "Yes!"]}
+
+    class FakeEncoder:
+        def __call__(self, input_ids_=None, attention_mask_=None, token_type_ids_=None, return_query=False):
+            assert return_query and input_ids_.shape == attention_mask_.shape == token_type_ids_.shape and input_ids_.shape[1] == args.max_query_length
+            b = input_ids_.shape[0]
+            return torch.ones((b, 1, 768)), torch.zeros((b, 1, 768))
+
+        def eval(self):
+            return self
+
+    class FakeMips:
+        num_docs_list = [1.0]
+
+        def search(self, query, q_texts=None, nprobe=256, top_k=10, max_answer_length=10, aggregate=False, agg_strat='opt1', return_sent=False):
+            assert query.shape == (len(q_texts), 1536) and top_k == 3
+            return [[{"answer": a, "context": "ctx " + a, "title": ["T"], "score": 10.0 - j, "start_pos": 4, "end_pos": 4 + len(a)}
+                     for j, a in enumerate(canned[q])] for q in q_texts]
+
+    tok = WordPieceTokenizer.from_pretrained_or_synthetic(None)
+    em1, f11, emk, f1k = mod.evaluate(args, mips=FakeMips(), query_encoder=FakeEncoder(), tokenizer=tok)
+    mine = R.evaluate(args, mips=FakeMips(), query_encoder=FakeEncoder(), tokenizer=tok)
+    assert (em1, f11, emk, f1k) == pytest.approx((100 * mine["exact_match_top1"], 100 * mine["f1_score_top1"], 100 * mine["exact_match_top3"],
+                                                  100 * mine["f1_score_top3"]))
+    assert em1 == pytest.approx(40.0) and emk == pytest.approx(80.0)
+    pred = json.load(open(tmp_path / "pred" / "test_5_top3.pred"))                       # written by the reference (:187-196)
+    assert pred["1"]["prediction"] == canned["who signed the treaty"] and pred["2"]["prediction"] == [""]
