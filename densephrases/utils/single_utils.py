@@ -1,1 +1,1 @@
-from densephrases_b200.runtime import load_encoder  # noqa: F401
+from densephrases_b200.runtime import backward_compat, load_encoder  # noqa: F401

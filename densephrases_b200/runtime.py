@@ -68,7 +68,23 @@ def drqa_metric_max_over_ground_truths(metric_fn, prediction, ground_truths):
     return max(metric_fn(prediction, gt) for gt in ground_truths)
 
 
-# ---- single_utils.load_encoder -------------------------------------------------------------------------------
+# ---- single_utils.backward_compat / load_encoder ----------------------------------------------------------------
+def backward_compat(model_dict):
+    """Old checkpoint names -> current ones, teacher / reader heads dropped (single_utils.py:36-56)."""
+    dropped = ('cross_encoder', 'bert_qd', 'qa_outputs')
+    renamed = (('bert_start', 'phrase_encoder'), ('bert_q_start', 'query_start_encoder'), ('bert_q_end', 'query_end_encoder'))
+    out = {}
+    for key, val in model_dict.items():
+        if key.startswith(dropped):
+            continue
+        hits = [(old, new) for old, new in renamed if key.startswith(old)]
+        if not hits:
+            out[key] = val
+        for old, new in hits:
+            out[key.replace(old, new)] = val
+    return out
+
+
 def load_encoder(device, args, phrase_only=False):
     """-> (model, tokenizer, config).  `args.load_dir/pytorch_model.bin` (a reference checkpoint) is used when present;
     otherwise seeded random weights (no checkpoint is reachable offline)."""

@@ -187,3 +187,98 @@ def test_unmodified_reference_evaluate_runs_on_the_facade(tmp_path):
     assert em1 == pytest.approx(40.0) and emk == pytest.approx(80.0)
     pred = json.load(open(tmp_path / "pred" / "test_5_top3.pred"))                       # written by the reference (:187-196)
     assert pred["1"]["prediction"] == canned["who signed the treaty"] and pred["2"]["prediction"] == [""]
+
+
+@pytest.mark.parametrize("unit", ["phrase", "sentence", "paragraph", "document"])
+def test_densephrases_search_wrapper_equals_unmodified_reference_class(oracle, unit):
+    """model.py:55-109 (`DensePhrases.search`: query2vec -> stacked vectors -> MIPS.search with the unit's aggregation -> field
+    selection) run UNMODIFIED over this repo's MIPS / query2vec gives exactly what densephrases_b200's DensePhrases.search returns."""
+    ref_path = "/root/reference/densephrases/model.py"
+    if not os.path.exists(ref_path):
+        pytest.skip("reference tree not present (GPU box)")
+    import importlib.util
+    import sys
+    import types
+    import torch
+    from densephrases import DensePhrases, Options
+    from densephrases_b200 import runtime as R
+    from densephrases_b200.mips import MIPS
+    from densephrases_b200.tokenization import WordPieceTokenizer
+    from tests.test_mips import OracleIndexAdapter, build
+    stub = types.ModuleType("densephrases.utils.squad_utils")
+    stub.TrueCaser = type("TrueCaser", (), {})
+    sys.modules["densephrases.utils.squad_utils"] = stub
+    try:
+        spec = importlib.util.spec_from_file_location("ref_densephrases_model", ref_path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        del sys.modules["densephrases.utils.squad_utils"]
+    doc_groups, idx_f, _, ref, query = build(oracle)
+    mips = MIPS.from_components(OracleIndexAdapter(ref), idx_f, doc_groups, cuda=False)
+    qvec = torch.from_numpy(query.astype(np.float32))
+
+    class FakeEncoder:
+        def __call__(self, input_ids_=None, attention_mask_=None, token_type_ids_=None, return_query=False):
+            b = input_ids_.shape[0]
+            return qvec[:b, None, :768], qvec[:b, None, 768:]
+
+    o = Options()
+    o.add_model_options(); o.add_index_options(); o.add_retrieval_options(); o.add_data_options()
+    args = o.parse([])
+    q2v = R.get_query2vec(query_encoder=FakeEncoder(), tokenizer=WordPieceTokenizer.from_pretrained_or_synthetic(None), args=args, batch_size=64)
+    theirs, ours = mod.DensePhrases.__new__(mod.DensePhrases), DensePhrases.__new__(DensePhrases)
+    for obj in (theirs, ours):
+        obj.query2vec, obj.mips, obj.truecase, obj.args = q2v, mips, None, args
+    qs = ["first question", "second question", "third"]
+    a = theirs.search(qs, retrieval_unit=unit, top_k=3, truecase=False, return_meta=True)
+    b = ours.search(qs, retrieval_unit=unit, top_k=3, truecase=False, return_meta=True)
+    assert a[0] == b[0] and len(a[0]) == 3 and all(len(x) <= 3 for x in a[0])
+    strip = lambda rets: [[{k: v for k, v in r.items() if k not in ("start_vec", "end_vec")} for r in ret] for ret in rets]
+    assert strip(a[1]) == strip(b[1])
+    assert theirs.search(qs[0], retrieval_unit=unit, top_k=2, truecase=False) == ours.search(qs[0], retrieval_unit=unit, top_k=2, truecase=False)
+
+
+def test_open_utils_and_single_utils_helpers_equal_unmodified_reference(tmp_path):
+    """`load_qa_pairs` (open_utils.py:103-163) and `backward_compat` (single_utils.py:36-56), the reference's code loaded by path
+    (its imports of squad_utils / embed_utils -- not on this path -- stubbed), against the facade's versions on awkward inputs."""
+    if not os.path.exists("/root/reference/densephrases/utils/open_utils.py"):
+        pytest.skip("reference tree not present (GPU box)")
+    import importlib.util
+    import sys
+    import types
+    from densephrases.utils import open_utils as mine_open, single_utils as mine_single
+    stubs = {"densephrases.utils.squad_utils": ("get_question_dataloader", "TrueCaser"), "densephrases.utils.embed_utils": ("get_question_results",)}
+    for name, attrs in stubs.items():
+        m = types.ModuleType(name)
+        for a in attrs:
+            setattr(m, a, object)
+        sys.modules[name] = m
+    try:
+        mods = {}
+        for short in ("single_utils", "open_utils"):
+            spec = importlib.util.spec_from_file_location(f"ref_{short}", f"/root/reference/densephrases/utils/{short}.py")
+            mods[short] = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mods[short])
+    finally:
+        for name in stubs:
+            del sys.modules[name]
+    data = {"data": [{"id": "a1", "question": "Which river?", "answers": ["Seine"]},
+                     {"id": "a2", "origin": "nq.dev.x", "question": "who signed it", "answers": ["Louis", "Anne"], "titles": ["T1", "T2"]},
+                     {"id": "a3", "question": "skipped", "answers": []},
+                     {"id": "a4", "question": "x" * 400 + " [START_ENT] Paris [END_ENT] " + "y" * 400 + "?", "answers": ["Paris"]},
+                     {"id": "a5", "question": "ALL CAPS?", "answers": ["x"]}]}
+    p = tmp_path / "qa.json"
+    json.dump(data, open(p, "w"))
+
+    class Args:
+        do_lower_case, draft, truecase, truecase_path = False, False, False, ""
+
+    for lower, q_idx in [(False, None), (True, None), (False, 1), (False, 3)]:
+        Args.do_lower_case = lower
+        want = mods["open_utils"].load_qa_pairs(str(p), Args, q_idx=q_idx)
+        got = mine_open.load_qa_pairs(str(p), Args, q_idx=q_idx)
+        assert [list(x) for x in got] == [list(x) for x in want]
+    sd = {"bert_q_start.embeddings.w": 1, "bert_q_end.x": 2, "bert_start.y": 3, "cross_encoder.z": 4, "bert_qd.q": 5, "qa_outputs.w": 6,
+          "query_start_encoder.k": 7, "linear.weight": 8}
+    assert mine_single.backward_compat(sd) == mods["single_utils"].backward_compat(sd)
