@@ -17,6 +17,7 @@ class Options(object):
         p.add_argument("--draft", action="store_true")
         p.add_argument("--verbose_logging", action="store_true")
         p.add_argument("--fp16", action="store_true")
+        p.add_argument("--fp16_opt_level", type=str, default="O1")
         p.add_argument("--local_rank", type=int, default=-1)
 
     def add_model_options(self):
@@ -46,6 +47,14 @@ class Options(object):
         p.add_argument('--fine_quant', default='SQ4')
         p.add_argument('--cuda', action='store_true', default=False)
         p.add_argument('--replace', action='store_true', default=False)
+        # build-side flags of build_phrase_index.py (options.py:57-68): declared for flag compatibility, unused on the serving path
+        for name in ('add_all', 'hnsw', 'first_passage'):
+            p.add_argument(f'--{name}', action='store_true', default=False)
+        p.add_argument('--norm_th', type=float, default=999)
+        p.add_argument('--doc_sample_ratio', type=float, default=0.2)
+        p.add_argument('--vec_sample_ratio', type=float, default=0.2)
+        p.add_argument('--num_docs_per_add', type=int, default=2000)
+        p.add_argument('--index_filter', type=float, default=-1e8)
         for name, default in (('quantizer_path', 'quantizer.faiss'), ('trained_index_path', 'trained.faiss'), ('inv_path', 'merged.invdata'),
                               ('subindex_name', 'index'), ('dump_paths', None)):
             p.add_argument(f'--{name}', default=default)

@@ -282,3 +282,25 @@ def test_open_utils_and_single_utils_helpers_equal_unmodified_reference(tmp_path
     sd = {"bert_q_start.embeddings.w": 1, "bert_q_end.x": 2, "bert_start.y": 3, "cross_encoder.z": 4, "bert_qd.q": 5, "qa_outputs.w": 6,
           "query_start_encoder.k": 7, "linear.weight": 8}
     assert mine_single.backward_compat(sd) == mods["single_utils"].backward_compat(sd)
+
+
+def test_option_flags_and_defaults_equal_reference_parser():
+    """Every flag of the four option groups eval_phrase_retrieval.py / model.py add (options.py: model, index, retrieval, data)
+    exists here with the same default; nothing is renamed."""
+    if not os.path.exists("/root/reference/densephrases/options.py"):
+        pytest.skip("reference tree not present (GPU box)")
+    import importlib.util
+    from densephrases import Options
+    spec = importlib.util.spec_from_file_location("ref_options", "/root/reference/densephrases/options.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    theirs, ours = mod.Options(), Options()
+    for group in ("add_model_options", "add_index_options", "add_retrieval_options", "add_data_options"):
+        getattr(theirs, group)()
+        getattr(ours, group)()
+    want, got = vars(theirs.parser.parse_args([])), vars(ours.parse([]))
+    assert not [k for k in want if k not in got]
+    assert {k: got[k] for k in want} == want
+    argv = ["--cuda", "--top_k", "40", "--nprobe", "64", "--index_name", "start/1048576_flat_OPQ96", "--eval_batch_size", "32", "--agg_strat", "opt2"]
+    got2 = vars(ours.parse(argv))
+    assert {k: got2[k] for k in want} == vars(theirs.parser.parse_args(argv))
