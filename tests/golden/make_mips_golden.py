@@ -84,6 +84,10 @@ def main():
                   "answer": r["answer"], "start_vec_sum": float(np.sum(r["start_vec"])), "end_vec_sum": float(np.sum(r["end_vec"]))}
                  for r in rs] for rs in res]
         out["configs"].append({"aggregate": aggregate, "agg_strat": agg, "results": rows})
+    # get_idxs on labels outside [0, ntotal): the reference logs, clips and carries on (index.py:128-133)
+    I = np.array([[-1, 0, ref.ntotal - 1, ref.ntotal, ref.ntotal + 7], [5, -3, 17, 10 ** 12, 1]], dtype=np.int64)
+    doc, word = fresh().get_idxs(I)
+    out["get_idxs"] = {"I": I.tolist(), "doc": np.asarray(doc).tolist(), "word": np.asarray(word).tolist()}
     path = os.path.join(ROOT, "tests", "golden", "mips_search.json")
     json.dump(out, open(path, "w"), ensure_ascii=True)
     print(path, os.path.getsize(path), [len(r) for r in out["configs"][0]["results"]])

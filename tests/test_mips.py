@@ -143,6 +143,10 @@ def test_phrase_stage_matches_reference_golden(oracle, which):
     from oracle.mips_ref import ref_search
     gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "mips_search.json")))
     doc_groups, idx_f, _, ref, query = build(oracle)
+    if which == "mips":                                       # out-of-range labels: clipped like index.py:128-133
+        m = MIPS.from_components(OracleIndexAdapter(ref), idx_f, doc_groups, cuda=False)
+        doc, word = m.get_idxs(np.array(gold["get_idxs"]["I"], dtype=np.int64))
+        assert doc.tolist() == gold["get_idxs"]["doc"] and word.tolist() == gold["get_idxs"]["word"]
     for cfg in gold["configs"]:
         kw = dict(top_k=gold["top_k"], aggregate=cfg["aggregate"], agg_strat=cfg["agg_strat"], return_idxs=True)
         if which == "restatement":
