@@ -123,6 +123,8 @@ def _read_invlists(c, path, ondisk_same_dir):
         if sizes.size != nlist:
             raise ValueError('inverted list size table does not match nlist')
         ntot = int(sizes.sum())
+        if ntot < 0 or ntot * (code_size + 8) > len(c.buf) - c.pos:
+            raise ValueError('truncated file (inverted lists)')
         codes = np.empty((ntot, code_size), dtype=np.uint8)
         ids = np.empty(ntot, dtype=np.int64)
         at = 0
@@ -146,6 +148,8 @@ def _read_invlists(c, path, ondisk_same_dir):
         payload = np.memmap(fname, dtype=np.uint8, mode='r')
         sizes = lists[:, 0].astype(np.int64)
         ntot = int(sizes.sum())
+        if ntot < 0 or ntot * (code_size + 8) > payload.size:
+            raise ValueError(f'{fname} is smaller than the lists it should hold')
         codes = np.empty((ntot, code_size), dtype=np.uint8)
         ids = np.empty(ntot, dtype=np.int64)
         at = 0
@@ -609,17 +613,20 @@ def read_hdf5(path, max_depth=8):
     """-> nested dict {name: dict (group) | ndarray (dataset)} of the whole file (meant for small tables like idx2id.hdf5)."""
     with open(path, 'rb') as f:
         buf = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
-    h = _H5(buf)
 
-    def visit(addr, depth):
+    def visit(h, addr, depth):
         kids = h.children(addr)
         if kids is None:
             return h.dataset(addr)
         if depth > max_depth:
             raise ValueError('group nesting too deep')
-        return {name: visit(a, depth + 1) for name, a in kids.items()}
+        return {name: visit(h, a, depth + 1) for name, a in kids.items()}
 
-    return visit(h.root_header, 0)
+    try:
+        h = _H5(buf)
+        return visit(h, h.root_header, 0)
+    except (struct.error, IndexError, OverflowError, UnicodeDecodeError, TypeError, RecursionError, MemoryError) as e:
+        raise ValueError(f'corrupt or unsupported HDF5 file {path}: {type(e).__name__}: {e}') from e
 
 
 def read_idx2id(path):
