@@ -36,6 +36,8 @@ struct dph_encoder {
     long long *ids = nullptr, *mask = nullptr, *tt = nullptr;
     float *out_s = nullptr, *out_e = nullptr;
     int64_t cap_b = 0;
+    int* bad_ids = nullptr;                      // device flag: an input id / token type was outside the embedding tables
+    bool bad_pending = false;                    // an asynchronous (device-buffer) forward has not had its flag checked yet
 };
 
 static int64_t tower_floats(const dph_encoder* e) {
@@ -82,11 +84,18 @@ __device__ __forceinline__ void ln_row_256(float v[3], const float* g, const flo
 }
 
 struct EmbedArgs { const long long* ids; const long long* tt; int S; const float* word[2]; const float* pos[2]; const float* type[2];
-                   const float* g[2]; const float* b[2]; float* out[2]; };
+                   const float* g[2]; const float* b[2]; float* out[2]; long long vocab, type_vocab; int* bad; };
 __global__ void __launch_bounds__(256) embed_ln_kernel(EmbedArgs a) {
     __shared__ float red[8];
     const long long tok = blockIdx.x; const int tw = blockIdx.y, t = threadIdx.x;
-    const long long id = a.ids[tok], ty = a.tt[tok]; const int s = (int)(tok % a.S);
+    long long id = a.ids[tok], ty = a.tt[tok]; const int s = (int)(tok % a.S);
+    // torch.nn.Embedding raises IndexError on an out-of-range id; here the row is clamped (no out-of-bounds read) and a sticky
+    // device flag makes the host call fail (host buffers: this call; device buffers: the next call that synchronises)
+    if (id < 0 || id >= a.vocab || ty < 0 || ty >= a.type_vocab) {
+        if (t == 0) atomicExch(a.bad, 1);
+        id = id < 0 ? 0 : (id >= a.vocab ? a.vocab - 1 : id);
+        ty = ty < 0 ? 0 : (ty >= a.type_vocab ? a.type_vocab - 1 : ty);
+    }
     const float* w = a.word[tw] + id * ENC_H; const float* p = a.pos[tw] + (long long)s * ENC_H; const float* y = a.type[tw] + ty * ENC_H;
     float v[3];
 #pragma unroll
@@ -339,7 +348,7 @@ DPH_API void dph_encoder_free(dph_encoder* e) {
         float* ws[] = {e->x[t], e->qkv[t], e->ctx[t], e->a[t], e->ffn[t], e->wsplit[t], e->act_hi[t], e->act_lo[t]};
         for (float* p : ws) if (p) cudaFree(p);
     }
-    void* misc[] = {e->ids, e->mask, e->tt, e->out_s, e->out_e};
+    void* misc[] = {e->ids, e->mask, e->tt, e->out_s, e->out_e, e->bad_ids};
     for (void* p : misc) if (p) cudaFree(p);
     delete e;
 }
@@ -440,6 +449,14 @@ DPH_API int dph_encoder_embed_query(dph_encoder* e, const int64_t* ids, const in
     cudaStream_t st = e->stream;
     const int64_t T = (int64_t)B * S;
     DPH_TRY(ensure_ws(e, T, B));
+    if (!e->bad_ids) { DPH_CUDA(cudaMalloc((void**)&e->bad_ids, 4)); DPH_CUDA(cudaMemset(e->bad_ids, 0, 4)); }
+    if (e->bad_pending) {       // flag of the previous asynchronous forward(s): report it now instead of never
+        int h = 0;
+        DPH_CUDA(cudaMemcpyAsync(&h, e->bad_ids, 4, cudaMemcpyDeviceToHost, st));
+        DPH_CUDA(cudaStreamSynchronize(st));
+        e->bad_pending = false;
+        if (h) { DPH_CUDA(cudaMemsetAsync(e->bad_ids, 0, 4, st)); dph_set_error("encoder: an earlier forward received input_ids / token_type_ids outside the embedding tables"); return 1; }
+    }
     const long long *d_ids = (const long long*)ids, *d_mask = (const long long*)mask, *d_tt = (const long long*)tt;
     if (mem == DPH_MEM_HOST) {
         DPH_CUDA(cudaMemcpyAsync(e->ids, ids, T * 8, cudaMemcpyHostToDevice, st));
@@ -451,6 +468,7 @@ DPH_API int dph_encoder_embed_query(dph_encoder* e, const int64_t* ids, const in
         EmbedArgs a;
         a.ids = d_ids; a.tt = d_tt; a.S = S;
         for (int t = 0; t < 2; t++) { a.word[t] = e->tw[t].word; a.pos[t] = e->tw[t].pos; a.type[t] = e->tw[t].type; a.g[t] = e->tw[t].embg; a.b[t] = e->tw[t].embb; a.out[t] = e->x[t]; }
+        a.vocab = e->vocab; a.type_vocab = e->type_vocab; a.bad = e->bad_ids;
         embed_ln_kernel<<<dim3((unsigned)T, 2), 256, 0, st>>>(a);
         DPH_CUDA(cudaGetLastError());
     }
@@ -531,7 +549,12 @@ DPH_API int dph_encoder_embed_query(dph_encoder* e, const int64_t* ids, const in
     if (mem == DPH_MEM_HOST) {
         DPH_CUDA(cudaMemcpyAsync(start_out, ds, (size_t)B * ENC_H * 4, cudaMemcpyDeviceToHost, st));
         DPH_CUDA(cudaMemcpyAsync(end_out, de, (size_t)B * ENC_H * 4, cudaMemcpyDeviceToHost, st));
+        int h = 0;
+        DPH_CUDA(cudaMemcpyAsync(&h, e->bad_ids, 4, cudaMemcpyDeviceToHost, st));
         DPH_CUDA(cudaStreamSynchronize(st));
+        if (h) { DPH_CUDA(cudaMemsetAsync(e->bad_ids, 0, 4, st)); dph_set_error("encoder: input_ids / token_type_ids outside the embedding tables (IndexError in torch)"); return 1; }
+    } else {
+        e->bad_pending = true;
     }
     return 0;
 }

@@ -718,6 +718,8 @@ DPH_API int dph_merge_shards(const float* Dg, const int64_t* Ig, const uint32_t*
     if (n == 0) return 0;
     DPH_CHECK(nshards >= 1 && k >= 1 && (long long)nshards * k <= 8192, "merge_shards: nshards*k must be <= 8192");
     int p2 = 1; while (p2 < nshards * k) p2 <<= 1;
+    static DphPerDeviceOnce once;
+    if (once.first()) { DPH_CUDA(cudaFuncSetAttribute(merge_shards_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8)); }
     merge_shards_kernel<<<(unsigned)n, 256, p2 * 8, (cudaStream_t)cuda_stream>>>(Dg, (const long long*)Ig, Gg, nshards, n, k, D, (long long*)I);
     DPH_CUDA(cudaGetLastError());
     return 0;

@@ -85,25 +85,61 @@ def backward_compat(model_dict):
     return out
 
 
+def _find_vocab(args, load_dir):
+    """vocab.txt the way the reference resolves its tokenizer (single_utils.py:72-77): `tokenizer_name`, else
+    `pretrained_name_or_path`, looked up as a directory / file and under `cache_dir`; `load_dir` last (a fine-tuned checkpoint
+    directory usually carries its own copy)."""
+    cands = []
+    for name in (getattr(args, 'tokenizer_name', None), getattr(args, 'pretrained_name_or_path', None)):
+        if not name:
+            continue
+        cands += [name, os.path.join(name, 'vocab.txt')]
+        cache = getattr(args, 'cache_dir', None)
+        if cache:
+            cands += [os.path.join(cache, name, 'vocab.txt'), os.path.join(cache, name.replace('/', '--'), 'vocab.txt'),
+                      os.path.join(cache, os.path.basename(name), 'vocab.txt')]
+    if load_dir:
+        cands.append(os.path.join(load_dir, 'vocab.txt'))
+    for c in cands:
+        if os.path.isfile(c) and c.endswith('.txt'):
+            return c
+    return None
+
+
 def load_encoder(device, args, phrase_only=False):
-    """-> (model, tokenizer, config).  `args.load_dir/pytorch_model.bin` (a reference checkpoint) is used when present;
-    otherwise seeded random weights (no checkpoint is reachable offline)."""
+    """-> (model, tokenizer, config) from `args.load_dir/pytorch_model.bin` + a WordPiece `vocab.txt` (single_utils.py:59-118).
+    A missing checkpoint or vocabulary raises FileNotFoundError like the reference does; seeded random weights and the
+    synthetic character-level vocabulary are used only when the caller opts in with `args.allow_random_init = True`
+    (tests and benchmarks: no checkpoint is reachable offline)."""
     if phrase_only:
         raise NotImplementedError('the phrase tower is only used offline (generate_phrase_vecs.py); out of scope')
     load_dir = getattr(args, 'load_dir', '') or ''
+    allow_random = bool(getattr(args, 'allow_random_init', False))
     config = BertGeometry()
     cfg_json = os.path.join(load_dir, 'config.json')
     if os.path.exists(cfg_json):
         config = BertGeometry(**json.load(open(cfg_json)))
-    tokenizer = WordPieceTokenizer.from_pretrained_or_synthetic(load_dir, do_lower_case=getattr(args, 'do_lower_case', False),
-                                                               vocab_size=config.vocab_size)
+    vocab_file = _find_vocab(args, load_dir)
+    if vocab_file is not None:
+        tokenizer = WordPieceTokenizer.from_vocab_file(vocab_file, do_lower_case=getattr(args, 'do_lower_case', False))
+    elif allow_random:
+        tokenizer = WordPieceTokenizer.from_pretrained_or_synthetic(None, do_lower_case=getattr(args, 'do_lower_case', False),
+                                                                   vocab_size=config.vocab_size)
+        logger.warning('no vocab.txt found: synthetic character-level WordPiece vocabulary (allow_random_init)')
+    else:
+        raise FileNotFoundError(f'no vocab.txt for the tokenizer (tokenizer_name / pretrained_name_or_path / cache_dir / load_dir={load_dir!r}); '
+                                'pass allow_random_init=True for a synthetic vocabulary')
+    if len(tokenizer.vocab) > config.vocab_size or max(tokenizer.vocab.values()) >= config.vocab_size:
+        raise ValueError(f'vocabulary has ids up to {max(tokenizer.vocab.values())} but the encoder embeds {config.vocab_size} rows')
     ckpt = os.path.join(load_dir, 'pytorch_model.bin')
     if os.path.exists(ckpt):
-        sd = torch.load(ckpt, map_location='cpu')
+        sd = backward_compat(torch.load(ckpt, map_location='cpu'))
         logger.info(f'DensePhrases encoder loaded from {load_dir}')
-    else:
+    elif allow_random:
         sd = random_state_dict(config, getattr(args, 'seed', 42))
-        logger.info('DensePhrases query encoder initialised with seeded random weights (no checkpoint found)')
+        logger.warning('no checkpoint found: query encoder initialised with seeded random weights (allow_random_init)')
+    else:
+        raise FileNotFoundError(f'{ckpt} not found (hub ids are not resolvable offline); pass allow_random_init=True for seeded random weights')
     dev_index = torch.cuda.current_device() if str(device).startswith('cuda') else 0
     model = Encoder(config, tokenizer=tokenizer, state_dict=sd, device=dev_index)
     return model, tokenizer, config
@@ -202,6 +238,7 @@ class DensePhrases(object):
     _AGG = {'phrase': 'opt1', 'sentence': 'opt2', 'paragraph': 'opt2', 'document': 'opt3'}
 
     def __init__(self, load_dir, dump_dir, index_name='start/1048576_flat_OPQ96', device='cuda', verbose=False, mips=None, **kwargs):
+        # kwargs land in args; allow_random_init=True opts into seeded random weights / synthetic vocabulary (tests, benchmarks)
         options = Options()
         options.add_model_options(); options.add_index_options(); options.add_retrieval_options(); options.add_data_options()
         self.args = options.parse([])            # the reference parses the live sys.argv here (model.py:30-35); we do not

@@ -112,4 +112,4 @@ class ShardedIvfPq:
         Dh.copy_(D, non_blocking=True)
         Ih.copy_(I, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
-        return Dh.numpy(), Ih.numpy()
+        return Dh.numpy().copy(), Ih.numpy().copy()       # fresh arrays like faiss index.search; the pinned pair is staging only

@@ -74,11 +74,15 @@ class WordPieceTokenizer(object):
         self.cls_token_id, self.sep_token_id = vocab[CLS], vocab[SEP]
 
     @classmethod
+    def from_vocab_file(cls, vocab_file, do_lower_case=False):
+        vocab = {line.rstrip('\n'): i for i, line in enumerate(open(vocab_file, encoding='utf-8'))}
+        return cls(vocab, do_lower_case)
+
+    @classmethod
     def from_pretrained_or_synthetic(cls, path=None, do_lower_case=False, vocab_size=28996, extra_words=()):
         vocab_file = os.path.join(path, 'vocab.txt') if path and os.path.isdir(path) else None
         if vocab_file and os.path.exists(vocab_file):
-            vocab = {line.rstrip('\n'): i for i, line in enumerate(open(vocab_file, encoding='utf-8'))}
-            return cls(vocab, do_lower_case)
+            return cls.from_vocab_file(vocab_file, do_lower_case)
         vocab = {f'[unused{i}]': i for i in range(vocab_size)}          # placeholder rows, overwritten below
         vocab = {}
         for tok, i in _SPECIAL_IDS.items():

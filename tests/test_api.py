@@ -57,6 +57,24 @@ def test_load_qa_pairs_and_metrics(tmp_path):
     assert f1_score("big red dog", "red dog")[0] == pytest.approx(0.8)
 
 
+def test_load_encoder_raises_without_checkpoint_or_vocab(tmp_path):
+    """A wrong load_dir / missing vocab.txt must not silently fall back to random weights (the reference raises, single_utils.py:62-93)."""
+    import argparse
+    from densephrases_b200.runtime import load_encoder
+    args = argparse.Namespace(load_dir=str(tmp_path / "nope"), pretrained_name_or_path="SpanBERT/spanbert-base-cased", tokenizer_name="",
+                              cache_dir="", do_lower_case=False)
+    with pytest.raises(FileNotFoundError, match="vocab.txt"):
+        load_encoder("cuda", args)
+    (tmp_path / "tok").mkdir()
+    (tmp_path / "tok" / "vocab.txt").write_text("\n".join(["[PAD]"] + [f"[unused{i}]" for i in range(99)] + ["[UNK]", "[CLS]", "[SEP]", "[MASK]", "a", "b"]) + "\n")
+    args.tokenizer_name = str(tmp_path / "tok")
+    with pytest.raises(FileNotFoundError, match="pytorch_model.bin"):
+        load_encoder("cuda", args)
+    args.load_dir = "princeton-nlp/densephrases-multi-query-multi"      # hub ids cannot be resolved offline: raise, do not invent weights
+    with pytest.raises(FileNotFoundError):
+        load_encoder("cuda", args)
+
+
 @pytest.mark.gpu
 def test_densephrases_search_and_evaluate_end_to_end(oracle, tmp_path):
     from densephrases import DensePhrases
@@ -69,7 +87,7 @@ def test_densephrases_search_and_evaluate_end_to_end(oracle, tmp_path):
     list_len, codes, ids = make_phrase_index_arrays(ntotal, 32, 5)
     index = IvfPqIndex.from_arrays(opq_matrix(5), oracle.gen_centroids(5, 0, 32), oracle.gen_pq(5), list_len, codes, ids)
     mips = MIPS.from_components(index, idx_f, doc_groups, cuda=True)
-    model = DensePhrases(load_dir="", dump_dir="unused", mips=mips)
+    model = DensePhrases(load_dir="", dump_dir="unused", mips=mips, allow_random_init=True)
     qs = ["which river crosses the city", "Who signed the treaty", "museum of the island"]   # load_qa_pairs strips a trailing "?"
     single = model.search(qs[0], retrieval_unit="phrase", top_k=5)
     batch, meta = model.search(qs, retrieval_unit="phrase", top_k=5, return_meta=True)
