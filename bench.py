@@ -337,22 +337,23 @@ def measure_search(cx, ix, wl, Q, Qh, nprobe, sample_clocks=False):
     scan_ms = [float(v) for v in local.profile_scan_ms()][-nsteps:]
     local.set_profile(False)
     flags = int(local.last_flags(B).sum())
-    pair_mode = local.last_used_pair_mode()
+    group = local.last_group_size()
+    pair_mode = group > 1
     pk, pk_kind = peaks()
     t_scan = sum(scan_ms) / len(scan_ms) / 1000.0
     mean_bytes = sum(alg_bytes) / len(alg_bytes)
     achieved = mean_bytes / t_scan / 1e9 if t_scan > 0 else 0.0
-    kernel = "scan_pair_kernel" if pair_mode else "scan_kernel<FAST>"
+    kernel = {1: "scan_kernel<FAST>", 2: "scan_pair_kernel", 4: "scan_quad_kernel"}[group]
     traffic, tsrc = lookup_traffic(kernel, wl["name"], nprobe, cx.world)
-    roofline = {"kernel": kernel, "gathers": "two queries per gather (pair-packed)" if pair_mode else "one query per gather",
+    roofline = {"kernel": kernel, "gathers": {1: "one query per gather (fp32 LUT)", 2: "two queries per gather (pair-packed u16 LUTs)", 4: "four queries per gather (quad-packed u8 LUTs)"}[group],
                 "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "peak_kind": pk_kind,
                 "traffic": traffic, "traffic_source": tsrc, "kernel_ms": 1000.0 * t_scan, "algorithmic_bytes_per_launch": mean_bytes,
                 "share_of_step": 1000.0 * t_scan / (ms_prof_pass / nsteps), "step_ms_same_pass": ms_prof_pass / nsteps,
                 "how": f"CUDA events around the kernel inside a back-to-back {nsteps}-step loop on the launching stream (rank 0's shard)"}
     if pair_mode:
-        roofline["note"] = ("algorithmic bytes count every (query, probed vector) pair; the pair kernel serves two queries from one code read and later "
-                            "readers of a list from L2, so achieved > DRAM traffic and frac may exceed 1; the kernel's own limiter is the LSU data "
-                            "pipe (shared-memory gathers), see profiles/ and DESIGN.md 4.1")
+        roofline["note"] = ("algorithmic bytes count every (query, probed vector) pair; the kernel serves the 2 / 4 queries of a group from one code read and "
+                            "later readers of a list from L2, so achieved > DRAM traffic and frac may exceed 1; the kernel's own limiters are the LSU "
+                            "data pipe (shared-memory gathers) and the issue slots, see profiles/ and DESIGN.md 4.1")
     # step-level fraction of the HBM roofline: all ranks' algorithmic bytes / (step time x N x peak)
     tot_bytes = cx.sum_over_ranks(mean_bytes)
     step_frac = tot_bytes / (ms_dev / K / 1000.0) / 1e9 / (cx.world * pk["hbm_gbs"])
@@ -545,7 +546,7 @@ def c1_leg(cx, build, queries, args):
         Dh, Ih = ix.search(Qh[0].numpy(), k)
     ms_e2e = (time.perf_counter() - t0) * 100.0
     out = {"workload": config_dict(wl, 1)["workload"], "gpu": {"value": wl["batch"] / ms * 1000.0, "unit": "queries/s", "ms_per_batch": ms,
-                                                              "e2e_value": wl["batch"] / ms_e2e * 1000.0, "pair_mode": ix.local.last_used_pair_mode()}}
+                                                              "e2e_value": wl["batch"] / ms_e2e * 1000.0, "queries_per_gather": ix.local.last_group_size()}}
     if not args.no_cpu:
         from oracle import ivfpq_ref as oracle
         oracle.build()

@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libdph_b200.so")
 _lib = None
 
 MEM_HOST, MEM_DEVICE = 0, 1
-SCAN_FAST, SCAN_EXACT, SCAN_PAIR, SCAN_SINGLE = 0, 1, 2, 3
+SCAN_FAST, SCAN_EXACT, SCAN_PAIR, SCAN_SINGLE, SCAN_QUAD = 0, 1, 2, 3, 4
 
 _vp, _i64, _i32, _u64, _f32 = C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_float
 _SIGS = {
@@ -53,6 +53,7 @@ _SIGS = {
     "dph_index_last_coarse": (_vp, [_vp]),
     "dph_index_last_xr": (_vp, [_vp]),
     "dph_index_last_used_pair_mode": (_i32, [_vp]),
+    "dph_index_last_group_size": (_i32, [_vp]),
     "dph_index_copy_last": (_i32, [_vp, _i32, _vp, _i64]),
     "dph_index_reconstruct_batch": (_i32, [_vp, _vp, _i64, _vp, _vp, _i32]),
     "dph_encoder_create": (_i32, [C.POINTER(_vp), _i32, _i32, _i32, _i32]),

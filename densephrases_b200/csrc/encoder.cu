@@ -15,6 +15,10 @@
 int dph_launch_gemm_tf32(int group, const float* const* A, const float* const* W, const float* const* bias, const float* const* residual,
                          float* const* out, int M, int N, int K, int act, cudaStream_t st, const float* const* A_lo, const float* const* W_lo);
 int dph_launch_split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t st);
+int dph_launch_split_bf16(const float* x, void* hi, void* lo, long long n, cudaStream_t st);                                                  // gemm_bf16x3.cu
+int dph_launch_gemm_bf16x3(int group, const void* const* A_hi, const void* const* A_lo, const void* const* W_hi, const void* const* W_lo,
+                           const float* const* bias, const float* const* residual, float* const* out, void* const* out_hi, void* const* out_lo,
+                           int M, int N, int K, int act, cudaStream_t st);
 int dph_launch_attention_tc(const float* const qkv[2], float* const ctx[2], const long long* mask, int B, int S, long long T, cudaStream_t st);   // attention_tc.cu
 
 struct LayerW { const float *Wqkv, *bqkv, *Wo, *bo, *ln1g, *ln1b, *Wi, *bi, *Wo2, *bo2, *ln2g, *ln2b; };
@@ -26,7 +30,8 @@ struct dph_encoder {
     float* blob[2] = {nullptr, nullptr};
     TowerW tw[2];
     // 3xTF32 mode: (hi, lo) copies of the four GEMM weight matrices of every layer, made lazily on the first precise forward
-    int precise = 0;
+    int precise = 0;                             // 0: 1xTF32, 1: 3xTF32 split (fp32 planes), 2: bf16x3 split (bf16 planes, gemm_bf16x3.cu)
+    unsigned short* wbf[2] = {nullptr, nullptr}; // bf16x3 mode: per tower, per layer [Wqkv_hi, Wqkv_lo, Wo_hi, Wo_lo, Wi_hi, Wi_lo, Wo2_hi, Wo2_lo]
     int attention_tc = 1;                        // S <= 64 and not precise: attention on the tensor cores (attention_tc.cu); 0: SIMT fp32 kernels below
     float* wsplit[2] = {nullptr, nullptr};       // per tower: for each layer [Wqkv_hi, Wqkv_lo, Wo_hi, Wo_lo, Wi_hi, Wi_lo, Wo2_hi, Wo2_lo]
     float *act_hi[2] = {}, *act_lo[2] = {};      // split copy of the current GEMM input activation (up to T x 3072)
@@ -345,7 +350,7 @@ DPH_API void dph_encoder_free(dph_encoder* e) {
     cudaSetDevice(e->device);
     for (int t = 0; t < 2; t++) {
         if (e->blob[t]) cudaFree(e->blob[t]);
-        float* ws[] = {e->x[t], e->qkv[t], e->ctx[t], e->a[t], e->ffn[t], e->wsplit[t], e->act_hi[t], e->act_lo[t]};
+        float* ws[] = {e->x[t], e->qkv[t], e->ctx[t], e->a[t], e->ffn[t], e->wsplit[t], e->act_hi[t], e->act_lo[t], (float*)e->wbf[t]};
         for (float* p : ws) if (p) cudaFree(p);
     }
     void* misc[] = {e->ids, e->mask, e->tt, e->out_s, e->out_e, e->bad_ids};
@@ -353,7 +358,11 @@ DPH_API void dph_encoder_free(dph_encoder* e) {
     delete e;
 }
 DPH_API int dph_encoder_set_stream(dph_encoder* e, void* s) { e->stream = (cudaStream_t)s; return 0; }
-DPH_API int dph_encoder_set_precision(dph_encoder* e, int precise) { e->precise = precise ? 1 : 0; return 0; }
+DPH_API int dph_encoder_set_precision(dph_encoder* e, int precise) {
+    DPH_CHECK(precise >= 0 && precise <= 2, "precision mode: 0 (1xTF32), 1 (3xTF32) or 2 (bf16x3)");
+    e->precise = precise;
+    return 0;
+}
 DPH_API int dph_encoder_set_attention(dph_encoder* e, int tensor_core) { e->attention_tc = tensor_core ? 1 : 0; return 0; }
 
 // C ABI (test / standalone use): one BERT self-attention over a [B*S, 2304] QKV activation (device pointers) -> ctx [B*S, 768].
@@ -391,6 +400,24 @@ static int ensure_split_weights(dph_encoder* e) {
     }
     return 0;
 }
+static int ensure_bf16_weights(dph_encoder* e) {
+    for (int t = 0; t < 2; t++) {
+        if (e->wbf[t]) continue;
+        DPH_CUDA(cudaMalloc((void**)&e->wbf[t], (size_t)split_layer_floats() * ENC_LAYERS * 2));
+        for (int l = 0; l < ENC_LAYERS; l++) {
+            const LayerW& L = e->tw[t].L[l];
+            const float* src[4] = {L.Wqkv, L.Wo, L.Wi, L.Wo2};
+            unsigned short* p = e->wbf[t] + (size_t)l * split_layer_floats();
+            for (int m = 0; m < 4; m++) { DPH_TRY(dph_launch_split_bf16(src[m], p, p + kGemmW[m], kGemmW[m], e->stream)); p += 2 * kGemmW[m]; }
+        }
+    }
+    return 0;
+}
+static void bf16_ptrs(const dph_encoder* e, int t, int l, int m, const void** hi, const void** lo) {
+    const unsigned short* p = e->wbf[t] + (size_t)l * split_layer_floats();
+    for (int i = 0; i < m; i++) p += 2 * kGemmW[i];
+    *hi = p; *lo = p + kGemmW[m];
+}
 static void split_ptrs(const dph_encoder* e, int t, int l, int m, const float** hi, const float** lo) {
     const float* p = e->wsplit[t] + (size_t)l * split_layer_floats();
     for (int i = 0; i < m; i++) p += 2 * kGemmW[i];
@@ -409,6 +436,7 @@ DPH_API int dph_encoder_load_tower(dph_encoder* e, int tower, const float* blob,
     DPH_CUDA(cudaMemcpy(e->blob[tower], blob, bytes, mem == DPH_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice));
     carve(e, tower);
     if (e->wsplit[tower]) { cudaFree(e->wsplit[tower]); e->wsplit[tower] = nullptr; }
+    if (e->wbf[tower]) { cudaFree(e->wbf[tower]); e->wbf[tower] = nullptr; }
     return 0;
 }
 // free + null + allocate, so that a failed allocation never leaves a dangling pointer behind for dph_encoder_free
@@ -472,7 +500,8 @@ DPH_API int dph_encoder_embed_query(dph_encoder* e, const int64_t* ids, const in
         embed_ln_kernel<<<dim3((unsigned)T, 2), 256, 0, st>>>(a);
         DPH_CUDA(cudaGetLastError());
     }
-    if (e->precise) DPH_TRY(ensure_split_weights(e));
+    if (e->precise == 1) DPH_TRY(ensure_split_weights(e));
+    if (e->precise == 2) DPH_TRY(ensure_bf16_weights(e));
     // one grouped (two-tower) linear layer: out = act(in . W^T + b) + residual; m = which weight of the layer (0 qkv, 1 attn out, 2 ffn in, 3 ffn out)
     auto linear = [&](int l, int m, float* const in[2], const float* const bias[2], float* const resid[2], float* const out[2], int N, int K, int act,
                       long long rows) -> int {
@@ -484,6 +513,24 @@ DPH_API int dph_encoder_embed_query(dph_encoder* e, const int64_t* ids, const in
         if (!e->precise) {
             const float* A[2] = {in[0], in[1]};
             return dph_launch_gemm_tf32(2, A, Wfull, bias, resid ? R : nullptr, out, (int)rows, N, K, act, st, nullptr, nullptr);
+        }
+        if (e->precise == 2) {
+            // bf16x3: operands as (hi, lo) bf16 planes.  The FFN intermediate never exists in fp32: the GELU epilogue of GEMM m = 2
+            // writes its planes (into the memory of `out`), GEMM m = 3 reads them; every other input is split by one pass.
+            const void *Whi[2], *Wlo[2], *Ahi[2], *Alo[2];
+            void *Ohi[2] = {nullptr, nullptr}, *Olo[2] = {nullptr, nullptr};
+            for (int t = 0; t < 2; t++) {
+                bf16_ptrs(e, t, l, m, &Whi[t], &Wlo[t]);
+                if (m == 3) {                                                     // planes left by GEMM m = 2 in `in`
+                    Ahi[t] = in[t]; Alo[t] = reinterpret_cast<const unsigned short*>(in[t]) + rows * (long long)K;
+                } else {
+                    DPH_TRY(dph_launch_split_bf16(in[t], e->act_hi[t], e->act_lo[t], rows * K, st));
+                    Ahi[t] = e->act_hi[t]; Alo[t] = e->act_lo[t];
+                }
+                if (m == 2) { Ohi[t] = out[t]; Olo[t] = reinterpret_cast<unsigned short*>(out[t]) + rows * (long long)N; }
+            }
+            return dph_launch_gemm_bf16x3(2, Ahi, Alo, Whi, Wlo, bias, resid ? R : nullptr, m == 2 ? nullptr : out, m == 2 ? Ohi : nullptr,
+                                          m == 2 ? Olo : nullptr, (int)rows, N, K, act, st);
         }
         const float *Whi[2], *Wlo[2];
         for (int t = 0; t < 2; t++) {

@@ -349,6 +349,11 @@ int dph_launch_split_tf32(const float* x, float* hi, float* lo, long long n, cud
     return 0;
 }
 
+int dph_launch_split_bf16(const float* x, void* hi, void* lo, long long n, cudaStream_t st);                                                  // gemm_bf16x3.cu
+int dph_launch_gemm_bf16x3(int group, const void* const* A_hi, const void* const* A_lo, const void* const* W_hi, const void* const* W_lo,
+                           const float* const* bias, const float* const* residual, float* const* out, void* const* out_hi, void* const* out_lo,
+                           int M, int N, int K, int act, cudaStream_t st);
+
 // how 1xTF32 GEMMs are scheduled: 0 one 128x128 tile per CTA (2 CTAs/SM); 1 the same as 2-CTA clusters sharing the A tile by TMA
 // multicast (needs an even number of N tiles); 2 persistent 128x256 tiles with double-buffered TMEM (needs N % 256 == 0)
 static int g_gemm_mode = 2;      // measured on the encoder forward (B=64, S=64): mode 0 5.44 ms, mode 1 5.65 ms, mode 2 4.41 ms
@@ -428,6 +433,19 @@ DPH_API int dph_gemm_tf32_nt(const float* A, const float* W, const float* bias, 
                              int act, int precise, void* cuda_stream) {
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const float* b[1] = {bias}; const float* r[1] = {residual}; float* o[1] = {out};
+    if (precise == 2) {                          // bf16x3 (gemm_bf16x3.cu): split both operands into (hi, lo) bf16 planes, N % 256 == 0
+        unsigned short* scratch = nullptr;
+        const size_t na = (size_t)M * K, nw = (size_t)N * K;
+        DPH_CUDA(cudaMalloc((void**)&scratch, (2 * na + 2 * nw) * 2));
+        unsigned short *ahi = scratch, *alo = scratch + na, *whi = scratch + 2 * na, *wlo = whi + nw;
+        int rc = dph_launch_split_bf16(A, ahi, alo, (long long)na, st);
+        if (!rc) rc = dph_launch_split_bf16(W, whi, wlo, (long long)nw, st);
+        const void* a1[1] = {ahi}; const void* a2[1] = {alo}; const void* w1[1] = {whi}; const void* w2[1] = {wlo};
+        if (!rc) rc = dph_launch_gemm_bf16x3(1, a1, a2, w1, w2, bias ? b : nullptr, residual ? r : nullptr, o, nullptr, nullptr, (int)M, (int)N, (int)K, act, st);
+        cudaStreamSynchronize(st);
+        cudaFree(scratch);
+        return rc;
+    }
     if (!precise) {
         const float* a[1] = {A}; const float* w[1] = {W};
         return dph_launch_gemm_tf32(1, a, w, bias ? b : nullptr, residual ? r : nullptr, o, (int)M, (int)N, (int)K, act, st, nullptr, nullptr);

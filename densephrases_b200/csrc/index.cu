@@ -3,7 +3,11 @@
 #include "index_internal.cuh"
 #include <algorithm>
 #include <numeric>
+#include <stdlib.h>
 #include <string.h>
+#include <thrust/device_ptr.h>
+#include <thrust/execution_policy.h>
+#include <thrust/sort.h>
 
 static thread_local std::string g_err;
 void dph_set_error(const std::string& msg) { g_err = msg; }
@@ -49,8 +53,8 @@ __device__ __forceinline__ long long list_of_block(const long long* blk_off, lon
 // raw != nullptr: gather from list-major rows [*,96] (row index = local_row_start[l] + j); else synthesise from seed.
 __global__ void __launch_bounds__(192) fill_blocks_kernel(uint8_t* codes, long long nblocks, const long long* blk_off, const int* list_len,
                                                           long long list_lo, long long list_hi, const uint8_t* raw,
-                                                          const long long* local_row_start, uint64_t seed) {
-    const long long blk = blockIdx.x;
+                                                          const long long* local_row_start, uint64_t seed, long long blk0, long long raw_row0) {
+    const long long blk = blk0 + blockIdx.x;                  // this launch covers blocks [blk0, nblocks)
     if (blk >= nblocks) return;
     const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;   // c in 0..5
     __shared__ long long s_l;
@@ -65,7 +69,7 @@ __global__ void __launch_bounds__(192) fill_blocks_kernel(uint8_t* codes, long l
 #pragma unroll
         for (int b = 0; b < 16; b++) bytes[b] = 0;
     } else if (raw) {
-        const uint8_t* row = raw + (local_row_start[l - list_lo] + j) * DPH_CODE;
+        const uint8_t* row = raw + (local_row_start[l - list_lo] + j - raw_row0) * DPH_CODE;      // raw holds rows [raw_row0, ...) of the shard
 #pragma unroll
         for (int b = 0; b < 16; b++) { int t = c * 16 + b; int m = seg * 32 + ((lane + (t & 31)) & 31); bytes[b] = row[m]; }
     } else {
@@ -83,13 +87,19 @@ __global__ void __launch_bounds__(192) fill_blocks_kernel(uint8_t* codes, long l
     *reinterpret_cast<uint4*>(codes + blk * DPH_BLK_BYTES + c * 512 + lane * 16) = v;
 }
 
+// labels of the padded rows of blocks [blk0, nblocks) + the direct-map pairs (label, padded row) of the real rows
 __global__ void fill_ids_kernel(long long* ids, long long nblocks, const long long* blk_off, const int* list_len, long long list_lo,
-                                long long list_hi, const long long* raw_ids, const long long* local_row_start) {
-    const long long blk = blockIdx.x;
+                                long long list_hi, const long long* raw_ids, const long long* local_row_start, long long blk0, long long raw_row0,
+                                long long* dm_ids, long long* dm_rows) {
+    const long long blk = blk0 + blockIdx.x;
     if (blk >= nblocks) return;
     const long long l = list_of_block(blk_off, list_lo, list_hi, blk);
     const long long j = (blk - blk_off[l]) * 32 + threadIdx.x;
-    ids[blk * 32 + threadIdx.x] = (j < (long long)list_len[l]) ? raw_ids[local_row_start[l - list_lo] + j] : -1;
+    const bool real = j < (long long)list_len[l];
+    const long long row = local_row_start[l - list_lo] + j;
+    const long long id = real ? raw_ids[row - raw_row0] : -1;
+    ids[blk * 32 + threadIdx.x] = id;
+    if (real) { dm_ids[row] = id; dm_rows[row] = blk * 32 + threadIdx.x; }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -116,7 +126,8 @@ DPH_API void dph_index_free(dph_index* ix) {
     for (void* p : ptrs) if (p) cudaFree(p);
     DevBuf* bufs[] = {&ix->xdev, &ix->xr, &ix->S, &ix->key, &ix->cd, &ix->lut_scan, &ix->lut_canon, &ix->lutmax, &ix->segs, &ix->wpre, &ix->qinfo,
                       &ix->cand, &ix->cand_off, &ix->cand_cnt, &ix->gthr, &ix->flags, &ix->work, &ix->Dp, &ix->Ip, &ix->Gp, &ix->Dh, &ix->Ih, &ix->eps, &ix->nseg, &ix->lutmin, &ix->lutmaxv, &ix->lutq, &ix->qparams, &ix->gdense,
-                      &ix->pl_cnt, &ix->pl_fill, &ix->pl_off, &ix->pl_blockpre, &ix->pl_entries, &ix->pl_unitpre, &ix->pl_units, &ix->pairwork, &ix->csplit, &ix->xsplit, &ix->candkeys, &ix->cflags};
+                      &ix->pl_cnt, &ix->pl_fill, &ix->pl_off, &ix->pl_blockpre, &ix->pl_entries, &ix->pl_unitpre, &ix->pl_units, &ix->pairwork, &ix->csplit, &ix->xsplit, &ix->candkeys, &ix->cflags,
+                      &ix->rb_ids, &ix->rb_out, &ix->rb_found, &ix->ws_q, &ix->ws_id, &ix->ws_out, &ix->ws_xq};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < DPH_PROF_RING; i++) { if (ix->ev0[i]) cudaEventDestroy(ix->ev0[i]); if (ix->ev1[i]) cudaEventDestroy(ix->ev1[i]); }
     delete ix;
@@ -189,42 +200,61 @@ static int set_lists_common(dph_index* ix, const int64_t* list_len, const uint8_
     DPH_CUDA(cudaMalloc((void**)&d_lrs, local_row_start.size() * 8));
     DPH_CUDA(cudaMemcpy(d_lrs, local_row_start.data(), local_row_start.size() * 8, cudaMemcpyHostToDevice));
     if (synthetic) {
-        fill_blocks_kernel<<<(unsigned)nb, 192, 0, ix->stream>>>(ix->codes, nb, (const long long*)ix->blk_off, ix->list_len, lo, hi, nullptr,
-                                                              (const long long*)d_lrs, seed);
+        for (int64_t b0 = 0; b0 < nb; b0 += (1ll << 30)) {          // grid.x limit
+            const unsigned g = (unsigned)std::min<int64_t>(nb - b0, 1ll << 30);
+            fill_blocks_kernel<<<g, 192, 0, ix->stream>>>(ix->codes, std::min<int64_t>(nb, b0 + g), (const long long*)ix->blk_off, ix->list_len, lo, hi, nullptr,
+                                                         (const long long*)d_lrs, seed, b0, 0);
+        }
         DPH_CUDA(cudaGetLastError());
     } else {
         DPH_CHECK(codes != nullptr, "codes is null");
-        uint8_t* d_raw = nullptr;
-        DPH_CUDA(cudaMalloc((void**)&d_raw, std::max<size_t>((size_t)rows * DPH_CODE, 1)));
-        DPH_CUDA(cudaMemcpy(d_raw, codes, (size_t)rows * DPH_CODE, cudaMemcpyHostToDevice));
-        fill_blocks_kernel<<<(unsigned)nb, 192, 0, ix->stream>>>(ix->codes, nb, (const long long*)ix->blk_off, ix->list_len, lo, hi, d_raw,
-                                                              (const long long*)d_lrs, 0);
-        DPH_CUDA(cudaGetLastError());
-        DPH_CUDA(cudaStreamSynchronize(ix->stream));
-        cudaFree(d_raw);
+        // Upload in chunks of whole lists through a bounded staging buffer (<= ~256 MB of rows): the raw list-major copy never
+        // sits on the device next to the blocked one.  Labels go the same way; the direct map (faiss DirectMap::Hashtable,
+        // build_phrase_index.py:139-141) is filled by the same kernel and sorted ON THE DEVICE.
+        int64_t chunk_rows = (256ll << 20) / DPH_CODE;
+        if (const char* ev = getenv("DPH_UPLOAD_CHUNK_ROWS")) chunk_rows = std::max<int64_t>(1, atoll(ev));      // tests: force many chunks
+        auto chunk_end = [&](int64_t l0, int64_t& acc) {       // lists [l0, l1) of one upload: whole lists, <= chunk_rows rows (one list may exceed it)
+            int64_t l1 = l0;
+            acc = 0;
+            while (l1 < hi && (acc == 0 || acc + list_len[l1] <= chunk_rows)) { acc += list_len[l1]; l1++; }
+            return l1;
+        };
+        int64_t max_rows = 0;
+        for (int64_t l0 = lo, acc = 0; l0 < hi;) { const int64_t l1 = chunk_end(l0, acc); max_rows = std::max(max_rows, acc); l0 = l1; }
+        uint8_t* d_raw = nullptr; int64_t* d_rawids = nullptr;
+        DPH_CUDA(cudaMalloc((void**)&d_raw, std::max<size_t>((size_t)max_rows * DPH_CODE, 1)));
         if (ids) {
-            int64_t* d_rawids = nullptr;
-            DPH_CUDA(cudaMalloc((void**)&d_rawids, std::max<size_t>((size_t)rows * 8, 8)));
-            DPH_CUDA(cudaMemcpy(d_rawids, ids, (size_t)rows * 8, cudaMemcpyHostToDevice));
+            DPH_CUDA(cudaMalloc((void**)&d_rawids, std::max<size_t>((size_t)max_rows * 8, 8)));
             DPH_TRY(dev_alloc(&ix->ids, (size_t)nb * 32, ix));
-            fill_ids_kernel<<<(unsigned)nb, 32, 0, ix->stream>>>((long long*)ix->ids, nb, (const long long*)ix->blk_off, ix->list_len, lo, hi,
-                                                               (const long long*)d_rawids, (const long long*)d_lrs);
-            DPH_CUDA(cudaGetLastError());
-            DPH_CUDA(cudaStreamSynchronize(ix->stream));
-            cudaFree(d_rawids);
-            // direct map (faiss DirectMap::Hashtable, build_phrase_index.py:139-141): sorted labels -> padded local row
-            std::vector<int64_t> order(rows);
-            std::iota(order.begin(), order.end(), 0);
-            std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return ids[a] < ids[b]; });
-            std::vector<int64_t> sid(rows), srow(rows);
-            std::vector<int64_t> prow(rows);
-            for (int64_t l = lo; l < hi; l++)
-                for (int64_t j = 0; j < list_len[l]; j++) prow[local_row_start[l - lo] + j] = (blk_off[l] + j / 32) * 32 + (j % 32);
-            for (int64_t i = 0; i < rows; i++) { sid[i] = ids[order[i]]; srow[i] = prow[order[i]]; }
             DPH_TRY(dev_alloc(&ix->dm_ids, (size_t)rows, ix));
             DPH_TRY(dev_alloc(&ix->dm_rows, (size_t)rows, ix));
-            DPH_CUDA(cudaMemcpy(ix->dm_ids, sid.data(), rows * 8, cudaMemcpyHostToDevice));
-            DPH_CUDA(cudaMemcpy(ix->dm_rows, srow.data(), rows * 8, cudaMemcpyHostToDevice));
+        }
+        int64_t l0 = lo;
+        while (l0 < hi) {
+            int64_t acc = 0;
+            const int64_t l1 = chunk_end(l0, acc);
+            const int64_t r0 = local_row_start[l0 - lo];
+            const int64_t b0 = blk_off[l0], b1 = (l1 < hi) ? blk_off[l1] : nb;
+            if (acc > 0 && b1 > b0) {
+                DPH_CUDA(cudaMemcpyAsync(d_raw, codes + (size_t)r0 * DPH_CODE, (size_t)acc * DPH_CODE, cudaMemcpyHostToDevice, ix->stream));
+                fill_blocks_kernel<<<(unsigned)(b1 - b0), 192, 0, ix->stream>>>(ix->codes, b1, (const long long*)ix->blk_off, ix->list_len, lo, hi, d_raw,
+                                                                                 (const long long*)d_lrs, 0, b0, r0);
+                if (ids) {
+                    DPH_CUDA(cudaMemcpyAsync(d_rawids, ids + r0, (size_t)acc * 8, cudaMemcpyHostToDevice, ix->stream));
+                    fill_ids_kernel<<<(unsigned)(b1 - b0), 32, 0, ix->stream>>>((long long*)ix->ids, b1, (const long long*)ix->blk_off, ix->list_len, lo, hi,
+                                                                                 (const long long*)d_rawids, (const long long*)d_lrs, b0, r0,
+                                                                                 (long long*)ix->dm_ids, (long long*)ix->dm_rows);
+                }
+                DPH_CUDA(cudaGetLastError());
+                DPH_CUDA(cudaStreamSynchronize(ix->stream));       // the staging buffers are reused by the next chunk
+            }
+            l0 = l1;
+        }
+        cudaFree(d_raw);
+        if (d_rawids) cudaFree(d_rawids);
+        if (ids) {
+            thrust::device_ptr<long long> kp((long long*)ix->dm_ids), vp((long long*)ix->dm_rows);
+            thrust::sort_by_key(thrust::cuda::par.on(ix->stream), kp, kp + rows, vp);
             ix->dm_n = rows;
         }
     }
@@ -254,7 +284,7 @@ DPH_API int dph_index_set_nprobe(dph_index* ix, int nprobe) {
 }
 DPH_API int dph_index_set_coarse_tc(dph_index* ix, int on) { ix->coarse_tc = on ? 1 : 0; return 0; }
 DPH_API int dph_index_set_scan_mode(dph_index* ix, int mode) {
-    DPH_CHECK(mode >= 0 && mode <= 3, "bad scan mode");
+    DPH_CHECK(mode >= 0 && mode <= 4, "bad scan mode");
     ix->scan_mode = mode;
     return 0;
 }
@@ -294,7 +324,8 @@ DPH_API const int32_t* dph_index_last_flags(const dph_index* ix) { return ix->fl
 DPH_API const int32_t* dph_index_last_probes(const dph_index* ix) { return ix->key.as<int32_t>(); }
 DPH_API const float* dph_index_last_coarse(const dph_index* ix) { return ix->cd.as<float>(); }
 DPH_API const float* dph_index_last_xr(const dph_index* ix) { return ix->xr.as<float>(); }
-DPH_API int dph_index_last_used_pair_mode(const dph_index* ix) { return ix->last_pair ? 1 : 0; }
+DPH_API int dph_index_last_used_pair_mode(const dph_index* ix) { return ix->last_group > 1 ? 1 : 0; }
+DPH_API int dph_index_last_group_size(const dph_index* ix) { return ix->last_group; }
 DPH_API int dph_index_copy_last(dph_index* ix, int which, void* dst_host, int64_t bytes) {
     const void* src = which == 0 ? ix->flags.p : which == 1 ? ix->key.p : which == 2 ? ix->cd.p : which == 3 ? ix->xr.p : nullptr;
     DPH_CHECK(src != nullptr, "copy_last: nothing to copy");
@@ -317,7 +348,11 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
     // the 10-bit quantisation, so its slack grows with k (order statistics: the gap between ranks k and 1.5k is ~0.1 sigma).
     const int keep_single = k + DPH_KEEP_SLACK;
     const int keep_pair = k + (k / 2 > DPH_KEEP_SLACK ? k / 2 : DPH_KEEP_SLACK);
-    const int keep_max = keep_pair;
+    // quad filter: 8-bit entries, eps ~2.7x the pair filter's: 2 eps ~ 0.26 sigma of the scores.  The drop threshold is some unit's
+    // keep-th best, i.e. at global rank >= keep; the proof needs score(rank k) - score(rank keep) > 2 eps.  Order statistics of the
+    // top of ~6 M scores: rank 10 -> rank 110 is ~0.5 sigma, which leaves a 2x margin (7-bit entries would need keep ~ 400).
+    const int keep_quad = k + (2 * k > 100 ? 2 * k : 100);
+    const int keep_max = keep_quad > keep_pair ? keep_quad : keep_pair;
     DPH_TRY(ix->xr.ensure((size_t)n * ix->d * 4));
     DPH_TRY(ix->S.ensure((size_t)n * ix->nlist * 4));
     DPH_TRY(ix->key.ensure((size_t)n * nprobe * 4));
@@ -329,14 +364,20 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
     DPH_TRY(ix->qinfo.ensure((size_t)n * 4));
     DPH_TRY(ix->eps.ensure((size_t)n * 4));
     DPH_TRY(ix->nseg.ensure((size_t)n * 4));
-    // pair mode (two queries per gather) pays when lists are probed by >= ~1.5 queries of the batch on average
+    // sharing gathers between the queries that probe a list pays when lists are probed by >= ~1.5 queries of the batch on average
     const int64_t eff_probe = std::min<int64_t>(nprobe, ix->nlist);
-    // ... and when lists are long enough to amortise rebuilding the packed 192 KB LUT at every (list, pair) item
+    // ... and when lists are long enough to amortise rebuilding the packed 192 KB LUT at every (list, query group) item
     const int64_t nl_local = std::max<int64_t>(ix->list_hi - ix->list_lo, 1);
     const bool long_lists = ix->ntotal_local / nl_local >= 4096;
-    bool pair = ix->scan_mode == DPH_SCAN_PAIR || (ix->scan_mode == DPH_SCAN_FAST && long_lists && n * eff_probe * 2 >= ix->nlist * 3);
-    if (keep_pair > 1536 - DPH_SCAN_THREADS || ix->scan_mode == DPH_SCAN_SINGLE) pair = false;
-    const int keep_fast = pair ? keep_pair : keep_single;
+    const bool shared = long_lists && n * eff_probe * 2 >= ix->nlist * 3;
+    int group = 1;                                  // queries per gather: 1, 2 (pair-packed) or 4 (quad-packed)
+    if (ix->scan_mode == DPH_SCAN_PAIR) group = 2;
+    else if (ix->scan_mode == DPH_SCAN_QUAD) group = 4;
+    else if (ix->scan_mode == DPH_SCAN_FAST && shared) group = 4;
+    if (group == 4 && keep_quad > DPH_QUAD_KEEP_MAX) group = 2;
+    if (group == 2 && keep_pair > 1536 - DPH_SCAN_THREADS) group = 1;
+    const bool pair = group > 1;
+    const int keep_fast = group == 4 ? keep_quad : (group == 2 ? keep_pair : keep_single);
     if (!pair) DPH_TRY(ix->lut_scan.ensure((size_t)n * DPH_LUT_SCAN_FLOATS * 4));
     DPH_TRY(ix->cand.ensure(((size_t)(2 * grid + 2 * n + 2) + (pair ? (size_t)(n * nprobe + 2 * DPH_PAIR_UNITS_PER_CTA * grid + 2 * n + 16) : 0)) * keep_max * 8));
     DPH_TRY(ix->cand_off.ensure((size_t)(n + 1) * 8));
@@ -361,7 +402,7 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
         DPH_TRY(ix->pairwork.ensure(sizeof(DphPairWork)));
     }
     ix->last_n = n;
-    if (stage != 1) ix->last_pair = pair;
+    if (stage != 1) ix->last_group = group;
     if (stage == 1) ix->last_coarse_n = n;
 
     if (stage == 1) {
@@ -386,22 +427,22 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
         }
     }
     DPH_TRY(dph_launch_lut(ix->xr.as<float>(), n, ix->pq, pair ? nullptr : ix->lut_scan.as<float>(), ix->lut_canon.as<float>(), ix->lutmax.as<float>(),
-                           ix->lutmin.as<float>(), ix->lutmaxv.as<float>(), pair ? ix->lutq.as<unsigned short>() : nullptr,
-                           pair ? ix->qparams.as<float2>() : nullptr, st));
+                           ix->lutmin.as<float>(), ix->lutmaxv.as<float>(), pair ? ix->lutq.p : nullptr,
+                           pair ? ix->qparams.as<float2>() : nullptr, st, group));
     if (ix->scan_mode != DPH_SCAN_EXACT) {
-        DPH_TRY(dph_launch_plan(ix, n, k, keep_fast, grid, nullptr, st, pair));
+        DPH_TRY(dph_launch_plan(ix, n, k, keep_fast, grid, nullptr, st, group));
         if (ix->profile) DPH_CUDA(cudaEventRecord(ix->ev0[ix->prof_n % DPH_PROF_RING], st));
-        if (pair) DPH_TRY(dph_launch_scan_pair(ix, n, keep_fast, grid, st));
+        if (pair) DPH_TRY(dph_launch_scan_pair(ix, n, keep_fast, grid, st, group));
         else DPH_TRY(dph_launch_scan(ix, n, k, keep_fast, DPH_SCAN_FAST, grid, st));
         if (ix->profile) { DPH_CUDA(cudaEventRecord(ix->ev1[ix->prof_n % DPH_PROF_RING], st)); ix->prof_n++; }
         DPH_TRY(dph_launch_merge(ix, n, k, DPH_SCAN_FAST, nullptr, D, I, G, st));
         // fallback for queries whose filter could not be proven exact (no-op launches when no flag is set)
-        DPH_TRY(dph_launch_plan(ix, n, k, k, grid, ix->flags.as<int32_t>(), st, false));
+        DPH_TRY(dph_launch_plan(ix, n, k, k, grid, ix->flags.as<int32_t>(), st, 1));
         DPH_TRY(dph_launch_scan(ix, n, k, k, DPH_SCAN_EXACT, grid, st));
         DPH_TRY(dph_launch_merge(ix, n, k, DPH_SCAN_EXACT, ix->flags.as<int32_t>(), D, I, G, st));
     } else {
         DPH_CUDA(cudaMemsetAsync(ix->flags.p, 0, (size_t)n * 4, st));
-        DPH_TRY(dph_launch_plan(ix, n, k, k, grid, nullptr, st, false));
+        DPH_TRY(dph_launch_plan(ix, n, k, k, grid, nullptr, st, 1));
         if (ix->profile) DPH_CUDA(cudaEventRecord(ix->ev0[ix->prof_n % DPH_PROF_RING], st));
         DPH_TRY(dph_launch_scan(ix, n, k, k, DPH_SCAN_EXACT, grid, st));
         if (ix->profile) { DPH_CUDA(cudaEventRecord(ix->ev1[ix->prof_n % DPH_PROF_RING], st)); ix->prof_n++; }
@@ -527,7 +568,7 @@ DPH_API int dph_index_reconstruct_batch(dph_index* ix, const int64_t* ids, int64
     DPH_CUDA(cudaSetDevice(ix->device));
     if (m == 0) return 0;
     const int64_t* d_ids = ids; float* d_out = out; uint8_t* d_found = found;
-    DevBuf tmp_ids, tmp_out, tmp_found;
+    DevBuf &tmp_ids = ix->rb_ids, &tmp_out = ix->rb_out, &tmp_found = ix->rb_found;       // grow-only pools: no cudaMalloc / cudaFree per call
     if (mem == DPH_MEM_HOST) {
         DPH_TRY(tmp_ids.ensure((size_t)m * 8)); DPH_TRY(tmp_out.ensure((size_t)m * ix->d * 4)); DPH_TRY(tmp_found.ensure((size_t)m));
         DPH_CUDA(cudaMemcpyAsync(tmp_ids.p, ids, (size_t)m * 8, cudaMemcpyHostToDevice, ix->stream));
@@ -539,7 +580,6 @@ DPH_API int dph_index_reconstruct_batch(dph_index* ix, const int64_t* ids, int64
         DPH_CUDA(cudaMemcpyAsync(out, d_out, (size_t)m * ix->d * 4, cudaMemcpyDeviceToHost, ix->stream));
         if (found) DPH_CUDA(cudaMemcpyAsync(found, d_found, (size_t)m, cudaMemcpyDeviceToHost, ix->stream));
         DPH_CUDA(cudaStreamSynchronize(ix->stream));
-        tmp_ids.release(); tmp_out.release(); tmp_found.release();
     }
     return 0;
 }
@@ -583,7 +623,7 @@ DPH_API int dph_index_window_scores(dph_index* ix, const float* q, const int64_t
     DPH_CHECK(L >= 1 && L <= 64, "window length out of range");
     DPH_CUDA(cudaSetDevice(ix->device));
     if (m == 0) return 0;
-    DevBuf tq, tid, tout, txq;
+    DevBuf &tq = ix->ws_q, &tid = ix->ws_id, &tout = ix->ws_out, &txq = ix->ws_xq;           // grow-only pools
     const float* dq = q; const int64_t* did = first_id; float* dout = out_scores;
     if (mem == DPH_MEM_HOST) {
         DPH_TRY(tq.ensure((size_t)m * ix->d * 4)); DPH_TRY(tid.ensure((size_t)m * 8)); DPH_TRY(tout.ensure((size_t)m * L * 4));
@@ -596,7 +636,6 @@ DPH_API int dph_index_window_scores(dph_index* ix, const float* q, const int64_t
     window_scores_kernel<<<(unsigned)m, 96, 0, ix->stream>>>(make_locate(ix), txq.as<float>(), (const long long*)did, L, ix->codes, ix->C, ix->pq, dout);
     DPH_CUDA(cudaGetLastError());
     if (mem == DPH_MEM_HOST) DPH_CUDA(cudaMemcpyAsync(out_scores, dout, (size_t)m * L * 4, cudaMemcpyDeviceToHost, ix->stream));
-    DPH_CUDA(cudaStreamSynchronize(ix->stream));
-    tq.release(); tid.release(); tout.release(); txq.release();
+    if (mem == DPH_MEM_HOST) DPH_CUDA(cudaStreamSynchronize(ix->stream));
     return 0;
 }

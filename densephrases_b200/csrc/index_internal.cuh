@@ -8,6 +8,7 @@
 #define DPH_SCAN_WARPS (DPH_SCAN_THREADS / 32)
 #define DPH_CAND_CAP 3072          // shared-memory candidate buffer (u64 keys) per scan CTA
 #define DPH_PAIR_CAP 1280          // pair mode: one buffer per query of the pair
+#define DPH_QUAD_KEEP_MAX 256       // quad mode: QCAP (768) - scan threads (512), see scan.cu
 
 #define DPH_KEEP_SLACK 32          // fast mode keeps k + slack candidates per CTA
 #define DPH_MAX_K 1024
@@ -60,11 +61,12 @@ struct dph_index {
     DevBuf xdev, xr, S, key, cd, lut_scan, lut_canon, lutmax, segs, wpre, qinfo, cand, cand_off, cand_cnt, gthr, flags,
         work, Dp, Ip, Gp, Dh, Ih, eps, nseg,
         lutmin, lutmaxv, lutq, qparams, gdense, pl_cnt, pl_fill, pl_off, pl_blockpre, pl_entries, pl_unitpre, pl_units, pairwork,
-        csplit, xsplit, candkeys, cflags;
+        csplit, xsplit, candkeys, cflags,
+        rb_ids, rb_out, rb_found, ws_q, ws_id, ws_out, ws_xq;        // reconstruct_batch / window_scores staging (host-buffer calls)
     int64_t csplit_lo = -1, csplit_nl = -1;
     int coarse_tc = 1;                 // tensor-core coarse quantizer with exact re-rank (0: always the SIMT sequential-k GEMM)
     int64_t last_n = 0;
-    bool last_pair = false;
+    int last_group = 1;                // queries per gather used by the last search (1, 2 or 4)
     int64_t last_coarse_n = -1;
     bool profile = false;              // CUDA events around the scan kernel of the last search chunk
     cudaEvent_t ev0[DPH_PROF_RING] = {}, ev1[DPH_PROF_RING] = {};
@@ -78,9 +80,10 @@ int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprob
 int dph_coarse_tc(dph_index* ix, int64_t n, int64_t lo, int64_t nl, int nprobe, unsigned long long* keys64, int32_t* key, float* cd, cudaStream_t st);
 int dph_launch_coarse_merge(const unsigned long long* keys, int W, int64_t n, int nprobe, int32_t* key, float* cd, cudaStream_t st);
 int dph_launch_lut(const float* xr, int64_t n, const float* pq, float* lut_scan, float* lut_canon, float* lutmax, float* lutmin, float* lutmaxv,
-                   unsigned short* lutq, float2* qparams, cudaStream_t st);
-int dph_launch_plan(dph_index* ix, int64_t n, int k, int keep, int grid, const int32_t* only_flagged, cudaStream_t st, bool pair);
-int dph_launch_scan_pair(dph_index* ix, int64_t n, int keep, int grid, cudaStream_t st);
+                   void* lutq, float2* qparams, cudaStream_t st, int group);
+// group: queries per gather of the scan -- 1 (fp32 LUT, one query), 2 (pair-packed u16 LUTs), 4 (quad-packed u8 LUTs)
+int dph_launch_plan(dph_index* ix, int64_t n, int k, int keep, int grid, const int32_t* only_flagged, cudaStream_t st, int group);
+int dph_launch_scan_pair(dph_index* ix, int64_t n, int keep, int grid, cudaStream_t st, int group);
 // ---- scan.cu ----
 int dph_launch_scan(dph_index* ix, int64_t n, int k, int keep, int mode, int grid, cudaStream_t st);
 int dph_launch_merge(dph_index* ix, int64_t n, int k, int mode, const int32_t* only_flagged, float* D, int64_t* I,

@@ -155,17 +155,108 @@ __global__ void __launch_bounds__(256) sgemm_nt_seq_small_kernel(const float* __
     }
 }
 
+// Few query rows (the usual case: 64 ... 2048 vectors per batch): (16 TM) x 64 tiles, TM x 4 micro-tile, 256 threads.  The k chain
+// of every output is sequential by definition, so the only parallelism is across outputs: small row tiles put the batch on many
+// SMs (n = 64, m = 768: 48 CTAs instead of 12) and keep several CTAs resident per SM so that the LDS -> FFMA latency of one
+// warp is covered by the others.  Same arithmetic as the kernels above (one FFMA per k per output, k ascending, from +0).
+template <int TM>
+__global__ void __launch_bounds__(256) sgemm_nt_seq_rows_kernel(const float* __restrict__ X, long long n, const float* __restrict__ W,
+                                                                 long long m, int K, float* __restrict__ out) {
+    constexpr int BM = 16 * TM;
+    __shared__ __align__(16) float As[2][GSK][BM];
+    __shared__ __align__(16) float Bs[2][GSK][64];
+    const int tid = threadIdx.x;
+    const long long row0 = (long long)blockIdx.y * BM, col0 = (long long)blockIdx.x * 64;
+    // A tile: BM rows x 8 float4 along k; thread -> (row = tid % BM, float4 slots tid / BM + i * (256 / BM))
+    constexpr int A_PER = (BM * 8 + 255) / 256;            // float4 loads per thread for the A tile (1 for TM <= 2, 2 for TM = 4)
+    constexpr int A_STEP = 256 / BM;                       // slots covered per pass
+    const int ar = tid % BM, aq = tid / BM;
+    const int br = tid & 63, bq = tid >> 6;
+    const bool aok = (row0 + ar) < n && (A_PER * A_STEP >= 8 || aq < 8);
+    const bool bok = (col0 + br) < m;
+    const float4* ap = reinterpret_cast<const float4*>(X + ((row0 + ar) < n ? (row0 + ar) : 0) * K);
+    const float4* bp = reinterpret_cast<const float4*>(W + (bok ? (col0 + br) : 0) * K);
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[TM][4];
+#pragma unroll
+    for (int i = 0; i < TM; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 ra[A_PER], rb[2];
+    auto fetch = [&](int kt) {
+#pragma unroll
+        for (int i = 0; i < A_PER; i++) { const int q = aq + i * A_STEP; ra[i] = (aok && q < 8) ? __ldg(ap + kt * 8 + q) : z4; }
+        rb[0] = bok ? __ldg(bp + kt * 8 + bq) : z4;
+        rb[1] = bok ? __ldg(bp + kt * 8 + bq + 4) : z4;
+    };
+    auto stash = [&](int b) {
+#pragma unroll
+        for (int i = 0; i < A_PER; i++) {
+            const int q = aq + i * A_STEP;
+            if (q < 8) { As[b][q * 4 + 0][ar] = ra[i].x; As[b][q * 4 + 1][ar] = ra[i].y; As[b][q * 4 + 2][ar] = ra[i].z; As[b][q * 4 + 3][ar] = ra[i].w; }
+        }
+        Bs[b][bq * 4 + 0][br] = rb[0].x; Bs[b][bq * 4 + 1][br] = rb[0].y; Bs[b][bq * 4 + 2][br] = rb[0].z; Bs[b][bq * 4 + 3][br] = rb[0].w;
+        Bs[b][16 + bq * 4 + 0][br] = rb[1].x; Bs[b][16 + bq * 4 + 1][br] = rb[1].y; Bs[b][16 + bq * 4 + 2][br] = rb[1].z; Bs[b][16 + bq * 4 + 3][br] = rb[1].w;
+    };
+    const int ktiles = K / GSK;
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    int buf = 0;
+    for (int kt = 0; kt < ktiles; kt++) {
+        if (kt + 1 < ktiles) fetch(kt + 1);
+#pragma unroll
+        for (int k = 0; k < GSK; k++) {
+            float a[TM];
+#pragma unroll
+            for (int i = 0; i < TM; i++) a[i] = As[buf][k][ty * TM + i];
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+            const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < TM; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (kt + 1 < ktiles) {
+            stash(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < TM; i++) {
+        const long long rr = row0 + ty * TM + i;
+        if (rr >= n) continue;
+        const long long c = col0 + tx * 4;
+        float* o = out + rr * m + c;
+        if (c + 3 < m && ((m & 3) == 0)) *reinterpret_cast<float4*>(o) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        else {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (c + j < m) o[j] = acc[i][j];
+        }
+    }
+}
+
 int dph_launch_sgemm_nt_seq(const float* X, int64_t n, const float* W, int64_t m, int K, float* out, cudaStream_t st) {
     DPH_CHECK(K % GSK == 0, "sgemm_nt_seq: K must be a multiple of 32");
     if (n == 0 || m == 0) return 0;
     dim3 grid((unsigned)((m + GBN - 1) / GBN), (unsigned)((n + GBM - 1) / GBM));
-    if ((long long)grid.x * grid.y < 2 * 148) {
-        dim3 gs((unsigned)((m + 63) / 64), (unsigned)((n + 63) / 64));
-        sgemm_nt_seq_small_kernel<<<gs, 256, 0, st>>>(X, n, W, m, K, out);
+    if ((long long)grid.x * grid.y >= 2 * 148) {
+        sgemm_nt_seq_kernel<<<grid, 256, 0, st>>>(X, n, W, m, K, out);
         DPH_CUDA(cudaGetLastError());
         return 0;
     }
-    sgemm_nt_seq_kernel<<<grid, 256, 0, st>>>(X, n, W, m, K, out);
+    // pick the row tile so that the grid covers the SMs a few times over (all CTAs co-resident: <= 24 KB of shared memory each)
+    const long long ct = (m + 63) / 64;
+    if (ct * ((n + 63) / 64) >= 3 * 148) {
+        sgemm_nt_seq_small_kernel<<<dim3((unsigned)ct, (unsigned)((n + 63) / 64)), 256, 0, st>>>(X, n, W, m, K, out);
+    } else if (ct * ((n + 31) / 32) >= 2 * 148) {
+        sgemm_nt_seq_rows_kernel<2><<<dim3((unsigned)ct, (unsigned)((n + 31) / 32)), 256, 0, st>>>(X, n, W, m, K, out);
+    } else {
+        sgemm_nt_seq_rows_kernel<1><<<dim3((unsigned)ct, (unsigned)((n + 15) / 16)), 256, 0, st>>>(X, n, W, m, K, out);
+    }
     DPH_CUDA(cudaGetLastError());
     return 0;
 }
@@ -431,11 +522,14 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ xr, 
 // Quantised LUT for the pair-packed scan: qv[m][j] = round((LUT[m][j] - min_m) / step) in [0, 682], one step per query
 // (step = max_m range_m / 682) so that 96 entries sum below 2^16 and two queries' tables can share one 32-bit word.
 // Written in the scan layout ([3][256][64] u16); qparams[q] = (step, sum_m min_m).
+// Quad mode (four queries per gather): the same with 8-bit entries, qv in [0, 255] (96 * 255 < 2^15), T = unsigned char.
 #define DPH_QMAX 682
+#define DPH_QMAX8 255
+template <class T, int QMAX>
 __global__ void __launch_bounds__(256) lutq_kernel(const float* __restrict__ lut_canon, const float* __restrict__ lutmin,
-                                                    const float* __restrict__ lutmaxv, unsigned short* __restrict__ lutq,
+                                                    const float* __restrict__ lutmaxv, T* __restrict__ lutq,
                                                     float2* __restrict__ qparams) {
-    __shared__ unsigned short tile[256 * 34];
+    __shared__ T tile[256 * 34];
     __shared__ float s_step, s_base;
     const long long q = blockIdx.x;
     const int seg = blockIdx.y, j = threadIdx.x, lane = j & 31;
@@ -444,7 +538,7 @@ __global__ void __launch_bounds__(256) lutq_kernel(const float* __restrict__ lut
         for (int m = lane; m < DPH_M; m += 32) { r = fmaxf(r, lutmaxv[q * DPH_M + m] - lutmin[q * DPH_M + m]); b += lutmin[q * DPH_M + m]; }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) { r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, off)); b += __shfl_xor_sync(0xffffffffu, b, off); }
-        if (lane == 0) { s_step = fmaxf(r / (float)DPH_QMAX, 1e-30f); s_base = b; }
+        if (lane == 0) { s_step = fmaxf(r / (float)QMAX, 1e-30f); s_base = b; }
     }
     __syncthreads();
     const float inv = 1.0f / s_step;
@@ -452,25 +546,26 @@ __global__ void __launch_bounds__(256) lutq_kernel(const float* __restrict__ lut
         const int m = seg * 32 + ml;
         const float v = lut_canon[(q * DPH_M + m) * 256 + j];
         int qv = (int)((v - lutmin[q * DPH_M + m]) * inv + 0.5f);
-        qv = qv < 0 ? 0 : (qv > DPH_QMAX ? DPH_QMAX : qv);
-        tile[j * 34 + ml] = (unsigned short)qv;
+        qv = qv < 0 ? 0 : (qv > QMAX ? QMAX : qv);
+        tile[j * 34 + ml] = (T)qv;
     }
     __syncthreads();
-    unsigned short* dst = lutq + ((size_t)q * 3 + seg) * (256 * 64);
+    T* dst = lutq + ((size_t)q * 3 + seg) * (256 * 64);
     for (int idx = j; idx < 256 * 64; idx += 256) {
         const int row = idx >> 6, w = idx & 63;
-        dst[idx] = (w < 63) ? tile[row * 34 + (w & 31)] : (unsigned short)0;
+        dst[idx] = (w < 63) ? tile[row * 34 + (w & 31)] : (T)0;
     }
     if (seg == 0 && j == 0) qparams[q] = make_float2(s_step, s_base);
 }
 
 int dph_launch_lut(const float* xr, int64_t n, const float* pq, float* lut_scan, float* lut_canon, float* lutmax, float* lutmin, float* lutmaxv,
-                   unsigned short* lutq, float2* qparams, cudaStream_t st) {
+                   void* lutq, float2* qparams, cudaStream_t st, int group) {
     if (n == 0) return 0;
     lut_kernel<<<dim3((unsigned)n, 3), 256, 0, st>>>(xr, pq, lut_scan, lut_canon, lutmax, lutmin, lutmaxv);
     DPH_CUDA(cudaGetLastError());
     if (lutq) {
-        lutq_kernel<<<dim3((unsigned)n, 3), 256, 0, st>>>(lut_canon, lutmin, lutmaxv, lutq, qparams);
+        if (group == 4) lutq_kernel<unsigned char, DPH_QMAX8><<<dim3((unsigned)n, 3), 256, 0, st>>>(lut_canon, lutmin, lutmaxv, (unsigned char*)lutq, qparams);
+        else lutq_kernel<unsigned short, DPH_QMAX><<<dim3((unsigned)n, 3), 256, 0, st>>>(lut_canon, lutmin, lutmaxv, (unsigned short*)lutq, qparams);
         DPH_CUDA(cudaGetLastError());
     }
     return 0;
@@ -497,6 +592,10 @@ __global__ void __launch_bounds__(256) plan_segs_kernel(PlanArgs a) {
     const long long q = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (q >= a.n) return;
     const bool active = a.only_flagged ? (a.only_flagged[q] != 0) : true;
+    if (!active) {                                   // fallback plan: nothing to do for queries whose fast filter was proven exact
+        if (lane == 0) { a.qblocks[q] = 0u; a.nseg[q] = 0; }
+        return;
+    }
     unsigned gacc = 0, wacc = 0;
     int sacc = 0;
     float dmax = 0.0f;
@@ -630,6 +729,7 @@ struct PairPlanArgs {
     const int* key; long long nq_probes; int nprobe; const int* list_len; long long list_lo, list_hi, nlist; int grid;
     int* cnt; int* fill; int* off; long long* blockpre; unsigned* entries; DphPairWork* work;
     int* unitpre; unsigned long long* units;
+    int gsz;                       // queries per work item: 2 (pair-packed scan) or 4 (quad-packed scan)
 };
 __global__ void pair_count_kernel(PairPlanArgs a) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -649,7 +749,7 @@ __global__ void __launch_bounds__(1024) pair_scan_kernel(PairPlanArgs a) {
         if (l < a.list_hi) {
             const int c = a.cnt[l];
             va = c;
-            vb = (long long)((c + 1) >> 1) * (long long)((a.list_len[l] + 31) >> 5);
+            vb = (long long)((c + a.gsz - 1) / a.gsz) * (long long)((a.list_len[l] + 31) >> 5);
         }
         long long ia = va, ib = vb;
 #pragma unroll
@@ -692,7 +792,7 @@ __global__ void __launch_bounds__(1024) pair_scan_kernel(PairPlanArgs a) {
         long long va = 0;
         if (l < a.list_hi) {
             const long long nb = (a.list_len[l] + 31) >> 5;
-            va = (long long)((a.cnt[l] + 1) >> 1) * ((nb + segb - 1) / segb);
+            va = (long long)((a.cnt[l] + a.gsz - 1) / a.gsz) * ((nb + segb - 1) / segb);
         }
         long long ia = va;
 #pragma unroll
@@ -718,7 +818,7 @@ __global__ void __launch_bounds__(1024) pair_scan_kernel(PairPlanArgs a) {
 __global__ void pair_units_kernel(PairPlanArgs a) {
     const long long l = a.list_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= a.list_hi) return;
-    const int items = (a.cnt[l] + 1) >> 1;
+    const int items = (a.cnt[l] + a.gsz - 1) / a.gsz;
     if (items == 0) return;
     const long long segb = a.work->per, nb = (a.list_len[l] + 31) >> 5;
     const int nsegs = (int)((nb + segb - 1) / segb);
@@ -737,7 +837,8 @@ __global__ void pair_fill_kernel(PairPlanArgs a) {
     }
 }
 
-int dph_launch_plan(dph_index* ix, int64_t n, int k, int keep, int grid, const int32_t* only_flagged, cudaStream_t st, bool pair) {
+int dph_launch_plan(dph_index* ix, int64_t n, int k, int keep, int grid, const int32_t* only_flagged, cudaStream_t st, int group) {
+    const bool pair = group > 1;
     (void)k;
     if (n == 0) return 0;
     PlanArgs a;
@@ -753,6 +854,7 @@ int dph_launch_plan(dph_index* ix, int64_t n, int k, int keep, int grid, const i
         p.list_hi = ix->list_hi; p.nlist = ix->nlist; p.grid = grid; p.cnt = ix->pl_cnt.as<int>(); p.fill = ix->pl_fill.as<int>();
         p.off = ix->pl_off.as<int>(); p.blockpre = ix->pl_blockpre.as<long long>(); p.entries = ix->pl_entries.as<unsigned>();
         p.work = ix->pairwork.as<DphPairWork>(); p.unitpre = ix->pl_unitpre.as<int>(); p.units = ix->pl_units.as<unsigned long long>();
+        p.gsz = group;
         DPH_CUDA(cudaMemsetAsync(p.cnt, 0, (size_t)ix->nlist * 4, st));
         DPH_CUDA(cudaMemsetAsync(p.fill, 0, (size_t)ix->nlist * 4, st));
         const unsigned nb = (unsigned)((p.nq_probes + 255) / 256);

@@ -315,14 +315,15 @@ __device__ __forceinline__ void compact_buffer(unsigned long long* cb, int* cnt,
     const int tid = threadIdx.x;
     const int n = *cnt;
     unsigned long long pivot = block_radix_select([&](int i) { return cb[i]; }, n, keep, sc);
-    unsigned long long mine[CAP / NT];
+    constexpr int PER = (CAP + NT - 1) / NT;
+    unsigned long long mine[PER];
 #pragma unroll
-    for (int e = 0; e < CAP / NT; e++) { int i = tid + e * NT; mine[e] = (i < n) ? cb[i] : 0ull; }
+    for (int e = 0; e < PER; e++) { int i = tid + e * NT; mine[e] = (i < n) ? cb[i] : 0ull; }
     __syncthreads();
     if (tid == 0) *cnt = 0;
     __syncthreads();
 #pragma unroll
-    for (int e = 0; e < CAP / NT; e++)
+    for (int e = 0; e < PER; e++)
         if (mine[e] >= pivot && mine[e] != 0ull) { int p = atomicAdd(cnt, 1); cb[p] = mine[e]; }
     if (tid == 0) {
         unsigned t = (unsigned)(pivot >> 32);
@@ -468,6 +469,210 @@ __global__ void __launch_bounds__(NT, 1) scan_pair_kernel(PairScanArgs a) {
     }
 }
 
+
+// =================================================================================================
+// QUAD mode: FOUR queries that probe the same list share every gather.  Their LUTs are quantised to 8-bit integers
+// (plan: lutq_kernel<unsigned char, 255>) and packed into one 32-bit word (query i in byte i), so one PRMT + LDS serves
+// four (query, code byte) lookups -- the shared-memory gather pipe, which bounds the pair kernel, does half the work per
+// lookup.  The byte lanes would overflow after two additions, so the running sums are kept as TWO 32-bit registers:
+//     sraw  = sum of the gathered words, plain 32-bit wrap-around arithmetic
+//           = S0 + 2^8 S1 + 2^16 S2 + 2^24 S3   (mod 2^32),        S_i = sum of query i's entries  (<= 96 * 255 < 2^15)
+//     accb  = sum of PRMT(word -> [b1, 0, b3, 0]) = S1 + 2^16 S3     (exact: both lanes stay below 2^16)
+// and decoded once per vector:  sraw - (accb << 8) = S0 + 2^16 S2 (exact, < 2^32).
+// The integer sums are exact; the only error is the quantisation (<= 0.5 step per entry), which the plan folds into eps, so the
+// same proof + exact canonical re-scoring applies (merge_kernel).  Work items are (list segment, group of <= 4 probing queries).
+// =================================================================================================
+#define QCAP 768
+struct QuadShared {
+    unsigned long long cbuf[4][QCAP];
+    SelectScratch sc;
+    int cnt[4]; unsigned thr[4]; int base[4]; int ndone; int ndone_snap; int unit; int full;
+};
+template <int T0> __device__ __forceinline__ void quad_word(unsigned wv, unsigned y, unsigned (&sr)[4], unsigned (&ab)[4]) {
+    constexpr int TB = DPH_DYN_SMEM_BASE + (T0 >> 5) * 65536 + (T0 & 31) * 4;
+    constexpr int A = (T0 >> 2) & 1;                  // two accumulator sets, alternating per code word
+    const unsigned w0 = lds_imm_u32<TB + 0>(__byte_perm(wv, y, 0x7504));
+    const unsigned w1 = lds_imm_u32<TB + 4>(__byte_perm(wv, y, 0x7514));
+    const unsigned w2 = lds_imm_u32<TB + 8>(__byte_perm(wv, y, 0x7524));
+    const unsigned w3 = lds_imm_u32<TB + 12>(__byte_perm(wv, y, 0x7534));
+    // 8-bit entries: the odd bytes are widened per gather (a lane-wise add of two words could carry).  A 7-bit variant that widens
+    // once per TWO gathers is 11 % faster (ncu r2d: the INT pipe -- PRMT, IADD3 at half rate -- bounds this kernel) but doubles eps,
+    // and then the exactness proof fails for ~10 % of the queries at C2 (measured); the exact fallback costs far more than it saves.
+    sr[2 * A] += w0 + w1;
+    sr[2 * A + 1] += w2 + w3;
+    ab[2 * A] += __byte_perm(w0, 0u, 0x4341) + __byte_perm(w1, 0u, 0x4341);
+    ab[2 * A + 1] += __byte_perm(w2, 0u, 0x4341) + __byte_perm(w3, 0u, 0x4341);
+}
+template <int C> __device__ __forceinline__ void quad_chunk(const uint4& v, unsigned y, unsigned (&sr)[4], unsigned (&ab)[4]) {
+    quad_word<C * 16 + 0>(v.x, y, sr, ab);
+    quad_word<C * 16 + 4>(v.y, y, sr, ab);
+    quad_word<C * 16 + 8>(v.z, y, sr, ab);
+    quad_word<C * 16 + 12>(v.w, y, sr, ab);
+}
+// append with an overflow latch: the round loop polls ONE flag instead of every buffer's counter
+__device__ __forceinline__ void warp_append_latch(bool pass, unsigned long long key, unsigned long long* cb, int* cnt, int* full, int lane) {
+    const unsigned pm = __ballot_sync(0xffffffffu, pass);
+    if (pm) {
+        int basep = 0;
+        const int np = __popc(pm);
+        if (lane == 0) { basep = atomicAdd(cnt, np); if (basep + np > QCAP - NT) *((volatile int*)full) = 1; }
+        basep = __shfl_sync(0xffffffffu, basep, 0);
+        if (pass) { int p = basep + __popc(pm & ((1u << lane) - 1u)); if (p < QCAP) cb[p] = key; }
+    }
+}
+
+__global__ void __launch_bounds__(NT, 1) scan_quad_kernel(PairScanArgs a) {
+    unsigned char* const smem = dph_smem;
+    QuadShared* sh = reinterpret_cast<QuadShared*>(smem + SMEM_LUT_FAST);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int total_units = a.work->total_units;
+    const unsigned segb = (unsigned)a.work->per;
+    const unsigned ywin = (((unsigned)__cvta_generic_to_shared(dph_smem)) & 0xFF000000u) | ((unsigned)lane * 4u);
+    const unsigned char* lut8 = reinterpret_cast<const unsigned char*>(a.lutq);
+
+    while (true) {
+        if (tid == 0) sh->unit = atomicAdd(a.next_unit, 1);
+        __syncthreads();
+        const int u = sh->unit;
+        if (u >= total_units) break;
+        const unsigned long long ud = a.units[u];
+        const long long l = (long long)(ud & 0xFFFFFFFFull);
+        const int it = (int)((ud >> 32) & 0xFFFFull);
+        const int len = a.list_len[l];
+        const unsigned nb = (unsigned)((len + 31) >> 5);
+        const unsigned bi0 = (unsigned)(ud >> 48) * segb;
+        const unsigned bend = (nb - bi0 < segb) ? nb : bi0 + segb;
+        const int e0 = a.pl_off[l] + 4 * it;
+        const int nq = min(4, a.pl_cnt[l] - 4 * it);          // queries in this group (1..4)
+        long long qv[4]; int rv[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const unsigned e = a.entries[e0 + (i < nq ? i : 0)];
+            qv[i] = e >> 10; rv[i] = (int)(e & 1023u);
+        }
+        __syncthreads();
+        {   // ---- packed LUT: byte i of every word = query i's 8-bit entry, same [3][256][64] scan layout ----
+            const unsigned* T0p = reinterpret_cast<const unsigned*>(lut8 + (size_t)qv[0] * DPH_LUT_SCAN_FLOATS);
+            const unsigned* T1p = reinterpret_cast<const unsigned*>(lut8 + (size_t)qv[1] * DPH_LUT_SCAN_FLOATS);
+            const unsigned* T2p = reinterpret_cast<const unsigned*>(lut8 + (size_t)qv[2] * DPH_LUT_SCAN_FLOATS);
+            const unsigned* T3p = reinterpret_cast<const unsigned*>(lut8 + (size_t)qv[3] * DPH_LUT_SCAN_FLOATS);
+            uint4* dst = reinterpret_cast<uint4*>(smem);
+#pragma unroll 4
+            for (int i = tid; i < DPH_LUT_SCAN_FLOATS / 4; i += NT) {
+                const unsigned va = __ldg(T0p + i);
+                const unsigned vb = nq > 1 ? __ldg(T1p + i) : 0u;
+                const unsigned vc = nq > 2 ? __ldg(T2p + i) : 0u;
+                const unsigned vd = nq > 3 ? __ldg(T3p + i) : 0u;
+                const unsigned t0 = __byte_perm(va, vb, 0x5140), t1 = __byte_perm(va, vb, 0x7362);     // [a0 b0 a1 b1], [a2 b2 a3 b3]
+                const unsigned u0 = __byte_perm(vc, vd, 0x5140), u1 = __byte_perm(vc, vd, 0x7362);
+                uint4 o;
+                o.x = __byte_perm(t0, u0, 0x5410); o.y = __byte_perm(t0, u0, 0x7632);
+                o.z = __byte_perm(t1, u1, 0x5410); o.w = __byte_perm(t1, u1, 0x7632);
+                dst[i] = o;
+            }
+        }
+        if (tid == 0) {
+            sh->ndone = 0; sh->ndone_snap = 0; sh->full = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) { sh->cnt[i] = 0; sh->thr[i] = i < nq ? *((volatile unsigned*)(a.gthr + qv[i])) : 0xFFFFFFFFu; }
+        }
+        __syncthreads();
+        float stepv[4], basev[4]; unsigned gsv[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float2 pp = a.qparams[qv[i]];
+            stepv[i] = pp.x; basev[i] = a.cd[qv[i] * a.nprobe + rv[i]] + pp.y; gsv[i] = a.gdense[qv[i] * a.nprobe + rv[i]];
+        }
+        const uint4* lbase = reinterpret_cast<const uint4*>(a.codes + a.blk_off[l] * DPH_BLK_BYTES);
+        unsigned thr0 = sh->thr[0], thr1 = sh->thr[1], thr2 = sh->thr[2], thr3 = sh->thr[3];     // refreshed after every barrier
+        // float images of the thresholds (0xFFFFFFFF = "never passes" for the empty slots of a short group -> +inf)
+        auto thr_f = [](unsigned t) { return t == 0xFFFFFFFFu ? __int_as_float(0x7f800000) : (t == 0u ? -__int_as_float(0x7f800000) : dph_fkey_inv(t)); };
+        float tf0 = thr_f(thr0), tf1 = thr_f(thr1), tf2 = thr_f(thr2), tf3 = thr_f(thr3);
+
+        unsigned b = bi0 + warp, bp = bi0 + warp;
+        uint4 nxt[6];
+#pragma unroll 1
+        for (int r = 0; r < DPH_L2_PREFETCH_ROUNDS && bp < bend; r++, bp += NW)
+            if (lane == 0) l2_prefetch_block(lbase + (size_t)bp * (DPH_BLK_BYTES / 16));
+        bool more = b < bend;
+        if (more) {
+            const uint4* p = lbase + (size_t)b * (DPH_BLK_BYTES / 16) + lane;
+#pragma unroll
+            for (int c6 = 0; c6 < 6; c6++) nxt[c6] = ldg_stream(p + c6 * 32);
+        }
+        bool counted = false;
+        while (true) {
+            while (more) {
+                if (*((volatile int*)&sh->full)) break;
+                uint4 cur[6];
+#pragma unroll
+                for (int c6 = 0; c6 < 6; c6++) cur[c6] = nxt[c6];
+                const unsigned bcur = b;
+                if (bp < bend) { if (lane == 0) l2_prefetch_block(lbase + (size_t)bp * (DPH_BLK_BYTES / 16)); bp += NW; }
+                b += NW;
+                more = b < bend;
+                if (more) {
+                    const uint4* p = lbase + (size_t)b * (DPH_BLK_BYTES / 16) + lane;
+#pragma unroll
+                    for (int c6 = 0; c6 < 6; c6++) nxt[c6] = ldg_stream(p + c6 * 32);
+                }
+                unsigned sr[4] = {0u, 0u, 0u, 0u}, ab[4] = {0u, 0u, 0u, 0u};
+                quad_chunk<0>(cur[0], ywin, sr, ab);
+                quad_chunk<1>(cur[1], ywin, sr, ab);
+                quad_chunk<2>(cur[2], ywin, sr, ab);
+                quad_chunk<3>(cur[3], ywin, sr, ab);
+                quad_chunk<4>(cur[4], ywin, sr, ab);
+                quad_chunk<5>(cur[5], ywin, sr, ab);
+                const unsigned SR = (sr[0] + sr[1]) + (sr[2] + sr[3]);
+                const unsigned AB = (ab[0] + ab[1]) + (ab[2] + ab[3]);          // S1 | S3 << 16
+                const unsigned AE = SR - (AB << 8);                             // S0 | S2 << 16
+                const unsigned j = bcur * 32u + lane;
+                const bool valid = (int)j < len;
+                // thresholds are compared in the float domain (one FSETP per query); the order-preserving integer key is built only for
+                // the rare vector that passes.  (float)(unsigned short) converts a 16-bit half of the register without a mask / shift.
+                const float f0 = fmaf(stepv[0], (float)(unsigned short)(AE), basev[0]);
+                const float f1 = fmaf(stepv[1], (float)(unsigned short)(AB), basev[1]);
+                const float f2 = fmaf(stepv[2], (float)(unsigned short)(AE >> 16), basev[2]);
+                const float f3 = fmaf(stepv[3], (float)(unsigned short)(AB >> 16), basev[3]);
+                const bool p0 = valid && f0 >= tf0, p1 = valid && f1 >= tf1, p2 = valid && f2 >= tf2, p3 = valid && f3 >= tf3;
+                if (__any_sync(0xffffffffu, p0 || p1 || p2 || p3)) {
+                    const unsigned k0 = dph_fkey(f0), k1 = dph_fkey(f1), k2 = dph_fkey(f2), k3 = dph_fkey(f3);
+                    warp_append_latch(p0 && k0 >= thr0, ((unsigned long long)k0 << 32) | (unsigned long long)(0xFFFFFFFFu - (gsv[0] + j)), sh->cbuf[0], &sh->cnt[0], &sh->full, lane);
+                    warp_append_latch(p1 && k1 >= thr1, ((unsigned long long)k1 << 32) | (unsigned long long)(0xFFFFFFFFu - (gsv[1] + j)), sh->cbuf[1], &sh->cnt[1], &sh->full, lane);
+                    warp_append_latch(p2 && k2 >= thr2, ((unsigned long long)k2 << 32) | (unsigned long long)(0xFFFFFFFFu - (gsv[2] + j)), sh->cbuf[2], &sh->cnt[2], &sh->full, lane);
+                    warp_append_latch(p3 && k3 >= thr3, ((unsigned long long)k3 << 32) | (unsigned long long)(0xFFFFFFFFu - (gsv[3] + j)), sh->cbuf[3], &sh->cnt[3], &sh->full, lane);
+                }
+            }
+            if (!more && !counted) { counted = true; if (lane == 0) atomicAdd(&sh->ndone, 1); }
+            __syncthreads();
+#pragma unroll 1
+            for (int i = 0; i < nq; i++)
+                if (sh->cnt[i] > a.keep) compact_buffer<QCAP>(sh->cbuf[i], &sh->cnt[i], &sh->thr[i], a.keep, a.gthr + qv[i], &sh->sc);
+            if (tid == 0) {
+                for (int i = 0; i < nq; i++) { unsigned g = *((volatile unsigned*)(a.gthr + qv[i])); if (g > sh->thr[i]) sh->thr[i] = g; }
+                sh->ndone_snap = sh->ndone;
+                sh->full = 0;
+            }
+            __syncthreads();
+            thr0 = sh->thr[0]; thr1 = sh->thr[1]; thr2 = sh->thr[2]; thr3 = sh->thr[3];
+            tf0 = thr_f(thr0); tf1 = thr_f(thr1); tf2 = thr_f(thr2); tf3 = thr_f(thr3);
+            if (sh->ndone_snap == NW) break;
+        }
+        // ---- publish the candidate sets ----
+#pragma unroll 1
+        for (int i = 0; i < nq; i++) {
+            const long long q = qv[i];
+            const int cnt = sh->cnt[i];
+            if (tid == 0) sh->base[i] = atomicAdd(a.cand_cnt + q, cnt);
+            __syncthreads();
+            const long long off = a.cand_off[q], cap = a.cand_off[q + 1] - off;
+            const int basep = sh->base[i];
+            for (int c = tid; c < cnt; c += NT)
+                if (basep + c < cap) a.cand[off + basep + c] = sh->cbuf[i][c];
+        }
+    }
+}
+
 __global__ void smem_base_probe_kernel(unsigned* out) { *out = (unsigned)__cvta_generic_to_shared(dph_smem) & 0x00FFFFFFu; }
 
 int dph_scan_setup_attrs() {
@@ -484,6 +689,7 @@ int dph_scan_setup_attrs() {
     DPH_CUDA(cudaFuncSetAttribute(scan_kernel<DPH_SCAN_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LUT_FAST + (int)sizeof(ScanShared)));
     DPH_CUDA(cudaFuncSetAttribute(scan_kernel<DPH_SCAN_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LUT_EXACT + (int)sizeof(ScanShared)));
     DPH_CUDA(cudaFuncSetAttribute(scan_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LUT_FAST + (int)sizeof(PairShared)));
+    DPH_CUDA(cudaFuncSetAttribute(scan_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LUT_FAST + (int)sizeof(QuadShared)));
     return 0;
 }
 
@@ -504,7 +710,7 @@ int dph_launch_scan(dph_index* ix, int64_t n, int k, int keep, int mode, int gri
     return 0;
 }
 
-int dph_launch_scan_pair(dph_index* ix, int64_t n, int keep, int grid, cudaStream_t st) {
+int dph_launch_scan_pair(dph_index* ix, int64_t n, int keep, int grid, cudaStream_t st, int group) {
     if (n == 0) return 0;
     DPH_TRY(dph_scan_setup_attrs());
     PairScanArgs a;
@@ -514,7 +720,8 @@ int dph_launch_scan_pair(dph_index* ix, int64_t n, int keep, int grid, cudaStrea
     a.cd = ix->cd.as<float>(); a.gdense = ix->gdense.as<unsigned>(); a.gthr = ix->gthr.as<unsigned>();
     a.cand = ix->cand.as<unsigned long long>(); a.cand_off = ix->cand_off.as<long long>(); a.cand_cnt = ix->cand_cnt.as<int>();
     a.list_lo = ix->list_lo; a.list_hi = ix->list_hi; a.nprobe = ix->nprobe; a.keep = keep;
-    scan_pair_kernel<<<grid, NT, SMEM_LUT_FAST + sizeof(PairShared), st>>>(a);
+    if (group == 4) scan_quad_kernel<<<grid, NT, SMEM_LUT_FAST + sizeof(QuadShared), st>>>(a);
+    else scan_pair_kernel<<<grid, NT, SMEM_LUT_FAST + sizeof(PairShared), st>>>(a);
     DPH_CUDA(cudaGetLastError());
     return 0;
 }
@@ -576,16 +783,30 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeArgs a) {
     int ns = scnt < DPH_SURV_CAP ? scnt : DPH_SURV_CAP;
     if (sflag) flag = 1;
     if (a.mode == DPH_SCAN_FAST) {
+        // exact re-scoring, one WARP per survivor: lane l fetches the code byte and the LUT entry of sub-quantizers l, l+32, l+64
+        // (96 independent loads in flight instead of a 96-long chain of dependent L2 round trips), then the lanes' values are added
+        // in canonical m-ascending order (bit-exact with the oracle: dis = dis0; for m: dis += LUT[m][c[m]]).
         const float* lutc = a.lut_canon + (size_t)q * DPH_LUT_CANON_FLOATS;
-        for (int i = tid; i < ns; i += blockDim.x) {
+        const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+        for (int i = warp; i < ns; i += nwarps) {
             const unsigned gidx = dph_ckey_gidx(surv[i]);
             const DphSeg s = segs[find_seg(segs, nsg, gidx)];
             const unsigned j = gidx - s.gstart;
             const uint8_t* blk = a.codes + (s.blk + (long long)(j >> 5)) * DPH_BLK_BYTES;
             const int ln = (int)(j & 31u);
+            float v[3];
+#pragma unroll
+            for (int h = 0; h < 3; h++) {
+                const int m = h * 32 + lane;
+                v[h] = __ldg(lutc + m * 256 + blk[dph_blk_addr(ln, m)]);
+            }
             float dis = s.dis0;
-            for (int m = 0; m < DPH_M; m++) dis += __ldg(lutc + m * 256 + blk[dph_blk_addr(ln, m)]);   // canonical order
-            surv[i] = dph_ckey(dis, gidx);
+#pragma unroll
+            for (int h = 0; h < 3; h++)
+#pragma unroll
+                for (int l2 = 0; l2 < 32; l2++) dis += __shfl_sync(0xffffffffu, v[h], l2);
+            __syncwarp();
+            if (lane == 0) surv[i] = dph_ckey(dis, gidx);
         }
     }
     const int p2 = dph_next_pow2(ns > 1 ? ns : 1);

@@ -75,3 +75,23 @@ typedef CUresult (*dph_PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
 int dph_tensormap_encoder(dph_PFN_encodeTiled* out);      // gemm_tf32.cu
 // [rows, cols] fp32 row-major (row stride ld floats) -> map with a [32 floats x box_rows] box, 128-byte swizzle, zero fill out of bounds
 int dph_make_map_f32(CUtensorMap* map, const float* ptr, long long rows, long long cols, long long ld, int box_rows);
+
+// ---- bf16 operands (gemm_bf16x3.cu) ----
+__device__ __forceinline__ void umma_bf16(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, SWIZZLE_64B operand tile: rows of 64 bytes (32 bf16), 8-row groups 512 bytes apart.
+__device__ __forceinline__ unsigned long long make_sw64_desc(unsigned smem_addr) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((smem_addr & 0x3FFFF) >> 4);        // start address, bits [0,14)
+    d |= (unsigned long long)1 << 16;                            // leading byte offset (ignored for swizzled K-major), bits [16,30)
+    d |= (unsigned long long)(512 >> 4) << 32;                   // stride byte offset, bits [32,46)
+    d |= (unsigned long long)1 << 46;                            // descriptor version (Blackwell)
+    d |= (unsigned long long)4 << 61;                            // layout type SWIZZLE_64B
+    return d;
+}
+// [rows, cols] bf16 row-major (row stride ld elements) -> map with a [32 bf16 x box_rows] box, 64-byte swizzle, zero fill out of bounds
+int dph_make_map_bf16(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows);

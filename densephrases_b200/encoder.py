@@ -67,11 +67,12 @@ class Encoder(object):
         if h and L is not None and L._lib is not None:
             L._lib.dph_encoder_free(h)
 
-    MODES = {'tf32': 0, '3xtf32': 1}      # name -> dph_encoder_set_precision argument
+    MODES = {'tf32': 0, '3xtf32': 1, 'bf16x3': 2}      # name -> dph_encoder_set_precision argument
 
     def set_precision(self, precise):
         """'tf32' / False (default): 1xTF32 GEMMs (== torch 1.9's default for fp32 matmuls on Ampere+);
-        '3xtf32' / True: 3xTF32 split, fp32-accurate (meets the 1e-3 tolerance of the north star)."""
+        '3xtf32' / True: 3xTF32 split, fp32-accurate; 'bf16x3': bf16 (hi, lo) planes, three bf16 MMAs per product -- both meet
+        the 1e-3 tolerance of the north star, bf16x3 at the speed of 'tf32'."""
         mode = precise if isinstance(precise, str) else ('3xtf32' if precise else 'tf32')
         if mode not in self.MODES:
             raise ValueError(f'unknown precision mode {mode!r}; choose one of {sorted(self.MODES)}')

@@ -105,6 +105,10 @@ class IvfPqIndex:
     def last_used_pair_mode(self):
         return bool(L.lib().dph_index_last_used_pair_mode(self._h))
 
+    def last_group_size(self):
+        """Queries per shared-memory gather in the last search: 1 (fp32 LUT), 2 (pair-packed) or 4 (quad-packed)."""
+        return int(L.lib().dph_index_last_group_size(self._h))
+
     def set_coarse_tc(self, on):
         L.check(L.lib().dph_index_set_coarse_tc(self._h, int(bool(on))))
 

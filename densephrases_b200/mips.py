@@ -19,6 +19,7 @@ On-disk artefacts: `MIPS(...)` takes the reference's paths.  It prefers this rep
 readers of densephrases_b200/artifacts.py (no faiss / h5py / blosc; see that module's STATUS note).
 `MIPS.from_components` wraps in-memory objects.
 """
+import json
 import logging
 import os
 import pickle
@@ -79,30 +80,60 @@ class _PackedDocs(object):
         return ok & (span >= 0) & (span <= max_len)
 
 
+def distributed_context():
+    """(rank, world, local_rank) of a one-process-per-GPU job (torchrun exports RANK / WORLD_SIZE / LOCAL_RANK); the NCCL process
+    group is created on first use so that the reference's drivers, which know nothing about ranks, can simply be launched with
+    `python -m torch.distributed.run --nproc-per-node N eval_phrase_retrieval.py ...` (all ranks enter search together)."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world <= 1:
+        return 0, 1, torch.cuda.current_device() if torch.cuda.is_available() else 0
+    import torch.distributed as dist
+    rank, local_rank = int(os.environ.get('RANK', '0')), int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    if not dist.is_initialized():
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    return rank, world, local_rank
+
+
 class MIPS(object):
     def __init__(self, phrase_dump_dir, index_path, idx2id_path, cuda=False, logging_level=logging.INFO):
-        from .ivfpq import IvfPqIndex
-        from . import artifacts
-        container = os.path.join(os.path.dirname(index_path), 'index.dph.npz')
-        if os.path.exists(container):
-            logger.info(f'Reading {container}')
-            z = np.load(container)
-            parts = {k: z[k] for k in z.files}
-        elif os.path.exists(index_path):
-            logger.info(f'Reading {index_path} (FAISS container, parsed natively)')
-            parts = artifacts.read_faiss_index(index_path, ondisk_same_dir=True)          # faiss.IO_FLAG_ONDISK_SAME_DIR, index.py:30
-            if not parts['by_residual'] or parts['metric'] != 0 or parts['quantizer_metric'] != 0:
-                raise RuntimeError('only the inner-product, by-residual IVF-PQ index of build_phrase_index.py:113-116 is supported')
+        from .sharded import ShardedIvfPq
+        from . import artifacts, synthetic_dump
+        rank, world, dev = distributed_context()
+        index_dir = os.path.dirname(index_path)
+        container, spec = os.path.join(index_dir, 'index.dph.npz'), os.path.join(index_dir, 'index.dph.json')
+        if os.path.exists(spec):                                         # synthetic index generated on the GPU(s) (synthetic_dump.py)
+            sp = json.load(open(spec))['synthetic_index']
+            logger.info(f'Generating the synthetic index of {spec}: {sp}')
+            rng = np.random.default_rng(sp['opq_seed'])
+            A = np.linalg.qr(rng.standard_normal((768, 768)))[0].astype(np.float32)
+            index = ShardedIvfPq(sp['nlist'], rank=rank, world=world, device=dev)
+            index.build_synthetic(A, synthetic_dump.uniform_list_lengths(sp['N'], sp['nlist']), sp['seed'])
         else:
-            raise RuntimeError(f'neither {container} nor {index_path} found')
-        index = IvfPqIndex.from_arrays(parts['A'], parts['centroids'], parts['pq'], parts['list_len'], parts['codes'], parts.get('ids'))
+            if os.path.exists(container):
+                logger.info(f'Reading {container}')
+                z = np.load(container)
+                parts = {k: z[k] for k in z.files}
+            elif os.path.exists(index_path):
+                logger.info(f'Reading {index_path} (FAISS container, parsed natively)')
+                parts = artifacts.read_faiss_index(index_path, ondisk_same_dir=True)      # faiss.IO_FLAG_ONDISK_SAME_DIR, index.py:30
+                if not parts['by_residual'] or parts['metric'] != 0 or parts['quantizer_metric'] != 0:
+                    raise RuntimeError('only the inner-product, by-residual IVF-PQ index of build_phrase_index.py:113-116 is supported')
+            else:
+                raise RuntimeError(f'neither {container}, {spec} nor {index_path} found')
+            index = ShardedIvfPq.from_arrays(parts['A'], parts['centroids'], parts['pq'], parts['list_len'], parts['codes'], parts.get('ids'),
+                                             rank=rank, world=world, device=dev)
         dump_root = phrase_dump_dir[:phrase_dump_dir.index('/phrase')] if '/phrase' in phrase_dump_dir else phrase_dump_dir
         doc_groups = None
         if 'PQ' in index_path:                                          # in-RAM metadata only with PQ indexes (index.py:69-74)
-            for name in ('meta_dph.pkl', 'meta_compressed.pkl'):
-                if os.path.exists(os.path.join(dump_root, name)):
-                    doc_groups = artifacts.read_meta(os.path.join(dump_root, name))
-                    break
+            if os.path.exists(os.path.join(dump_root, 'meta_dph.json')):
+                sp = json.load(open(os.path.join(dump_root, 'meta_dph.json')))['synthetic_meta']
+                doc_groups = synthetic_dump.LazyDocs(sp['tokens_per_doc'], sp['seed'])
+            else:
+                for name in ('meta_dph.pkl', 'meta_compressed.pkl'):
+                    if os.path.exists(os.path.join(dump_root, name)):
+                        doc_groups = artifacts.read_meta(os.path.join(dump_root, name))
+                        break
         self.phrase_dump_dir = phrase_dump_dir
         self._attach(index, self.load_idx_f(idx2id_path), doc_groups, index_path, cuda, logging_level)
 
@@ -129,6 +160,7 @@ class MIPS(object):
         self.R = torch.from_numpy(np.ascontiguousarray(index.opq_matrix(), dtype=np.float32)).to(self.device)   # index.py:32,57
         self.index.nprobe = 256                                        # fixed at load time in the reference (index.py:53,62)
         self.num_docs_list = []
+        self.stage_seconds = {'mips': 0.0, 'get_idxs': 0.0, 'phrase_vectors': 0.0, 'phrase_select': 0.0, 'metadata': 0.0, 'batches': 0}
         self.sentencizer = RuleSentencizer()
         self.offset = self.scale = None
         logger.info(f'index ntotal: {self.index.ntotal} | PQ: {self.is_pq} | nprobe: {self.index.nprobe}')
@@ -138,6 +170,11 @@ class MIPS(object):
         """{offset_key: {'doc': int32[], 'word': int32[]}} like index.py:78-88; read from `idx2id.npz` (members '<offset>/<type>')
         when it exists next to idx2id_path, else from the HDF5 file itself."""
         npz = os.path.splitext(idx2id_path)[0] + '.npz'
+        spec = os.path.splitext(idx2id_path)[0] + '.dph.json'
+        if os.path.exists(spec):
+            from . import synthetic_dump
+            sp = json.load(open(spec))['synthetic_idx2id']
+            return synthetic_dump.synthetic_idx2id(sp['ntotal'], sp['tokens_per_doc'])
         if not os.path.exists(npz):
             from . import artifacts
             return artifacts.read_idx2id(idx2id_path)
@@ -190,11 +227,14 @@ class MIPS(object):
         tic = time()
         halves = np.split(query.astype(np.float32), 2, axis=1)
         scores, labels = self.index.search(np.concatenate(halves, axis=0), top_k)
+        self.stage_seconds['mips'] += time() - tic
+        self.stage_seconds['batches'] += 1
         logger.debug(f'1) {time()-tic:.3f}s: MIPS')
         tic = time()
         s_doc, s_word = self.get_idxs(labels[:B])
         e_doc, e_word = self.get_idxs(labels[B:])
         self.num_docs_list.append(sum(len(set(a.tolist()) | set(b.tolist())) for a, b in zip(s_doc, e_doc)) / B)
+        self.stage_seconds['get_idxs'] += time() - tic
         logger.debug(f'2) {time()-tic:.3f}s: get index')
         return s_doc, s_word, labels[:B], e_doc, e_word, labels[B:], scores[:B], scores[B:]
 
@@ -236,6 +276,7 @@ class MIPS(object):
             vecs, _ = self.reconst_batch(np.concatenate([fwd_labels.ravel(), bwd_labels.ravel()]))   # missing label -> zeros
             vecs = np.asarray(vecs, dtype=np.float32)
             fwd, bwd = vecs[:H * L].reshape(H, L, -1), vecs[H * L:].reshape(H, L, -1)
+        self.stage_seconds['phrase_vectors'] += time() - tic
         logger.debug(f'1) {time()-tic:.3f}s: reconstruct vecs')
 
         tic = time()
@@ -246,6 +287,7 @@ class MIPS(object):
         score_se = s_sc[:, None] + end_sc + np.where(ok_end, 0.0, _MASKED)
         pick_e = score_se.argmax(1)
         best_end = np.where(ok_end, cand_end, -1)[np.arange(H), pick_e]
+        self.stage_seconds['phrase_select'] += time() - tic
         logger.debug(f'2) {time()-tic:.3f}s: find end')
 
         tic = time()
@@ -256,6 +298,7 @@ class MIPS(object):
         score_es = start_sc + e_sc[:, None] + np.where(ok_start, 0.0, _MASKED)
         pick_s = score_es.argmax(1)
         best_start = np.where(ok_start, cand_start, -1)[np.arange(H), pick_s]
+        self.stage_seconds['phrase_select'] += time() - tic
         logger.debug(f'3) {time()-tic:.3f}s: find start')
 
         # interleave (start-anchored, end-anchored) results per hit (index.py:375-378)
@@ -287,6 +330,7 @@ class MIPS(object):
                 rec = self.adjust_sent(rec)
             results[owner[h]].append(rec)
         results = [[r for r in sorted(rs, key=lambda r: -r['score']) if r['score'] > _KEEP_ABOVE] for rs in results]
+        self.stage_seconds['metadata'] += time() - tic
         logger.debug(f'4) {time()-tic:.3f}s: get metadata')
         return results
 

@@ -109,12 +109,12 @@ def _find_vocab(args, load_dir):
 def load_encoder(device, args, phrase_only=False):
     """-> (model, tokenizer, config) from `args.load_dir/pytorch_model.bin` + a WordPiece `vocab.txt` (single_utils.py:59-118).
     A missing checkpoint or vocabulary raises FileNotFoundError like the reference does; seeded random weights and the
-    synthetic character-level vocabulary are used only when the caller opts in with `args.allow_random_init = True`
-    (tests and benchmarks: no checkpoint is reachable offline)."""
+    synthetic character-level vocabulary are used only when the caller opts in with `args.allow_random_init = True` or the
+    environment variable DPH_ALLOW_RANDOM_INIT=1 (tests and benchmarks: no checkpoint is reachable offline)."""
     if phrase_only:
         raise NotImplementedError('the phrase tower is only used offline (generate_phrase_vecs.py); out of scope')
     load_dir = getattr(args, 'load_dir', '') or ''
-    allow_random = bool(getattr(args, 'allow_random_init', False))
+    allow_random = bool(getattr(args, 'allow_random_init', False)) or os.environ.get('DPH_ALLOW_RANDOM_INIT', '') == '1'
     config = BertGeometry()
     cfg_json = os.path.join(load_dir, 'config.json')
     if os.path.exists(cfg_json):
@@ -254,6 +254,21 @@ class DensePhrases(object):
         self.args.load_dir = load_dir
         self.model, self.tokenizer, self.config = load_encoder(device, self.args)
         self.query2vec = get_query2vec(query_encoder=self.model, tokenizer=self.tokenizer, args=self.args, batch_size=64)
+
+    def evaluate(self, test_path, **kwargs):
+        """model.py:118-128: run the evaluation loop of eval_phrase_retrieval.py on `test_path` with this model's index and encoder.
+        The reference imports `evaluate` from the script on its path; when that module is importable it is used unmodified, else
+        this package's restatement of the same loop (runtime.evaluate)."""
+        import copy
+        new_args = copy.deepcopy(self.args)
+        new_args.test_path = test_path
+        new_args.truecase = True
+        new_args.__dict__.update(kwargs)
+        try:
+            from eval_phrase_retrieval import evaluate as evaluate_fn
+        except ImportError:
+            evaluate_fn = evaluate
+        return evaluate_fn(new_args, self.mips, self.model, self.tokenizer)
 
     def search(self, query='', retrieval_unit='phrase', top_k=10, truecase=True, return_meta=False):
         single = isinstance(query, str)

@@ -61,9 +61,9 @@ def sharded_search(x, k, world, group, coarse_local, search_preassigned, pack, m
 
 
 class ShardedIvfPq:
-    def __init__(self, nlist, rank=0, world=1, device=0, group=None):
+    def __init__(self, nlist, rank=0, world=1, device=0, group=None, local=None):
         self.rank, self.world, self.device, self.group = rank, world, device, group
-        self.local = IvfPqIndex(nlist, device=device)
+        self.local = local if local is not None else IvfPqIndex(nlist, device=device)      # `local`: any object with the IvfPqIndex API (tests)
         self._pinned_in = None
         self._pinned_out = None
 
@@ -78,6 +78,62 @@ class ShardedIvfPq:
             ix.set_shard(lo, hi)
         ix.set_lists_synthetic(list_len, seed)
         return self
+
+    @classmethod
+    def from_arrays(cls, A, centroids, pq, list_len, codes, ids=None, rank=0, world=1, device=0, group=None):
+        """The arrays of a faiss IndexPreTransform(OPQ) -> IndexIVFPQ file (index.py:30), list-major rows of ALL lists; this rank
+        uploads only the rows of its own list range."""
+        list_len = np.asarray(list_len, dtype=np.int64)
+        self = cls(len(list_len), rank=rank, world=world, device=device, group=group)
+        lo, hi = shard_ranges(list_len, world)[rank]
+        self.range = (lo, hi)
+        off = np.concatenate([[0], np.cumsum(list_len)])
+        ix = self.local
+        ix.set_opq(A)
+        ix.set_centroids(centroids)
+        ix.set_pq(pq)
+        if world > 1:
+            ix.set_shard(lo, hi)
+        ix.set_lists(list_len, codes[off[lo]:off[hi]], None if ids is None else ids[off[lo]:off[hi]])
+        return self
+
+    # ---- the slice of the faiss index API that MIPS uses (index.py:30-33,200,286,296) ----
+    @property
+    def ntotal(self):
+        return self.local.ntotal
+
+    @property
+    def d(self):
+        return self.local.d
+
+    @property
+    def nlist(self):
+        return self.local.nlist
+
+    def opq_matrix(self):
+        return self.local.opq_matrix()
+
+    def _sum_over_shards(self, arr, op=None):
+        """Every label lives on exactly one shard and the others return zeros: the all-reduce sum IS the gather."""
+        if self.world == 1:
+            return arr
+        import torch.distributed as dist
+        dev = torch.device("cuda", self.device) if dist.get_backend(self.group) == "nccl" else torch.device("cpu")    # gloo: CPU tests
+        t = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
+        dist.all_reduce(t, op=op or dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
+    def reconstruct_batch(self, ids):
+        """labels [m] (numpy) -> (vec [m,d] f32 rotated space, found [m] u8), collective over the shards."""
+        import torch.distributed as dist
+        vec, found = self.local.reconstruct_batch(np.ascontiguousarray(ids, dtype=np.int64))
+        if self.world == 1:
+            return vec, found
+        return self._sum_over_shards(vec), self._sum_over_shards(found.astype(np.int32), dist.ReduceOp.MAX).astype(np.uint8)
+
+    def window_scores(self, q, first_ids, L):
+        """q [m,768], first_ids [m] -> [m,L] phrase-window scores (dph_index_window_scores), collective over the shards."""
+        return self._sum_over_shards(self.local.window_scores(q, first_ids, L))
 
     @property
     def nprobe(self):

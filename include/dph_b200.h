@@ -29,10 +29,11 @@ extern "C" {
 #define DPH_MEM_DEVICE 1
 
 /* scan kernel selection (dph_index_set_scan_mode) */
-#define DPH_SCAN_FAST 0   /* default: conflict-free gather filter + proof + exact fp32 re-scoring; picks PAIR or SINGLE per batch */
+#define DPH_SCAN_FAST 0   /* default: conflict-free gather filter + proof + exact fp32 re-scoring; picks QUAD / PAIR / SINGLE per batch */
 #define DPH_SCAN_EXACT 1  /* canonical-order fp32 ADC for every code (slow; fallback + cross-check) */
 #define DPH_SCAN_PAIR 2   /* force: two queries share every gather (int16-packed quantised LUTs), lists grouped by probing queries */
 #define DPH_SCAN_SINGLE 3 /* force: one query per gather (fp32 LUT) */
+#define DPH_SCAN_QUAD 4   /* force: four queries share every gather (int8-packed quantised LUTs), lists grouped by probing queries */
 
 typedef struct dph_index dph_index;
 
@@ -112,7 +113,8 @@ const int32_t* dph_index_last_flags(const dph_index* ix);
 const int32_t* dph_index_last_probes(const dph_index* ix);
 const float* dph_index_last_coarse(const dph_index* ix);
 const float* dph_index_last_xr(const dph_index* ix);
-int dph_index_last_used_pair_mode(const dph_index* ix);
+int dph_index_last_used_pair_mode(const dph_index* ix);   /* 1 when the last search shared gathers between queries (pair or quad) */
+int dph_index_last_group_size(const dph_index* ix);       /* queries per gather of the last search: 1, 2 or 4 */
 /* Copy one of them to the host (synchronises): which = 0 flags, 1 probes, 2 coarse scores, 3 rotated queries. */
 int dph_index_copy_last(dph_index* ix, int which, void* dst_host, int64_t bytes);
 
@@ -138,7 +140,9 @@ int dph_encoder_set_stream(dph_encoder* e, void* cuda_stream);
 int64_t dph_encoder_tower_floats(const dph_encoder* e);
 int dph_encoder_load_tower(dph_encoder* e, int tower, const float* blob, int mem);
 /* 0 (default): GEMMs as one TF32 MMA per product -- what torch 1.9 (the reference's pin) does for fp32 matmuls on Ampere+;
- * 1: 3xTF32 split GEMMs, fp32-accurate (matches the reference's CPU/fp32 path to ~1e-5). */
+ * 1: 3xTF32 split GEMMs, fp32-accurate (matches the reference's CPU/fp32 path to ~1e-5);
+ * 2: bf16x3 split GEMMs (operands as (hi, lo) bf16 planes, three kind::f16 MMAs per product, ~2^-17 relative): meets the 1e-3
+ *    tolerance on the query vectors at the speed of mode 0. */
 int dph_encoder_set_precision(dph_encoder* e, int precise);
 /* 1 (default): self-attention of sequences with S <= 64 on the tensor cores (TF32 operands, fp32 accumulation and softmax) unless
  * precise is set; 0: always the fp32 SIMT attention kernels. */
@@ -159,7 +163,8 @@ int dph_sgemm_nt_seq(const float* X, int64_t n, const float* W, int64_t m, int64
  * out [M,N] = act(A [M,K] . W [N,K]^T + bias [N]) + residual [M,N]; act: 0 none, 1 erf-GELU; device pointers;
  * N % 128 == 0, K % 32 == 0.  == torch.nn.functional.linear (HF BertSelfAttention/BertOutput/BertIntermediate). */
 int dph_gemm_tf32_nt(const float* A, const float* W, const float* bias, const float* residual, float* out, int64_t M, int64_t N,
-                     int64_t K, int act, int precise /* 0: 1xTF32, 1: 3xTF32 split (fp32-accurate) */, void* cuda_stream);
+                     int64_t K, int act, int precise /* 0: 1xTF32, 1: 3xTF32 split (fp32-accurate), 2: bf16x3 split (N % 256 == 0) */,
+                     void* cuda_stream);
 /* Scheduling of the 1xTF32 GEMMs (process-wide; every mode issues the same MMAs in the same order -> bit-identical results):
  * 0: one 128x128 tile per CTA, two CTAs per SM;  1: the same as 2-CTA thread-block clusters sharing the A tile through TMA
  * multicast (N/128 even);  2 (default): persistent CTAs walking 128x256 tiles with double-buffered TMEM accumulators and twelve

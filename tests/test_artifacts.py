@@ -115,8 +115,8 @@ def test_hdf5_round_trip_and_superblock(tmp_path):
 
 def test_mips_loads_the_reference_file_layout(tmp_path, monkeypatch):
     """MIPS(phrase_dump_dir, index_path, idx2id_path) over index.faiss (merged, on-disk lists) + idx2id.hdf5 + meta_compressed.pkl,
-    with the device index replaced by a recorder (CPU test): the arrays handed to IvfPqIndex.from_arrays are the file's."""
-    from densephrases_b200 import ivfpq, mips
+    with the device index replaced by a recorder (CPU test): the arrays handed to ShardedIvfPq.from_arrays (world size 1 = one IvfPqIndex) are the file's."""
+    from densephrases_b200 import mips, sharded
     from densephrases_b200.synthetic import make_corpus, make_phrase_index_arrays
     rng = np.random.default_rng(4)
     doc_groups, idx_f, ntotal = make_corpus(6, 1)
@@ -148,7 +148,7 @@ def test_mips_loads_the_reference_file_layout(tmp_path, monkeypatch):
 
         reconstruct_batch = None
 
-    monkeypatch.setattr(ivfpq.IvfPqIndex, "from_arrays", staticmethod(lambda *a: Recorder(*a)))
+    monkeypatch.setattr(sharded.ShardedIvfPq, "from_arrays", staticmethod(lambda *a, **kw: Recorder(*a)))
     m = mips.MIPS(str(dump / "phrase"), index_path, str(dump / "start" / "8_flat_OPQ96" / "idx2id.hdf5"), cuda=False)
     for got, want in zip(m.index.arrays, (ix["A"], ix["centroids"], ix["pq"], list_len, codes, ids)):
         assert np.array_equal(got, want)
@@ -157,3 +157,61 @@ def test_mips_loads_the_reference_file_layout(tmp_path, monkeypatch):
     meta = m.decompress_meta(k0)
     assert meta["context"] == doc_groups[k0]["context"] and np.array_equal(meta["f2o_start"], doc_groups[k0]["f2o_start"])
     assert np.allclose(m.R.numpy(), ix["A"])
+
+
+# ---- cross-checks against the real libraries: run automatically wherever faiss / h5py / blosc can be imported (none of them exists in
+# ---- the build container or on the GPU box, so they are skipped there; DESIGN.md keeps the readers marked "unverified" until one runs)
+def test_faiss_reader_and_search_oracle_against_real_faiss(tmp_path):
+    """A tiny IndexPreTransform(OPQMatrix, IndexIVFPQ(IndexFlatIP)) built and written by faiss itself (build_phrase_index.py:113-116,
+    142): (1) artifacts.read_faiss_index parses the file faiss wrote, (2) the CPU oracle (oracle/ivfpq_ref.c) reproduces faiss'
+    own search results on it -- the check that would lift 'parity unpinned' (labels equal, scores within 1e-3)."""
+    faiss = pytest.importorskip("faiss")
+    if "IndexIVFPQ" not in vars(faiss):
+        pytest.skip("only this repo's importable `faiss` stub is present (eval_phrase_retrieval.py:12 imports the name), not the library")
+    from oracle import ivfpq_ref as R
+    rng = np.random.default_rng(0)
+    d, nlist, n = 768, 8, 4000
+    xb = rng.standard_normal((n, d)).astype(np.float32)
+    quantizer = faiss.IndexFlatIP(d)
+    sub = faiss.IndexIVFPQ(quantizer, d, nlist, 96, 8, faiss.METRIC_INNER_PRODUCT)
+    opq = faiss.OPQMatrix(d, 96)
+    opq.niter = 2
+    index = faiss.IndexPreTransform(opq, sub)
+    index.train(xb)
+    index.add_with_ids(xb, np.arange(n, dtype=np.int64) * 7 + 5)
+    p = str(tmp_path / "index.faiss")
+    faiss.write_index(index, p)
+    got = A.read_faiss_index(p)
+    assert got["ntotal"] == n and got["by_residual"] and got["metric"] == 0 and got["A"].shape == (d, d) and got["pq"].shape == (96, 256, 8)
+    assert np.array_equal(got["A"].ravel(), faiss.vector_to_array(opq.A))
+    ref = R.RefIndex(got["A"], got["pq"], got["list_len"], centroids=got["centroids"], codes=got["codes"], ids=got["ids"])
+    xq = rng.standard_normal((9, d)).astype(np.float32)
+    faiss.extract_index_ivf(index).nprobe = 4
+    Df, If = index.search(xq, 10)
+    Dr, Ir = ref.search(xq, 10, 4)
+    assert np.array_equal(If, Ir) and np.abs(Df - Dr).max() < 1e-3
+
+
+def test_hdf5_reader_against_h5py(tmp_path):
+    h5py = pytest.importorskip("h5py")
+    rng = np.random.default_rng(0)
+    p = str(tmp_path / "idx2id.hdf5")
+    want = {}
+    with h5py.File(p, "w") as f:                                  # build_phrase_index.py:268-276
+        for off in (0, 1_000_000_000):
+            g = f.create_group(str(off))
+            want[str(off)] = {"doc": rng.integers(0, 1000, 777).astype(np.int32), "word": rng.integers(0, 300, 777).astype(np.int32)}
+            g.create_dataset("doc", data=want[str(off)]["doc"])
+            g.create_dataset("word", data=want[str(off)]["word"])
+    got = A.read_idx2id(p)
+    assert set(got) == set(want)
+    for k in want:
+        assert np.array_equal(got[k]["doc"], want[k]["doc"]) and np.array_equal(got[k]["word"], want[k]["word"])
+
+
+def test_blosc_decoder_against_blosc():
+    blosc = pytest.importorskip("blosc")
+    rng = np.random.default_rng(0)
+    for arr in (rng.integers(0, 5000, 3000).astype(np.int32), np.arange(100000, dtype=np.int64), np.zeros(0, np.int32)):
+        frame = blosc.compress(arr.tobytes(), typesize=arr.dtype.itemsize, cname="zlib")       # compress_metadata.py:32-53
+        assert A.blosc_decompress(frame) == arr.tobytes()

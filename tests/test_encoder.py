@@ -98,6 +98,24 @@ def test_cuda_encoder_3xtf32_is_fp32_accurate():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["b4_s64", "b3_s24", "b2_s100"])
+def test_cuda_encoder_bf16x3_meets_the_north_star_tolerance(name):
+    """'bf16x3' (gemm_bf16x3.cu: operands as two bf16 planes, three bf16 MMAs per product; fp32 attention, LayerNorm, softmax):
+    max |diff| < 1e-3 against the UNMODIFIED fp32 reference class on every fixture -- the tolerance BASELINE.json states --
+    at the speed of the 1xTF32 mode (bench.py encoder leg)."""
+    from densephrases_b200.encoder import BertGeometry, Encoder, random_state_dict
+    seed, vocab, ids, mask, tt, start, end = load_case(name)
+    geo = BertGeometry(vocab_size=vocab)
+    enc = Encoder(geo, state_dict=random_state_dict(geo, seed))
+    enc.set_precision("bf16x3")
+    s, e = enc(input_ids_=ids, attention_mask_=mask, token_type_ids_=tt, return_query=True)
+    ds, de = (s.cpu() - start).abs().max().item(), (e.cpu() - end).abs().max().item()
+    print(f"bf16x3 {name}: max|diff| start {ds:.2e} end {de:.2e}")
+    assert torch.isfinite(s).all() and ds < 1e-3 and de < 1e-3
+    assert enc.default_mode() == "bf16x3"
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("B,S", [(5, 64), (3, 24), (2, 8), (7, 37)])
 def test_tensor_core_attention_matches_simt_attention(B, S):
     """attention_tc.cu (tcgen05 TF32 QK^T and PV, S <= 64, padded / ragged masks) against the fp32 SIMT attention kernels inside the
@@ -137,3 +155,23 @@ def test_attention_kernels_against_torch(B, S, tensor_core, tol):
     d = (ctx - ref).abs().max().item()
     print(f"attention B={B} S={S} tensor_core={tensor_core}: max|diff| {d:.2e}")
     assert d < tol
+
+
+@pytest.mark.gpu
+def test_out_of_range_token_ids_raise():
+    """torch.nn.Embedding raises IndexError for an id outside the table; the CUDA path must not read out of bounds silently."""
+    from densephrases_b200.encoder import BertGeometry, Encoder, random_state_dict
+    geo = BertGeometry(vocab_size=500)
+    enc = Encoder(geo, state_dict=random_state_dict(geo, 1))
+    ids = torch.full((2, 8), 3, dtype=torch.int64)
+    mask, tt = torch.ones_like(ids), torch.zeros_like(ids)
+    enc.embed_query(ids, mask, tt)
+    bad = ids.clone(); bad[1, 3] = 500
+    with pytest.raises(IndexError):
+        enc.embed_query(bad, mask, tt)                       # host tensor: range-checked before the copy
+    with pytest.raises(IndexError):
+        enc.embed_query(ids, mask, tt + 2)
+    enc.embed_query(bad.cuda(), mask.cuda(), tt.cuda())      # device tensor: the kernel clamps the row and latches a flag ...
+    with pytest.raises(RuntimeError, match="embedding tables"):
+        enc.embed_query(ids.cuda(), mask.cuda(), tt.cuda())  # ... which the next call reports
+    enc.embed_query(ids.cuda(), mask.cuda(), tt.cuda())      # and the encoder stays usable

@@ -84,3 +84,38 @@ def test_gemm_schedules_are_bit_identical(M, N, K, mode):
         L.check(L.lib().dph_gemm_tf32_set_mode(DEFAULT_MODE))
     assert torch.isfinite(other).all()
     assert torch.equal(base, other), f"max|diff| {(base - other).abs().max().item():.3e}"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (4096, 768, 768), (4096, 2304, 768), (4096, 3072, 768), (4096, 768, 3072), (100, 256, 64), (1, 256, 96),
+                                   (333, 768, 768)])
+@pytest.mark.parametrize("variant", ["plain", "bias_gelu", "bias_resid"])
+def test_gemm_bf16x3_matches_fp64(M, N, K, variant):
+    """gemm_bf16x3.cu: fp32 operands carried as (hi, lo) bf16 planes, a_hi.b_lo + a_lo.b_hi + a_hi.b_hi in an fp32 TMEM accumulator.
+    Representation error 2^-18 per operand + the dropped lo.lo term 2^-18 -> relative Frobenius error well below 2e-5 (1xTF32: ~3e-4,
+    torch fp32: ~1e-7); operands that are exact in two bf16 planes (16 mantissa bits) must reproduce the fp32 product to rounding."""
+    import torch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(M * 5 + N * 3 + K)
+    A = torch.randn((M, K), generator=g, device="cuda")
+    W = torch.randn((N, K), generator=g, device="cuda") * 0.05
+    bias = torch.randn((N,), generator=g, device="cuda") if variant != "plain" else None
+    resid = torch.randn((M, N), generator=g, device="cuda") if variant == "bias_resid" else None
+    act = 1 if variant == "bias_gelu" else 0
+    out = run_gemm(A, W, bias, resid, act, precise=2)
+    ref = A.double() @ W.double().T
+    if bias is not None:
+        ref = ref + bias.double()
+    if act:
+        ref = torch.nn.functional.gelu(ref)
+    if resid is not None:
+        ref = ref + resid.double()
+    assert torch.isfinite(out).all()
+    err = (out.double() - ref).norm() / ref.norm()
+    err1 = (run_gemm(A, W, bias, resid, act, precise=0).double() - ref).norm() / ref.norm() if N % 128 == 0 else 1.0
+    print(f"bf16x3 {M}x{N}x{K} {variant}: rel err {err:.2e} (1xTF32 {err1:.2e})")
+    assert err < 2e-5, f"relative error {err:.3e}"
+    A2 = (A * 256).round() / 256            # <= 11 significant bits -> exact in (hi, lo)
+    W2 = (W * 4096).round() / 4096
+    out2 = run_gemm(A2.contiguous(), W2.contiguous(), None, None, 0, precise=2)
+    ref2 = A2.double() @ W2.double().T
+    assert (out2.double() - ref2).abs().max() < 2e-5 * max(1.0, ref2.abs().max().item())

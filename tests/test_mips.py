@@ -163,3 +163,39 @@ def test_phrase_stage_matches_reference_golden(oracle, which):
                     assert g[key] == w[key], (cfg["agg_strat"], key, g[key], w[key])
                 assert abs(g["score"] - w["score"]) <= 1e-3 * max(1.0, abs(w["score"]))
                 assert abs(float(np.sum(g["start_vec"])) - w["start_vec_sum"]) < 5e-2 and abs(float(np.sum(g["end_vec"])) - w["end_vec_sum"]) < 5e-2
+
+
+@pytest.mark.gpu
+def test_mips_loads_a_synthetic_dump_and_equals_the_oracle(oracle, tmp_path):
+    """The spec-file dump of densephrases_b200/synthetic_dump.py (C5 at full scale) loaded through the reference's own path
+    convention (load_phrase_index -> MIPS(phrase_dump_dir, index_path, idx2id_path)): the GPU-generated index equals the oracle's
+    synthetic index (same seed), idx2id is arithmetic, documents are generated on demand; results == the reference restatement."""
+    import logging
+    from densephrases import Options
+    from densephrases_b200 import runtime as R
+    from densephrases_b200 import synthetic_dump as SD
+    from oracle.mips_ref import ref_search
+    nlist, per_doc = 32, 128
+    ntotal = SD.write_synthetic_dump(str(tmp_path), f"start/{nlist}_flat_OPQ96", 128 * 300 + 77, nlist, per_doc, seed=1234)
+    assert ntotal == 128 * 300
+    o = Options()
+    o.add_model_options(); o.add_index_options(); o.add_retrieval_options(); o.add_data_options()
+    args = o.parse(["--dump_dir", str(tmp_path), "--index_name", f"start/{nlist}_flat_OPQ96", "--cuda"])
+    mips = R.load_phrase_index(args, ignore_logging=True)
+    assert mips.index.ntotal == ntotal and mips.is_pq and mips.index.nprobe == 256
+    rng = np.random.default_rng(1234)                       # MIPS derives the OPQ matrix from opq_seed the same way
+    A = np.linalg.qr(rng.standard_normal((768, 768)))[0].astype(np.float32)
+    assert np.array_equal(mips.index.opq_matrix(), A)
+    lens = SD.uniform_list_lengths(ntotal, nlist)
+    ref = oracle.RefIndex(A, oracle.gen_pq(1234), lens, centroids=oracle.gen_centroids(1234, 0, nlist), seed=1234)
+    qr = np.random.default_rng(5)
+    pick = qr.integers(0, ntotal - 8, 5)
+    vs, _ = ref.reconstruct(pick)
+    ve, _ = ref.reconstruct(pick + qr.integers(0, 4, 5))
+    query = np.concatenate([vs @ A, ve @ A], 1).astype(np.float64) + 0.05 * qr.standard_normal((5, 1536))
+    outs = mips.search(query, q_texts=["q"] * 5, top_k=10, aggregate=True)
+    want = ref_search(ref, mips.idx_f, mips.doc_groups, query, top_k=10, nprobe=256, aggregate=True, agg_strat='opt1')
+    compare(outs, want)
+    assert mips.stage_seconds['batches'] == 1 and mips.stage_seconds['mips'] > 0
+    rec = mips.doc_groups['7']
+    assert rec['context'][rec['word2char_start'][5]:rec['word2char_end'][5]] in SD._WORDS

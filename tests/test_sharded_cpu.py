@@ -162,3 +162,66 @@ def test_gloo_world2_sharded_merge_equals_unsharded(tmp_path, oracle):
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     g = np.load(out)
     assert_topk_equal(g["D"], g["I"], g["Dfull"], g["Ifull"], "sharded vs unsharded")
+
+
+class _OracleShard(object):
+    """IvfPqIndex-shaped stand-in for one list-range shard, backed by the CPU oracle: labels outside the shard reconstruct to
+    zeros / found 0 and contribute 0 to window scores, exactly like dph_index_reconstruct_batch / dph_index_window_scores."""
+
+    def __init__(self, ref, lo, hi):
+        self.ref, self.lo, self.hi = ref, lo, hi
+        self.ntotal, self.d, self.nlist = ref.ntotal, ref.d, ref.nlist
+
+    def opq_matrix(self):
+        return self.ref.A
+
+    def reconstruct_batch(self, ids):
+        v, f = self.ref.reconstruct(ids)
+        l, _ = self.ref.locate(ids)
+        mine = (l >= self.lo) & (l < self.hi)
+        return np.where(mine[:, None], v, 0).astype(np.float32), (f.astype(bool) & mine).astype(np.uint8)
+
+    def window_scores(self, q, first_ids, L):
+        out = np.zeros((len(first_ids), L), dtype=np.float32)
+        xq = self.ref.rotate(q)                                           # <q, A^T v> == <A q, v>
+        for j in range(L):
+            v, _ = self.reconstruct_batch(np.asarray(first_ids) + j)
+            out[:, j] = (xq * v).sum(1)
+        return out
+
+
+def _worker3(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from densephrases_b200.sharded import ShardedIvfPq, shard_ranges
+    from oracle import ivfpq_ref as R
+    seed, nlist = 4, 24
+    lens = np.random.default_rng(seed).integers(0, 200, nlist).astype(np.int64)
+    ref = R.RefIndex(opq_matrix(seed), R.gen_pq(seed), lens, centroids=R.gen_centroids(seed, 0, nlist), seed=seed)
+    lo, hi = shard_ranges(lens, world)[rank]
+    sh = ShardedIvfPq(nlist, rank=rank, world=world, local=_OracleShard(ref, lo, hi))
+    ids = np.concatenate([np.random.default_rng(1).integers(0, ref.ntotal, 40), [-1, ref.ntotal + 5]])
+    v, f = sh.reconstruct_batch(ids)
+    q = near_queries(ref, 6, 2)
+    first = np.random.default_rng(2).integers(0, ref.ntotal - 12, 6)
+    w = sh.window_scores(q, first, 10)
+    if rank == 0:
+        vr, fr = ref.reconstruct(ids)
+        xq = ref.rotate(q)
+        wr = np.stack([(xq * ref.reconstruct(first + j)[0]).sum(1) for j in range(10)], 1)
+        np.savez(out, v=v, f=f, vr=vr, fr=fr, w=w, wr=wr)
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_sharded_reconstruct_and_window_scores(tmp_path, oracle):
+    """MIPS over a sharded index: every label lives on one shard, the all-reduce sum of the per-shard answers is the unsharded
+    answer (reconstruct rows, found flags, phrase-window scores)."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "recon.npz")
+    mp.spawn(_worker3, args=(2, port, out), nprocs=2, join=True)
+    g = np.load(out)
+    assert np.array_equal(g["v"].view(np.int32), g["vr"].view(np.int32)) and np.array_equal(g["f"], g["fr"])
+    assert np.allclose(g["w"], g["wr"], atol=1e-5)

@@ -7,15 +7,17 @@ B, S = int(sys.argv[1]) if len(sys.argv) > 1 else 64, int(sys.argv[2]) if len(sy
 geo = BertGeometry()
 enc = Encoder(geo, state_dict=random_state_dict(geo, 1))
 ids, mask, tt = (t.cuda() for t in synthetic_query_batch(B, S, geo.vocab_size, 2))
-enc.set_precision(len(sys.argv) > 3 and sys.argv[3] == "precise")
+mode = sys.argv[3] if len(sys.argv) > 3 else "tf32"
+enc.set_precision({"precise": "3xtf32"}.get(mode, mode))     # tf32 | 3xtf32 | bf16x3
+n_iter = int(sys.argv[4]) if len(sys.argv) > 4 else 20
 for _ in range(3): enc.embed_query(ids, mask, tt)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-n = 20
+n = n_iter
 e0.record()
 for _ in range(n): enc.embed_query(ids, mask, tt)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
 T = B * S
 flops = 2 * 12 * (2.0 * T * 768 * (2304 + 768 + 3072 + 3072) + 2.0 * B * 12 * S * S * 64 * 2)
-print(f"B={B} S={S} precise={enc.precise}: {ms:.3f} ms/forward  {B/ms*1000:.0f} questions/s  {flops/ms/1e9:.1f} TFLOP/s (dense tf32 peak ~ half of bf16)")
+print(f"B={B} S={S} mode={enc.mode}: {ms:.3f} ms/forward  {B/ms*1000:.0f} questions/s  {flops/ms/1e9:.1f} TFLOP/s (dense tf32 peak ~ half of bf16)")

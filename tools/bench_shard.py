@@ -2,7 +2,7 @@
 by building shard 0 only (125M phrases, 12 GB) and timing the rank-local work of a sharded search:
     coarse_local (this shard's 8192 centroids)  +  search_preassigned (LUT, plan, scan of this shard's probed lists, merge)
 (the two NCCL all-gathers, ~2 x 20 us, are not included).  Projected 8-GPU QPS = 1024 / rank step time.
-python tools/bench_shard.py [nprobe ...]"""
+python tools/bench_shard.py [c4|c5] [auto|single|pair|quad] [nprobe ...]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -26,6 +26,11 @@ print(f"shard 0: lists [{lo},{hi}), {ix.ntotal_local/1e6:.1f} M phrases, {ix.dev
 g = torch.Generator(device="cuda").manual_seed(4321)
 X = [0.5 * torch.randn((B, 768), generator=g, device="cuda") for _ in range(6)]
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+MODES = {"auto": 0, "single": 3, "pair": 2, "quad": 4}
+mode = "auto"
+if len(sys.argv) > 1 and sys.argv[1] in MODES:
+    mode = sys.argv.pop(1)
+ix.set_scan_mode(MODES[mode])
 for nprobe in [int(a) for a in sys.argv[1:]] or [256, 32]:
     ix.nprobe = nprobe
     res = {}
@@ -50,6 +55,6 @@ for nprobe in [int(a) for a in sys.argv[1:]] or [256, 32]:
     pr = ix.last_probes(B).astype(np.int64); m = (pr >= lo) & (pr < hi)
     gb = float(lens[pr[m]].sum()) * 96 / 1e9
     step = res["preassigned"]
-    print(f"nprobe={nprobe}: rank step {step:.3f} ms (coarse_local {res['coarse_local']:.3f} ms), pair_mode={ix.last_used_pair_mode()}, "
+    print(f"nprobe={nprobe} mode={mode}: rank step {step:.3f} ms (coarse_local {res['coarse_local']:.3f} ms), queries/gather={ix.last_group_size()}, "
           f"algorithmic {gb:.2f} GB/rank/step = {gb/step*1000:.0f} GB/s; projected 8-GPU {B/step*1000:.0f} QPS "
           f"(HBM roofline {8*6590.9/(gb*8/B):.0f} QPS)", flush=True)
