@@ -63,7 +63,8 @@ def config_dict(wl, n_gpus, nprobe=None):
     return {"workload": f"{wl['name']}: {wl['N']}-phrase IVF{wl['nlist']},PQ96 (OPQ96) index, batch {wl['batch']} d=768 near queries, "
                         f"nprobe {nprobe}, top-{wl['k']}", "N": wl["N"], "nlist": wl["nlist"], "batch": wl["batch"], "nprobe": nprobe,
             "k": wl["k"], "parallelism": f"list-range shards x{n_gpus}" if n_gpus > 1 else "1 gpu",
-            "l2": f"index ({per_gpu_gb:.1f} GB of codes per GPU) is larger than L2; every step uses a different query batch"}
+            "l2": (f"index ({per_gpu_gb:.1f} GB of codes per GPU) is larger than L2; every step uses a different query batch" if per_gpu_gb > 0.2 else
+                   f"index ({per_gpu_gb * 1000:.0f} MB of codes) fits L2: a latency case, not a bandwidth case")}
 
 
 def peaks():
@@ -295,10 +296,7 @@ def measure_search(cx, ix, wl, Q, Qh, nprobe, sample_clocks=False):
     W, K, k = cx.W, cx.K, wl["k"]
     ix.nprobe = nprobe
     B = wl["batch"]
-    sampler = None
-    if sample_clocks and cx.rank == 0:
-        sampler = ClockSampler(cx.local_rank)
-        sampler.start()
+    sampler = cx.sampler if (sample_clocks and cx.rank == 0) else None      # started at process start: nvidia-smi needs time to warm up
     ms_dev, last, (tw0, tw1) = timed_loop(cx, lambda s: ix.search_device(Q[s], k), K)
     clocks = sampler.stop(tw0, tw1) if sampler else None
     last_dev = (last[0].cpu().numpy(), last[1].cpu().numpy())
@@ -460,6 +458,10 @@ def run_ours(args):
 
     wl = workload_for(world, args.scale)
     W, K = cx.W, cx.K
+    cx.sampler = None
+    if rank == 0:
+        cx.sampler = ClockSampler(local_rank)
+        cx.sampler.start()
     ix = build(wl)
     Q, Qh = queries(ix, wl, W + K)
     stage(f"{wl['name']} index built ({ix.local.device_bytes / 1e9:.1f} GB on this rank), queries made")

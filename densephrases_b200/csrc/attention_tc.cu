@@ -2,7 +2,10 @@
 // Makefile:441) on the 5th-gen tensor cores.  Same arithmetic as HF BertSelfAttention behind Encoder.embed_query
 // (/root/reference/densephrases/encoder.py:101-118): softmax(Q K^T / 8 + (1 - mask) * -10000) V per head, fp32 softmax; the two
 // contractions run as tcgen05.mma kind::tf32 with fp32 accumulation in TMEM (torch 1.9 -- the reference's pin -- also ran the
-// attention matmuls in TF32 on Ampere+).  The 3xTF32 ("precise") encoder mode keeps the SIMT fp32 kernel in encoder.cu.
+// attention matmuls in TF32 on Ampere+).  SPLIT = true is the fp32-accurate variant used by the 3xTF32 / bf16x3 encoder modes: Q, K, P and
+// V^T are split IN SHARED MEMORY into exact-TF32 (hi, lo) pairs and every contraction is hi.lo + lo.hi + hi.hi (3 MMAs, ~2^-22 relative);
+// it needs twice the operand tiles (193 KB, one CTA per SM) and can write the context directly as the (hi, lo) bf16 planes the next
+// bf16x3 GEMM consumes.
 //
 // One CTA (128 threads) handles TWO heads of one sequence of one tower so that every MMA has M = 128:
 //   rows 0..63 = tokens of head h0, rows 64..127 = tokens of head h0+1.
@@ -27,13 +30,29 @@
 #define AT_SMEM_VT (4 * AT_TILE)       // [head][kb] : 4 blocks
 #define AT_SMEM_TAIL (AT_SMEM_VT + 4 * AT_VT_TILE)
 #define AT_SMEM_BYTES (AT_SMEM_TAIL + 64 * 4 + 64 + 1024)
+// SPLIT layout: [QK hi 64 KB][QK lo 64 KB][V^T hi 32 KB][V^T lo 32 KB][tail]
+#define ATS_QK_LO (4 * AT_TILE)
+#define ATS_VT_HI (8 * AT_TILE)
+#define ATS_VT_LO (8 * AT_TILE + 4 * AT_VT_TILE)
+#define ATS_TAIL (8 * AT_TILE + 8 * AT_VT_TILE)
+#define ATS_SMEM_BYTES (ATS_TAIL + 64 * 4 + 64 + 1024)
 
 struct AttnTcMaps { CUtensorMap qkv[2]; };
-struct AttnTcArgs { const float* qkv[2]; float* ctx[2]; const long long* mask; int S; };
+struct AttnTcArgs { const float* qkv[2]; float* ctx[2]; const long long* mask; int S;
+                    unsigned short* ctx_hi[2]; unsigned short* ctx_lo[2]; };       // SPLIT only, nullable: bf16 (hi, lo) planes of the context
+
+__device__ __forceinline__ float tf32_rna(float x) { unsigned r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r); }
+__device__ __forceinline__ unsigned short bf16_bits_rn(float x) {            // round-to-nearest-even bf16 of a finite float
+    const unsigned u = __float_as_uint(x);
+    return (unsigned short)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
+}
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__global__ void __launch_bounds__(128, 2) attention_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcArgs a) {
+template <bool SPLIT>
+__global__ void __launch_bounds__(128, SPLIT ? 1 : 2) attention_tc_kernel(const __grid_constant__ AttnTcMaps maps, const AttnTcArgs a) {
+    constexpr int VT_OFF = SPLIT ? ATS_VT_HI : AT_SMEM_VT;
+    constexpr int TAIL_OFF = SPLIT ? ATS_TAIL : AT_SMEM_TAIL;
     extern __shared__ __align__(1024) unsigned char atsm[];
     // swizzle atoms need 1024-byte alignment: the window is rounded up here (the launch reserves 1 KB of slack)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -41,9 +60,9 @@ __global__ void __launch_bounds__(128, 2) attention_tc_kernel(const __grid_const
     const int S = a.S, h0 = hp * 2;
     unsigned char* base = (unsigned char*)((((unsigned long long)atsm) + 1023ull) & ~1023ull);
     const unsigned sbase = smem_u32(base);
-    float* mb = reinterpret_cast<float*>(base + AT_SMEM_TAIL);                         // [64] additive key mask
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + AT_SMEM_TAIL + 256);   // tma, mma
-    unsigned* tmem_slot = reinterpret_cast<unsigned*>(base + AT_SMEM_TAIL + 256 + 32);
+    float* mb = reinterpret_cast<float*>(base + TAIL_OFF);                             // [64] additive key mask
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + TAIL_OFF + 256);       // tma, mma
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(base + TAIL_OFF + 256 + 32);
     const unsigned bar_tma = smem_u32(bars), bar_mma = smem_u32(bars + 1);
     const CUtensorMap* map = &maps.qkv[tw];
     const long long row0 = (long long)b * S;
@@ -78,7 +97,7 @@ __global__ void __launch_bounds__(128, 2) attention_tc_kernel(const __grid_const
         const int hh = warp >> 1, j = (warp & 1) * 32 + lane;
         const bool ok = j < S;
         const float4* src = reinterpret_cast<const float4*>(a.qkv[tw] + (row0 + j) * (3 * AT_H) + 2 * AT_H + (h0 + hh) * AT_DH);
-        unsigned char* blk = base + AT_SMEM_VT + warp * AT_VT_TILE;
+        unsigned char* blk = base + VT_OFF + warp * AT_VT_TILE;
         const unsigned kk = (unsigned)lane;
 #pragma unroll 4
         for (int d4 = 0; d4 < 16; d4++) {
@@ -87,10 +106,31 @@ __global__ void __launch_bounds__(128, 2) attention_tc_kernel(const __grid_const
 #pragma unroll
             for (int t = 0; t < 4; t++) {
                 const unsigned d = (unsigned)(d4 * 4 + t);
-                *reinterpret_cast<float*>(blk + d * 128 + ((((kk >> 2) ^ (d & 7u)) << 4) | ((kk & 3u) << 2))) = e[t];
+                const unsigned off = d * 128 + ((((kk >> 2) ^ (d & 7u)) << 4) | ((kk & 3u) << 2));
+                if (SPLIT) {
+                    const float hi = tf32_rna(e[t]);
+                    *reinterpret_cast<float*>(blk + off) = hi;
+                    *reinterpret_cast<float*>(blk + (ATS_VT_LO - ATS_VT_HI) + off) = tf32_rna(e[t] - hi);
+                } else {
+                    *reinterpret_cast<float*>(blk + off) = e[t];
+                }
             }
         }
         if (tid < 64) mb[tid] = (tid < S) ? (1.0f - (float)a.mask[row0 + tid]) * -10000.0f : 0.f;
+    }
+    if (SPLIT) {
+        // Q and K arrived as fp32 through TMA: every thread waits for them and splits 32 float4 in place (hi) / into the lo tiles.
+        // The split is element-wise, so the 128-byte swizzle the TMA applied is preserved.
+        mbar_wait(bar_tma, 0);
+        float4* qk = reinterpret_cast<float4*>(base + AT_SMEM_QK);
+        float4* qk_lo = reinterpret_cast<float4*>(base + ATS_QK_LO);
+#pragma unroll 4
+        for (int i = tid; i < 4 * AT_TILE / 16; i += 128) {
+            const float4 v = qk[i];
+            const float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+            qk[i] = h;
+            qk_lo[i] = make_float4(tf32_rna(v.x - h.x), tf32_rna(v.y - h.y), tf32_rna(v.z - h.z), tf32_rna(v.w - h.w));
+        }
     }
     fence_proxy_async_smem();                       // generic-proxy stores above -> visible to the tensor core's async-proxy reads
     __syncthreads();
@@ -105,8 +145,18 @@ __global__ void __launch_bounds__(128, 2) attention_tc_kernel(const __grid_const
 #pragma unroll
             for (int kb = 0; kb < 2; kb++) {
                 const unsigned long long qd = make_sw128_desc(sbase + AT_SMEM_QK + kb * AT_TILE), kd = make_sw128_desc(sbase + AT_SMEM_QK + (2 + kb) * AT_TILE);
+                const unsigned long long ql = make_sw128_desc(sbase + ATS_QK_LO + kb * AT_TILE), kl = make_sw128_desc(sbase + ATS_QK_LO + (2 + kb) * AT_TILE);
 #pragma unroll
-                for (int k = 0; k < 4; k++) umma_tf32(tmem_base, qd + (unsigned long long)(k * 2), kd + (unsigned long long)(k * 2), IDESC_S, (kb | k) ? 1u : 0u);
+                for (int k = 0; k < 4; k++) {
+                    const unsigned long long ko = (unsigned long long)(k * 2);
+                    if (SPLIT) {
+                        umma_tf32(tmem_base, qd + ko, kl + ko, IDESC_S, (kb | k) ? 1u : 0u);
+                        umma_tf32(tmem_base, ql + ko, kd + ko, IDESC_S, 1u);
+                        umma_tf32(tmem_base, qd + ko, kd + ko, IDESC_S, 1u);
+                    } else {
+                        umma_tf32(tmem_base, qd + ko, kd + ko, IDESC_S, (kb | k) ? 1u : 0u);
+                    }
+                }
             }
             umma_commit(bar_mma);
         }
@@ -142,8 +192,15 @@ __global__ void __launch_bounds__(128, 2) attention_tc_kernel(const __grid_const
 #pragma unroll
             for (int c = 0; c < 8; c++) {
                 const int j = kb * 32 + c * 4;
-                *reinterpret_cast<float4*>(base + AT_SMEM_QK + kb * AT_TILE + r * 128 + ((((unsigned)c) ^ (r & 7u)) << 4)) =
-                    make_float4(p[j] * inv, p[j + 1] * inv, p[j + 2] * inv, p[j + 3] * inv);
+                const unsigned off = kb * AT_TILE + r * 128 + ((((unsigned)c) ^ (r & 7u)) << 4);
+                const float4 pv = make_float4(p[j] * inv, p[j + 1] * inv, p[j + 2] * inv, p[j + 3] * inv);
+                if (SPLIT) {
+                    const float4 h = make_float4(tf32_rna(pv.x), tf32_rna(pv.y), tf32_rna(pv.z), tf32_rna(pv.w));
+                    *reinterpret_cast<float4*>(base + AT_SMEM_QK + off) = h;
+                    *reinterpret_cast<float4*>(base + ATS_QK_LO + off) = make_float4(tf32_rna(pv.x - h.x), tf32_rna(pv.y - h.y), tf32_rna(pv.z - h.z), tf32_rna(pv.w - h.w));
+                } else {
+                    *reinterpret_cast<float4*>(base + AT_SMEM_QK + off) = pv;
+                }
             }
     }
     fence_proxy_async_smem();
@@ -157,10 +214,21 @@ __global__ void __launch_bounds__(128, 2) attention_tc_kernel(const __grid_const
 #pragma unroll
                 for (int kb = 0; kb < 2; kb++) {
                     const unsigned long long pd = make_sw128_desc(sbase + AT_SMEM_QK + kb * AT_TILE);
-                    const unsigned long long vd = make_sw128_desc(sbase + AT_SMEM_VT + (vh * 2 + kb) * AT_VT_TILE);
+                    const unsigned long long vd = make_sw128_desc(sbase + VT_OFF + (vh * 2 + kb) * AT_VT_TILE);
+                    const unsigned long long pl = make_sw128_desc(sbase + ATS_QK_LO + kb * AT_TILE);
+                    const unsigned long long vl = make_sw128_desc(sbase + ATS_VT_LO + (vh * 2 + kb) * AT_VT_TILE);
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        umma_tf32(tmem_base + 128u + (unsigned)(vh * 64), pd + (unsigned long long)(k * 2), vd + (unsigned long long)(k * 2), IDESC_O, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < 4; k++) {
+                        const unsigned long long ko = (unsigned long long)(k * 2);
+                        const unsigned d_o = tmem_base + 128u + (unsigned)(vh * 64);
+                        if (SPLIT) {
+                            umma_tf32(d_o, pd + ko, vl + ko, IDESC_O, (kb | k) ? 1u : 0u);
+                            umma_tf32(d_o, pl + ko, vd + ko, IDESC_O, 1u);
+                            umma_tf32(d_o, pd + ko, vd + ko, IDESC_O, 1u);
+                        } else {
+                            umma_tf32(d_o, pd + ko, vd + ko, IDESC_O, (kb | k) ? 1u : 0u);
+                        }
+                    }
                 }
             umma_commit(bar_mma);
         }
@@ -180,6 +248,22 @@ __global__ void __launch_bounds__(128, 2) attention_tc_kernel(const __grid_const
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4*>(out + half * 32 + j) =
                         make_float4(__uint_as_float(o[j]), __uint_as_float(o[j + 1]), __uint_as_float(o[j + 2]), __uint_as_float(o[j + 3]));
+                if (SPLIT && a.ctx_hi[tw]) {      // the same row segment as (hi, lo) bf16 planes for the bf16x3 output projection
+                    unsigned short* ph = a.ctx_hi[tw] + (row0 + i) * AT_H + (h0 + hh) * AT_DH + half * 32;
+                    unsigned short* pl = a.ctx_lo[tw] + (row0 + i) * AT_H + (h0 + hh) * AT_DH + half * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        __align__(16) unsigned short h8[8], l8[8];
+#pragma unroll
+                        for (int e = 0; e < 8; e++) {
+                            const float x = __uint_as_float(o[j + e]);
+                            h8[e] = bf16_bits_rn(x);
+                            l8[e] = bf16_bits_rn(x - __uint_as_float((unsigned)h8[e] << 16));
+                        }
+                        *reinterpret_cast<uint4*>(ph + j) = *reinterpret_cast<const uint4*>(h8);
+                        *reinterpret_cast<uint4*>(pl + j) = *reinterpret_cast<const uint4*>(l8);
+                    }
+                }
             }
         }
     }
@@ -189,18 +273,24 @@ __global__ void __launch_bounds__(128, 2) attention_tc_kernel(const __grid_const
 }
 
 // qkv[t]: [T, 2304] fp32 (Q | K | V, heads contiguous inside each), ctx[t]: [T, 768]; mask int64 [B, S]; S <= 64, 12 heads.
-int dph_launch_attention_tc(const float* const qkv[2], float* const ctx[2], const long long* mask, int B, int S, long long T, cudaStream_t st) {
+int dph_launch_attention_tc(const float* const qkv[2], float* const ctx[2], const long long* mask, int B, int S, long long T, cudaStream_t st, int split,
+                            unsigned short* const* ctx_hi, unsigned short* const* ctx_lo) {
     DPH_CHECK(S >= 1 && S <= 64 && B >= 1 && T >= (long long)B * S, "attention_tc: S must be 1..64");
     static DphPerDeviceOnce once;
-    if (once.first()) { DPH_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES)); }
+    if (once.first()) {
+        DPH_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
+        DPH_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATS_SMEM_BYTES));
+    }
     AttnTcMaps maps;
     AttnTcArgs a;
     for (int t = 0; t < 2; t++) {
         DPH_TRY(dph_make_map_f32(&maps.qkv[t], qkv[t], T, 3 * AT_H, 3 * AT_H, 64));
         a.qkv[t] = qkv[t]; a.ctx[t] = ctx[t];
+        a.ctx_hi[t] = ctx_hi ? ctx_hi[t] : nullptr; a.ctx_lo[t] = ctx_lo ? ctx_lo[t] : nullptr;
     }
     a.mask = mask; a.S = S;
-    attention_tc_kernel<<<dim3(6, (unsigned)B, 2), 128, AT_SMEM_BYTES, st>>>(maps, a);
+    if (split) attention_tc_kernel<true><<<dim3(6, (unsigned)B, 2), 128, ATS_SMEM_BYTES, st>>>(maps, a);
+    else attention_tc_kernel<false><<<dim3(6, (unsigned)B, 2), 128, AT_SMEM_BYTES, st>>>(maps, a);
     DPH_CUDA(cudaGetLastError());
     return 0;
 }

@@ -19,7 +19,8 @@ int dph_launch_split_bf16(const float* x, void* hi, void* lo, long long n, cudaS
 int dph_launch_gemm_bf16x3(int group, const void* const* A_hi, const void* const* A_lo, const void* const* W_hi, const void* const* W_lo,
                            const float* const* bias, const float* const* residual, float* const* out, void* const* out_hi, void* const* out_lo,
                            int M, int N, int K, int act, cudaStream_t st);
-int dph_launch_attention_tc(const float* const qkv[2], float* const ctx[2], const long long* mask, int B, int S, long long T, cudaStream_t st);   // attention_tc.cu
+int dph_launch_attention_tc(const float* const qkv[2], float* const ctx[2], const long long* mask, int B, int S, long long T, cudaStream_t st, int split,
+                            unsigned short* const* ctx_hi, unsigned short* const* ctx_lo);   // attention_tc.cu
 
 struct LayerW { const float *Wqkv, *bqkv, *Wo, *bo, *ln1g, *ln1b, *Wi, *bi, *Wo2, *bo2, *ln2g, *ln2b; };
 struct TowerW { const float *word, *pos, *type, *embg, *embb; LayerW L[ENC_LAYERS]; };
@@ -88,8 +89,19 @@ __device__ __forceinline__ void ln_row_256(float v[3], const float* g, const flo
     out[t + 512] = d2 * rstd * g[t + 512] + b[t + 512];
 }
 
+// round-to-nearest-even bf16 bits of a finite float; (hi, lo) planes with x ~= hi + lo (gemm_bf16x3.cu)
+__device__ __forceinline__ unsigned short enc_bf16_rn(float x) {
+    const unsigned u = __float_as_uint(x);
+    return (unsigned short)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
+}
+__device__ __forceinline__ void enc_split(float x, unsigned short& hi, unsigned short& lo) {
+    hi = enc_bf16_rn(x);
+    lo = enc_bf16_rn(x - __uint_as_float((unsigned)hi << 16));
+}
+
 struct EmbedArgs { const long long* ids; const long long* tt; int S; const float* word[2]; const float* pos[2]; const float* type[2];
-                   const float* g[2]; const float* b[2]; float* out[2]; long long vocab, type_vocab; int* bad; };
+                   const float* g[2]; const float* b[2]; float* out[2]; long long vocab, type_vocab; int* bad;
+                   unsigned short* out_hi[2]; unsigned short* out_lo[2]; };      // nullable: bf16 planes of the output for the first bf16x3 GEMM
 __global__ void __launch_bounds__(256) embed_ln_kernel(EmbedArgs a) {
     __shared__ float red[8];
     const long long tok = blockIdx.x; const int tw = blockIdx.y, t = threadIdx.x;
@@ -106,8 +118,19 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(EmbedArgs a) {
 #pragma unroll
     for (int i = 0; i < 3; i++) v[i] = (w[t + 256 * i] + y[t + 256 * i]) + p[t + 256 * i];   // inputs_embeds + token_type, + position (HF order)
     ln_row_256(v, a.g[tw], a.b[tw], a.out[tw] + tok * ENC_H, red);
+    if (a.out_hi[tw]) {
+        const float* o = a.out[tw] + tok * ENC_H;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            unsigned short h, l;
+            enc_split(o[t + 256 * i], h, l);          // this thread's own three outputs (written just above)
+            a.out_hi[tw][tok * ENC_H + t + 256 * i] = h;
+            a.out_lo[tw][tok * ENC_H + t + 256 * i] = l;
+        }
+    }
 }
-struct LnArgs { const float* in[2]; const float* g[2]; const float* b[2]; float* out[2]; long long rows; long long in_stride, out_stride; };
+struct LnArgs { const float* in[2]; const float* g[2]; const float* b[2]; float* out[2]; long long rows; long long in_stride, out_stride;
+                unsigned short* out_hi[2]; unsigned short* out_lo[2]; };          // nullable: dense [rows, 768] bf16 planes of the output
 // One warp per row, 24 elements per lane as six float4: no shared memory, no block barrier; two-pass mean / variance like
 // torch.nn.LayerNorm.  in/out row strides allow normalising only the [CLS] rows of the last layer.
 __global__ void __launch_bounds__(256) layernorm_kernel(LnArgs a) {
@@ -137,7 +160,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(LnArgs a) {
 #pragma unroll
     for (int i = 0; i < 6; i++) {
         const float4 gg = g[lane + 32 * i], bb = b[lane + 32 * i];
-        o[lane + 32 * i] = make_float4(v[i].x * rstd * gg.x + bb.x, v[i].y * rstd * gg.y + bb.y, v[i].z * rstd * gg.z + bb.z, v[i].w * rstd * gg.w + bb.w);
+        const float4 r4 = make_float4(v[i].x * rstd * gg.x + bb.x, v[i].y * rstd * gg.y + bb.y, v[i].z * rstd * gg.z + bb.z, v[i].w * rstd * gg.w + bb.w);
+        o[lane + 32 * i] = r4;
+        if (a.out_hi[tw]) {
+            __align__(8) unsigned short h4[4], l4[4];
+            enc_split(r4.x, h4[0], l4[0]); enc_split(r4.y, h4[1], l4[1]); enc_split(r4.z, h4[2], l4[2]); enc_split(r4.w, h4[3], l4[3]);
+            reinterpret_cast<uint2*>(a.out_hi[tw] + row * ENC_H)[lane + 32 * i] = *reinterpret_cast<const uint2*>(h4);
+            reinterpret_cast<uint2*>(a.out_lo[tw] + row * ENC_H)[lane + 32 * i] = *reinterpret_cast<const uint2*>(l4);
+        }
     }
 }
 // gather rows b*S of [B*S, 768] into a dense [B, 768] buffer (the [CLS] rows the last layer's output actually needs)
@@ -369,13 +399,14 @@ DPH_API int dph_encoder_set_attention(dph_encoder* e, int tensor_core) { e->atte
 DPH_API int dph_attention_bert(const float* qkv, const int64_t* mask, int B, int S, float* ctx, int tensor_core, void* cuda_stream) {
     DPH_CHECK(qkv && mask && ctx && B >= 1 && S >= 1 && S <= ENC_MAX_S, "attention: bad arguments");
     DPH_CHECK(!tensor_core || S <= 64, "tensor-core attention handles S <= 64");
+    DPH_CHECK(tensor_core >= 0 && tensor_core <= 2, "tensor_core: 0 SIMT fp32, 1 tcgen05 TF32, 2 tcgen05 3xTF32 split (fp32-accurate)");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     float* scratch = nullptr;                            // the launchers run two towers: the second one repeats the first into scratch
     DPH_CUDA(cudaMalloc((void**)&scratch, (size_t)B * S * ENC_H * 4));
     int rc;
     if (tensor_core) {
         const float* q2[2] = {qkv, qkv}; float* c2[2] = {ctx, scratch};
-        rc = dph_launch_attention_tc(q2, c2, (const long long*)mask, B, S, (long long)B * S, st);
+        rc = dph_launch_attention_tc(q2, c2, (const long long*)mask, B, S, (long long)B * S, st, tensor_core == 2, nullptr, nullptr);
     } else {
         AttnArgs aa; aa.qkv[0] = qkv; aa.qkv[1] = qkv; aa.ctx[0] = ctx; aa.ctx[1] = scratch; aa.mask = (const long long*)mask; aa.S = S;
         rc = launch_attention(aa, B, st);
@@ -492,19 +523,31 @@ DPH_API int dph_encoder_embed_query(dph_encoder* e, const int64_t* ids, const in
         DPH_CUDA(cudaMemcpyAsync(e->tt, tt, T * 8, cudaMemcpyHostToDevice, st));
         d_ids = e->ids; d_mask = e->mask; d_tt = e->tt;
     }
+    // bf16x3 mode: (hi, lo) planes of the three T x 768 GEMM inputs (x, ctx, a) live in act_hi / act_lo; their producers (LayerNorm,
+    // attention) write them, so no separate split pass runs.  The T x 3072 FFN intermediate's planes live in ffn[] (see `linear`).
+    unsigned short *xh[2], *xl[2], *ch[2], *cl[2], *ah[2], *al[2];
+    for (int t = 0; t < 2; t++) {
+        xh[t] = reinterpret_cast<unsigned short*>(e->act_hi[t]); xl[t] = reinterpret_cast<unsigned short*>(e->act_lo[t]);
+        ch[t] = xh[t] + T * ENC_H; cl[t] = xl[t] + T * ENC_H;
+        ah[t] = ch[t] + T * ENC_H; al[t] = cl[t] + T * ENC_H;
+    }
     {
         EmbedArgs a;
         a.ids = d_ids; a.tt = d_tt; a.S = S;
         for (int t = 0; t < 2; t++) { a.word[t] = e->tw[t].word; a.pos[t] = e->tw[t].pos; a.type[t] = e->tw[t].type; a.g[t] = e->tw[t].embg; a.b[t] = e->tw[t].embb; a.out[t] = e->x[t]; }
         a.vocab = e->vocab; a.type_vocab = e->type_vocab; a.bad = e->bad_ids;
+        for (int t = 0; t < 2; t++) { a.out_hi[t] = e->precise == 2 ? xh[t] : nullptr; a.out_lo[t] = e->precise == 2 ? xl[t] : nullptr; }
         embed_ln_kernel<<<dim3((unsigned)T, 2), 256, 0, st>>>(a);
         DPH_CUDA(cudaGetLastError());
     }
     if (e->precise == 1) DPH_TRY(ensure_split_weights(e));
     if (e->precise == 2) DPH_TRY(ensure_bf16_weights(e));
     // one grouped (two-tower) linear layer: out = act(in . W^T + b) + residual; m = which weight of the layer (0 qkv, 1 attn out, 2 ffn in, 3 ffn out)
+    unsigned short* const PH[3][2] = {{xh[0], xh[1]}, {ch[0], ch[1]}, {ah[0], ah[1]}};
+    unsigned short* const PL[3][2] = {{xl[0], xl[1]}, {cl[0], cl[1]}, {al[0], al[1]}};
+    // planes_ready (bf16x3 mode): the producer of `in` already wrote its (hi, lo) planes into PH[m] / PL[m]
     auto linear = [&](int l, int m, float* const in[2], const float* const bias[2], float* const resid[2], float* const out[2], int N, int K, int act,
-                      long long rows) -> int {
+                      long long rows, bool planes_ready) -> int {
         const LayerW &L0 = e->tw[0].L[l], &L1 = e->tw[1].L[l];
         const float* Wfull[2];
         switch (m) { case 0: Wfull[0] = L0.Wqkv; Wfull[1] = L1.Wqkv; break; case 1: Wfull[0] = L0.Wo; Wfull[1] = L1.Wo; break;
@@ -516,7 +559,8 @@ DPH_API int dph_encoder_embed_query(dph_encoder* e, const int64_t* ids, const in
         }
         if (e->precise == 2) {
             // bf16x3: operands as (hi, lo) bf16 planes.  The FFN intermediate never exists in fp32: the GELU epilogue of GEMM m = 2
-            // writes its planes (into the memory of `out`), GEMM m = 3 reads them; every other input is split by one pass.
+            // writes its planes (into the memory of `out`), GEMM m = 3 reads them; the other inputs' planes come from their producers
+            // (LayerNorm / embedding / tensor-core attention) or, failing that, from one split pass.
             const void *Whi[2], *Wlo[2], *Ahi[2], *Alo[2];
             void *Ohi[2] = {nullptr, nullptr}, *Olo[2] = {nullptr, nullptr};
             for (int t = 0; t < 2; t++) {
@@ -524,8 +568,8 @@ DPH_API int dph_encoder_embed_query(dph_encoder* e, const int64_t* ids, const in
                 if (m == 3) {                                                     // planes left by GEMM m = 2 in `in`
                     Ahi[t] = in[t]; Alo[t] = reinterpret_cast<const unsigned short*>(in[t]) + rows * (long long)K;
                 } else {
-                    DPH_TRY(dph_launch_split_bf16(in[t], e->act_hi[t], e->act_lo[t], rows * K, st));
-                    Ahi[t] = e->act_hi[t]; Alo[t] = e->act_lo[t];
+                    if (!planes_ready) DPH_TRY(dph_launch_split_bf16(in[t], PH[m][t], PL[m][t], rows * K, st));
+                    Ahi[t] = PH[m][t]; Alo[t] = PL[m][t];
                 }
                 if (m == 2) { Ohi[t] = out[t]; Olo[t] = reinterpret_cast<unsigned short*>(out[t]) + rows * (long long)N; }
             }
@@ -548,11 +592,14 @@ DPH_API int dph_encoder_embed_query(dph_encoder* e, const int64_t* ids, const in
         float* A2[2] = {e->a[0], e->a[1]};
         float* FF[2] = {e->ffn[0], e->ffn[1]};
         const float* bqkv[2] = {L0.bqkv, L1.bqkv}; const float* bo[2] = {L0.bo, L1.bo}; const float* bi[2] = {L0.bi, L1.bi}; const float* bo2[2] = {L0.bo2, L1.bo2};
-        DPH_TRY(linear(l, 0, X, bqkv, nullptr, QKV, 3 * ENC_H, ENC_H, 0, T));
+        const bool bx = e->precise == 2;
+        DPH_TRY(linear(l, 0, X, bqkv, nullptr, QKV, 3 * ENC_H, ENC_H, 0, T, bx));          // x planes: embedding LayerNorm / previous layer's LayerNorm
         AttnArgs aa; aa.qkv[0] = e->qkv[0]; aa.qkv[1] = e->qkv[1]; aa.ctx[0] = e->ctx[0]; aa.ctx[1] = e->ctx[1]; aa.mask = d_mask; aa.S = S;
-        if (e->attention_tc && !e->precise && S <= 64) {
+        bool ctx_planes = false;
+        if (e->attention_tc && S <= 64) {      // tensor cores: TF32 in the 1xTF32 mode, the 3xTF32-split kernel (fp32-accurate) in the precise modes
             const float* q2[2] = {e->qkv[0], e->qkv[1]}; float* c2[2] = {e->ctx[0], e->ctx[1]};
-            DPH_TRY(dph_launch_attention_tc(q2, c2, d_mask, B, S, T, st));
+            DPH_TRY(dph_launch_attention_tc(q2, c2, d_mask, B, S, T, st, e->precise ? 1 : 0, bx ? ch : nullptr, bx ? cl : nullptr));
+            ctx_planes = bx;
         } else {
             DPH_TRY(launch_attention(aa, B, st));
         }
@@ -570,15 +617,17 @@ DPH_API int dph_encoder_embed_query(dph_encoder* e, const int64_t* ids, const in
             X[0] = e->ffn[0] + (size_t)B * ENC_H; X[1] = e->ffn[1] + (size_t)B * ENC_H;
             FF[0] = e->qkv[0]; FF[1] = e->qkv[1];                                                                                     // qkv is dead after attention: [B, 3072] fits
         }
-        DPH_TRY(linear(l, 1, CTX, bo, X, A2, ENC_H, ENC_H, 0, rows));                                   // dense + residual
-        LnArgs ln1; for (int t = 0; t < 2; t++) { ln1.in[t] = e->a[t]; ln1.out[t] = e->a[t]; } ln1.g[0] = L0.ln1g; ln1.g[1] = L1.ln1g; ln1.b[0] = L0.ln1b; ln1.b[1] = L1.ln1b;
+        DPH_TRY(linear(l, 1, CTX, bo, X, A2, ENC_H, ENC_H, 0, rows, ctx_planes && !last));           // dense + residual (last layer: gathered rows, split here)
+        LnArgs ln1; for (int t = 0; t < 2; t++) { ln1.in[t] = e->a[t]; ln1.out[t] = e->a[t]; ln1.out_hi[t] = bx ? ah[t] : nullptr; ln1.out_lo[t] = bx ? al[t] : nullptr; }
+        ln1.g[0] = L0.ln1g; ln1.g[1] = L1.ln1g; ln1.b[0] = L0.ln1b; ln1.b[1] = L1.ln1b;
         ln1.rows = rows; ln1.in_stride = ENC_H; ln1.out_stride = ENC_H;
         layernorm_kernel<<<dim3((unsigned)((rows + 7) / 8), 2), 256, 0, st>>>(ln1);
         DPH_CUDA(cudaGetLastError());
-        DPH_TRY(linear(l, 2, A2, bi, nullptr, FF, ENC_FF, ENC_H, 1, rows));                              // intermediate + erf-GELU
+        DPH_TRY(linear(l, 2, A2, bi, nullptr, FF, ENC_FF, ENC_H, 1, rows, bx));                          // intermediate + erf-GELU
         float* XO[2] = {last ? e->ctx[0] : e->x[0], last ? e->ctx[1] : e->x[1]};                         // last layer: dense [B,768] result in ctx
-        DPH_TRY(linear(l, 3, FF, bo2, A2, XO, ENC_H, ENC_FF, 0, rows));                                  // output dense + residual
-        LnArgs ln2; for (int t = 0; t < 2; t++) { ln2.in[t] = XO[t]; ln2.out[t] = XO[t]; } ln2.g[0] = L0.ln2g; ln2.g[1] = L1.ln2g; ln2.b[0] = L0.ln2b; ln2.b[1] = L1.ln2b;
+        DPH_TRY(linear(l, 3, FF, bo2, A2, XO, ENC_H, ENC_FF, 0, rows, bx));                              // output dense + residual
+        LnArgs ln2; for (int t = 0; t < 2; t++) { ln2.in[t] = XO[t]; ln2.out[t] = XO[t]; ln2.out_hi[t] = (bx && !last) ? xh[t] : nullptr; ln2.out_lo[t] = (bx && !last) ? xl[t] : nullptr; }
+        ln2.g[0] = L0.ln2g; ln2.g[1] = L1.ln2g; ln2.b[0] = L0.ln2b; ln2.b[1] = L1.ln2b;
         ln2.rows = rows; ln2.in_stride = ENC_H; ln2.out_stride = ENC_H;
         layernorm_kernel<<<dim3((unsigned)((rows + 7) / 8), 2), 256, 0, st>>>(ln2);
         DPH_CUDA(cudaGetLastError());

@@ -124,7 +124,7 @@ DPH_API void dph_index_free(dph_index* ix) {
     cudaSetDevice(ix->device);
     void* ptrs[] = {ix->A, ix->C, ix->pq, ix->list_len, ix->list_start, ix->blk_off, ix->codes, ix->ids, ix->dm_ids, ix->dm_rows};
     for (void* p : ptrs) if (p) cudaFree(p);
-    DevBuf* bufs[] = {&ix->xdev, &ix->xr, &ix->S, &ix->key, &ix->cd, &ix->lut_scan, &ix->lut_canon, &ix->lutmax, &ix->segs, &ix->wpre, &ix->qinfo,
+    DevBuf* bufs[] = {&ix->xdev, &ix->xr, &ix->S, &ix->key, &ix->cd, &ix->lut_canon, &ix->lutmax, &ix->segs, &ix->wpre, &ix->qinfo,
                       &ix->cand, &ix->cand_off, &ix->cand_cnt, &ix->gthr, &ix->flags, &ix->work, &ix->Dp, &ix->Ip, &ix->Gp, &ix->Dh, &ix->Ih, &ix->eps, &ix->nseg, &ix->lutmin, &ix->lutmaxv, &ix->lutq, &ix->qparams, &ix->gdense,
                       &ix->pl_cnt, &ix->pl_fill, &ix->pl_off, &ix->pl_blockpre, &ix->pl_entries, &ix->pl_unitpre, &ix->pl_units, &ix->pairwork, &ix->csplit, &ix->xsplit, &ix->candkeys, &ix->cflags,
                       &ix->rb_ids, &ix->rb_out, &ix->rb_found, &ix->ws_q, &ix->ws_id, &ix->ws_out, &ix->ws_xq};
@@ -378,7 +378,6 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
     if (group == 2 && keep_pair > 1536 - DPH_SCAN_THREADS) group = 1;
     const bool pair = group > 1;
     const int keep_fast = group == 4 ? keep_quad : (group == 2 ? keep_pair : keep_single);
-    if (!pair) DPH_TRY(ix->lut_scan.ensure((size_t)n * DPH_LUT_SCAN_FLOATS * 4));
     DPH_TRY(ix->cand.ensure(((size_t)(2 * grid + 2 * n + 2) + (pair ? (size_t)(n * nprobe + 2 * DPH_PAIR_UNITS_PER_CTA * grid + 2 * n + 16) : 0)) * keep_max * 8));
     DPH_TRY(ix->cand_off.ensure((size_t)(n + 1) * 8));
     DPH_TRY(ix->cand_cnt.ensure((size_t)n * 4));
@@ -426,7 +425,7 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
             DPH_TRY(dph_launch_coarse_select(ix->S.as<float>(), n, ix->nlist, nprobe, ix->key.as<int32_t>(), ix->cd.as<float>(), st));
         }
     }
-    DPH_TRY(dph_launch_lut(ix->xr.as<float>(), n, ix->pq, pair ? nullptr : ix->lut_scan.as<float>(), ix->lut_canon.as<float>(), ix->lutmax.as<float>(),
+    DPH_TRY(dph_launch_lut(ix->xr.as<float>(), n, ix->pq, ix->lut_canon.as<float>(), ix->lutmax.as<float>(),
                            ix->lutmin.as<float>(), ix->lutmaxv.as<float>(), pair ? ix->lutq.p : nullptr,
                            pair ? ix->qparams.as<float2>() : nullptr, st, group));
     if (ix->scan_mode != DPH_SCAN_EXACT) {

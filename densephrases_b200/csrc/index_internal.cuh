@@ -17,6 +17,11 @@
 #define DPH_SURV_CAP 2048          // merge kernel: survivors re-scored exactly per query
 #define DPH_LUT_SCAN_FLOATS (3 * 256 * 64)   // per query: 3 segments x 256 codes x (32 + 31 dup + 1 pad)
 #define DPH_LUT_CANON_FLOATS (96 * 256)
+// The canonical fp32 table of a query, LUT[m][code] = <xr[8m..8m+8), pq[m][code]>, is stored segment-major, code-major,
+// sub-quantizer-minor: [3 segments of 32 sub-quantizers][256 codes][32] -- i.e. already in the row order the conflict-free scan
+// layout needs (scan.cu), so ONE 96 KB table per query serves the one-query scan (staged with its wrap copies), the quantised
+// pair / quad tables, the exact kernel and the exact re-scoring in the merge.
+#define DPH_LUTC_IDX(m, code) ((((m) >> 5) << 13) + ((code) << 5) + ((m) & 31))
 #define DPH_SEG_SMEM 256            // segment descriptors of one query kept in shared memory by the scan kernel
 #define DPH_L2_PREFETCH_ROUNDS 4    // scan kernel: bulk L2 prefetch distance, in rounds (one 3 KB block per warp per round)
 
@@ -58,7 +63,7 @@ struct dph_index {
     int64_t bytes = 0;
 
     // per-batch workspace
-    DevBuf xdev, xr, S, key, cd, lut_scan, lut_canon, lutmax, segs, wpre, qinfo, cand, cand_off, cand_cnt, gthr, flags,
+    DevBuf xdev, xr, S, key, cd, lut_canon, lutmax, segs, wpre, qinfo, cand, cand_off, cand_cnt, gthr, flags,
         work, Dp, Ip, Gp, Dh, Ih, eps, nseg,
         lutmin, lutmaxv, lutq, qparams, gdense, pl_cnt, pl_fill, pl_off, pl_blockpre, pl_entries, pl_unitpre, pl_units, pairwork,
         csplit, xsplit, candkeys, cflags,
@@ -79,7 +84,7 @@ int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprob
                              unsigned long long* keys64 = nullptr, unsigned list_base = 0, const int* only_rows = nullptr, int64_t ld = 0);
 int dph_coarse_tc(dph_index* ix, int64_t n, int64_t lo, int64_t nl, int nprobe, unsigned long long* keys64, int32_t* key, float* cd, cudaStream_t st);
 int dph_launch_coarse_merge(const unsigned long long* keys, int W, int64_t n, int nprobe, int32_t* key, float* cd, cudaStream_t st);
-int dph_launch_lut(const float* xr, int64_t n, const float* pq, float* lut_scan, float* lut_canon, float* lutmax, float* lutmin, float* lutmaxv,
+int dph_launch_lut(const float* xr, int64_t n, const float* pq, float* lut_canon, float* lutmax, float* lutmin, float* lutmaxv,
                    void* lutq, float2* qparams, cudaStream_t st, int group);
 // group: queries per gather of the scan -- 1 (fp32 LUT, one query), 2 (pair-packed u16 LUTs), 4 (quad-packed u8 LUTs)
 int dph_launch_plan(dph_index* ix, int64_t n, int k, int keep, int grid, const int32_t* only_flagged, cudaStream_t st, int group);

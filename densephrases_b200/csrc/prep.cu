@@ -465,14 +465,13 @@ int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprob
 }
 
 // =================================================================================================
-// lut: grid (n, 3), 256 threads.  Block (q, seg) computes LUT[m][j] for m in [32 seg, 32 seg + 32), j = tid:
-//   canonical  lut_canon[q][m][j]                      (exact re-scoring, canonical-order scan)
-//   scan       lut_scan[q][seg][j][w], w in 0..63:  w<32 -> m=32seg+w ; 32<=w<63 -> m=32seg+w-32 (wrap copy)
-// so that lane l reading word (l + s) at step s never has to wrap (scan.cu).  lutmax[q][m] = max_j |LUT[m][j]|.
+// lut: grid (n, 3), 256 threads.  Block (q, seg) computes LUT[m][j] for m in [32 seg, 32 seg + 32), j = tid, and writes the
+// canonical table in the layout of DPH_LUTC_IDX: lut_canon[q][seg][j][m % 32] (index_internal.cuh) -- 96 KB per query, the only
+// fp32 table that goes to memory.  lutmax[q][m] = max_j |LUT[m][j]|, lutmin / lutmaxv = min / max over j.
 // Each entry is the sequential FMA chain over the 8 sub-dimensions (compute_inner_prod_table).
 // =================================================================================================
 __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ xr, const float* __restrict__ pq,
-                                                   float* __restrict__ lut_scan, float* __restrict__ lut_canon,
+                                                   float* __restrict__ lut_canon,
                                                    float* __restrict__ lutmax, float* __restrict__ lutmin, float* __restrict__ lutmaxv) {
     __shared__ float tile[256 * 33];
     __shared__ float xs[32 * 8];
@@ -491,7 +490,6 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ xr, 
         acc = fmaf(x[0], c0.x, acc); acc = fmaf(x[1], c0.y, acc); acc = fmaf(x[2], c0.z, acc); acc = fmaf(x[3], c0.w, acc);
         acc = fmaf(x[4], c1.x, acc); acc = fmaf(x[5], c1.y, acc); acc = fmaf(x[6], c1.z, acc); acc = fmaf(x[7], c1.w, acc);
         tile[j * 33 + ml] = acc;
-        lut_canon[(q * DPH_M + m) * 256 + j] = acc;
         float a = fabsf(acc), lo = acc, hi = acc;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
@@ -510,13 +508,8 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ xr, 
         lutmin[q * DPH_M + seg * 32 + j] = lo;
         lutmaxv[q * DPH_M + seg * 32 + j] = hi;
     }
-    if (lut_scan == nullptr) return;          // pair mode scans the quantised table (lutq_kernel) instead
-    float* dst = lut_scan + ((size_t)q * 3 + seg) * (256 * 64);
-    for (int idx = j; idx < 256 * 64; idx += 256) {
-        int row = idx >> 6, w = idx & 63;
-        float v = (w < 63) ? tile[row * 33 + (w & 31)] : 0.0f;
-        dst[idx] = v;
-    }
+    float* dst = lut_canon + (size_t)q * DPH_LUT_CANON_FLOATS + (size_t)seg * (256 * 32);
+    for (int idx = j; idx < 256 * 32; idx += 256) dst[idx] = tile[(idx >> 5) * 33 + (idx & 31)];      // row = code, column = m % 32: coalesced
 }
 
 // Quantised LUT for the pair-packed scan: qv[m][j] = round((LUT[m][j] - min_m) / step) in [0, 682], one step per query
@@ -544,7 +537,7 @@ __global__ void __launch_bounds__(256) lutq_kernel(const float* __restrict__ lut
     const float inv = 1.0f / s_step;
     for (int ml = 0; ml < 32; ml++) {
         const int m = seg * 32 + ml;
-        const float v = lut_canon[(q * DPH_M + m) * 256 + j];
+        const float v = lut_canon[(size_t)q * DPH_LUT_CANON_FLOATS + DPH_LUTC_IDX(m, j)];
         int qv = (int)((v - lutmin[q * DPH_M + m]) * inv + 0.5f);
         qv = qv < 0 ? 0 : (qv > QMAX ? QMAX : qv);
         tile[j * 34 + ml] = (T)qv;
@@ -558,10 +551,10 @@ __global__ void __launch_bounds__(256) lutq_kernel(const float* __restrict__ lut
     if (seg == 0 && j == 0) qparams[q] = make_float2(s_step, s_base);
 }
 
-int dph_launch_lut(const float* xr, int64_t n, const float* pq, float* lut_scan, float* lut_canon, float* lutmax, float* lutmin, float* lutmaxv,
+int dph_launch_lut(const float* xr, int64_t n, const float* pq, float* lut_canon, float* lutmax, float* lutmin, float* lutmaxv,
                    void* lutq, float2* qparams, cudaStream_t st, int group) {
     if (n == 0) return 0;
-    lut_kernel<<<dim3((unsigned)n, 3), 256, 0, st>>>(xr, pq, lut_scan, lut_canon, lutmax, lutmin, lutmaxv);
+    lut_kernel<<<dim3((unsigned)n, 3), 256, 0, st>>>(xr, pq, lut_canon, lutmax, lutmin, lutmaxv);
     DPH_CUDA(cudaGetLastError());
     if (lutq) {
         if (group == 4) lutq_kernel<unsigned char, DPH_QMAX8><<<dim3((unsigned)n, 3), 256, 0, st>>>(lut_canon, lutmin, lutmaxv, (unsigned char*)lutq, qparams);

@@ -27,7 +27,7 @@
 
 struct ScanArgs {
     const uint8_t* codes; const long long* qpre; const DphSeg* segs; const int* nseg; const DphWork* work;
-    const float* lut_scan; const float* lut_canon;
+    const float* lut_canon;
     unsigned* gthr; unsigned long long* cand; const long long* cand_off; int* cand_cnt;
     long long n; int nprobe; int keep;
 };
@@ -143,12 +143,26 @@ __global__ void __launch_bounds__(NT, 1) scan_kernel(ScanArgs a) {
         __syncthreads();
         // ---- stage this query's LUT into shared memory ----
         {
-            const float4* src = reinterpret_cast<const float4*>(MODE == DPH_SCAN_FAST ? a.lut_scan + (size_t)q * DPH_LUT_SCAN_FLOATS
-                                                                                      : a.lut_canon + (size_t)q * DPH_LUT_CANON_FLOATS);
-            constexpr int NF4 = ((MODE == DPH_SCAN_FAST) ? DPH_LUT_SCAN_FLOATS : DPH_LUT_CANON_FLOATS) / 4;
-            float4* dst = reinterpret_cast<float4*>(smem);
+            const float4* src = reinterpret_cast<const float4*>(a.lut_canon + (size_t)q * DPH_LUT_CANON_FLOATS);
+            if (MODE == DPH_SCAN_FAST) {
+                // canonical rows [seg][code][32] -> scan rows [seg][code][64]: words 0..31 = the row, words 32..62 = its first 31
+                // entries again (the wrap copies that let lane l read word l + t without a modulo), word 63 unused.  One thread
+                // moves one float4; a quarter-warp writes 128 contiguous bytes of one row -> conflict-free.
+                float* dstf = reinterpret_cast<float*>(smem);
+#pragma unroll 4
+                for (int i = tid; i < DPH_LUT_CANON_FLOATS / 4; i += NT) {
+                    const float4 v = __ldg(src + i);
+                    const int row = i >> 3, w = (i & 7) * 4;              // row = seg * 256 + code
+                    float* r = dstf + row * 64;
+                    *reinterpret_cast<float4*>(r + w) = v;
+                    if (w < 28) *reinterpret_cast<float4*>(r + 32 + w) = v;
+                    else { r[60] = v.x; r[61] = v.y; r[62] = v.z; r[63] = 0.0f; }
+                }
+            } else {
+                float4* dst = reinterpret_cast<float4*>(smem);
 #pragma unroll 8
-            for (int i = tid; i < NF4; i += NT) dst[i] = __ldg(src + i);
+                for (int i = tid; i < DPH_LUT_CANON_FLOATS / 4; i += NT) dst[i] = __ldg(src + i);
+            }
         }
         {
             const int nsg0 = a.nseg[q];
@@ -222,7 +236,7 @@ __global__ void __launch_bounds__(NT, 1) scan_kernel(ScanArgs a) {
                     __syncwarp();
                     float dis = c_dis0;
 #pragma unroll 8
-                    for (int m = 0; m < DPH_M; m++) dis += lutc[m * 256 + stage[dph_blk_addr(lane, m)]];
+                    for (int m = 0; m < DPH_M; m++) dis += lutc[DPH_LUTC_IDX(m, (int)stage[dph_blk_addr(lane, m)])];
                     score = dis;
                     __syncwarp();
                 }
@@ -699,7 +713,7 @@ int dph_launch_scan(dph_index* ix, int64_t n, int k, int keep, int mode, int gri
     DPH_TRY(dph_scan_setup_attrs());
     ScanArgs a;
     a.codes = ix->codes; a.qpre = ix->wpre.as<long long>(); a.segs = ix->segs.as<DphSeg>(); a.nseg = ix->nseg.as<int>(); a.work = ix->work.as<DphWork>();
-    a.lut_scan = ix->lut_scan.as<float>(); a.lut_canon = ix->lut_canon.as<float>(); a.gthr = ix->gthr.as<unsigned>();
+    a.lut_canon = ix->lut_canon.as<float>(); a.gthr = ix->gthr.as<unsigned>();
     a.cand = ix->cand.as<unsigned long long>(); a.cand_off = ix->cand_off.as<long long>(); a.cand_cnt = ix->cand_cnt.as<int>();
     a.n = n; a.nprobe = ix->nprobe; a.keep = keep;
     if (mode == DPH_SCAN_FAST)
@@ -798,7 +812,7 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeArgs a) {
 #pragma unroll
             for (int h = 0; h < 3; h++) {
                 const int m = h * 32 + lane;
-                v[h] = __ldg(lutc + m * 256 + blk[dph_blk_addr(ln, m)]);
+                v[h] = __ldg(lutc + DPH_LUTC_IDX(m, (int)blk[dph_blk_addr(ln, m)]));
             }
             float dis = s.dis0;
 #pragma unroll

@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--top_k", default="10,40")
     ap.add_argument("--tokens_per_doc", type=int, default=128)
     a = ap.parse_args()
+    real_stdout = os.dup(1)            # NCCL prints its version banner on stdout: keep fd 1 for the one JSON line
+    os.dup2(2, 1)
     import numpy as np
     import torch
     os.environ["DPH_ALLOW_RANDOM_INIT"] = "1"
@@ -67,7 +69,12 @@ def main():
     mips = R.load_phrase_index(args)
     torch.cuda.synchronize()
     t_index = time.time() - t0
-    out["load_seconds"] = {"encoder": t_enc_load, "index": t_index}
+    # one untimed batch: first-call allocations (probe / LUT / candidate workspaces, the split centroid copy of the tensor-core coarse quantizer)
+    t0 = time.time()
+    rng = np.random.default_rng(0)
+    mips.search(rng.standard_normal((64, 1536)), q_texts=["warm-up"] * 64, top_k=10, aggregate=True)
+    torch.cuda.synchronize()
+    out["load_seconds"] = {"encoder": t_enc_load, "index": t_index, "first_search_batch": time.time() - t0}
     for top_k in [int(v) for v in a.top_k.split(",")]:
         args = o.parse(base + ["--top_k", str(top_k)])
         for k_ in mips.stage_seconds:
@@ -91,7 +98,7 @@ def main():
                             "questions_per_s_end_to_end": len(questions) / (t_embed + t_search),
                             "stage_seconds": st, "vector_queries_per_s_index_only": 2 * len(questions) / st["mips"]})
     if rank == 0:
-        print(json.dumps(out))
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
