@@ -146,6 +146,11 @@ def finish_queries(v, noise, A):
     """v [m,768] fp32 reconstructed rows (rotated space), A the OPQ matrix -> q = v A + noise, the product in fp64 on the host so
     that the GPU arm and the CPU arm get the same fp32 bits from the same rows."""
     import torch
+    try:                                   # torchrun exports OMP_NUM_THREADS=1: give this one-off fp64 product a fair share of the host
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    torch.set_num_threads(max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))))
     q = (v.double() @ torch.from_numpy(A).double()).float() + noise
     return q.contiguous()
 

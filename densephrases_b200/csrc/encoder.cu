@@ -399,7 +399,7 @@ DPH_API int dph_encoder_set_attention(dph_encoder* e, int tensor_core) { e->atte
 DPH_API int dph_attention_bert(const float* qkv, const int64_t* mask, int B, int S, float* ctx, int tensor_core, void* cuda_stream) {
     DPH_CHECK(qkv && mask && ctx && B >= 1 && S >= 1 && S <= ENC_MAX_S, "attention: bad arguments");
     DPH_CHECK(!tensor_core || S <= 64, "tensor-core attention handles S <= 64");
-    DPH_CHECK(tensor_core >= 0 && tensor_core <= 2, "tensor_core: 0 SIMT fp32, 1 tcgen05 TF32, 2 tcgen05 3xTF32 split (fp32-accurate)");
+    DPH_CHECK(tensor_core >= 0 && tensor_core <= 2, "tensor_core: 0 SIMT fp32, 1 tcgen05 TF32, 2 tcgen05 bf16x3 planes (fp32-accurate)");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     float* scratch = nullptr;                            // the launchers run two towers: the second one repeats the first into scratch
     DPH_CUDA(cudaMalloc((void**)&scratch, (size_t)B * S * ENC_H * 4));
@@ -596,7 +596,7 @@ DPH_API int dph_encoder_embed_query(dph_encoder* e, const int64_t* ids, const in
         DPH_TRY(linear(l, 0, X, bqkv, nullptr, QKV, 3 * ENC_H, ENC_H, 0, T, bx));          // x planes: embedding LayerNorm / previous layer's LayerNorm
         AttnArgs aa; aa.qkv[0] = e->qkv[0]; aa.qkv[1] = e->qkv[1]; aa.ctx[0] = e->ctx[0]; aa.ctx[1] = e->ctx[1]; aa.mask = d_mask; aa.S = S;
         bool ctx_planes = false;
-        if (e->attention_tc && S <= 64) {      // tensor cores: TF32 in the 1xTF32 mode, the 3xTF32-split kernel (fp32-accurate) in the precise modes
+        if (e->attention_tc && S <= 64) {      // tensor cores: TF32 in the 1xTF32 mode, the bf16 (hi, lo) plane kernel (fp32-accurate) in the precise modes
             const float* q2[2] = {e->qkv[0], e->qkv[1]}; float* c2[2] = {e->ctx[0], e->ctx[1]};
             DPH_TRY(dph_launch_attention_tc(q2, c2, d_mask, B, S, T, st, e->precise ? 1 : 0, bx ? ch : nullptr, bx ? cl : nullptr));
             ctx_planes = bx;

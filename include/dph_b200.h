@@ -144,12 +144,12 @@ int dph_encoder_load_tower(dph_encoder* e, int tower, const float* blob, int mem
  * 2: bf16x3 split GEMMs (operands as (hi, lo) bf16 planes, three kind::f16 MMAs per product, ~2^-17 relative): meets the 1e-3
  *    tolerance on the query vectors at the speed of mode 0. */
 int dph_encoder_set_precision(dph_encoder* e, int precise);
-/* 1 (default): self-attention of sequences with S <= 64 on the tensor cores -- TF32 operands in precision mode 0, the in-kernel
- * 3xTF32 split (fp32-accurate) in modes 1 and 2; fp32 accumulation and softmax.  0: always the fp32 SIMT attention kernels. */
+/* 1 (default): self-attention of sequences with S <= 64 on the tensor cores -- TF32 operands in precision mode 0, bf16 (hi, lo) planes with three
+ * MMAs per contraction (fp32-accurate) in modes 1 and 2; fp32 accumulation and softmax.  0: always the fp32 SIMT attention kernels. */
 int dph_encoder_set_attention(dph_encoder* e, int tensor_core);
 /* One BERT-base self-attention (12 heads x 64; HF BertSelfAttention as used by encoder.py:101-118) on device buffers:
  * qkv fp32 [B*S, 2304] = (Q | K | V), mask int64 [B,S] -> ctx fp32 [B*S, 768].  tensor_core: 0 SIMT fp32, 1 tcgen05 TF32,
- * 2 tcgen05 with the 3xTF32 operand split (fp32-accurate); 1 and 2 need S <= 64. */
+ * 2 tcgen05 on bf16 (hi, lo) operand planes, three MMAs per contraction (fp32-accurate); 1 and 2 need S <= 64. */
 int dph_attention_bert(const float* qkv, const int64_t* attention_mask, int B, int S, float* ctx, int tensor_core, void* cuda_stream);
 /* input_ids / attention_mask / token_type_ids int64 [B,S] (S <= 384); start_out / end_out fp32 [B,768] = hidden state at
  * position 0 of each tower (the reference returns them as [B,1,768]). */

@@ -135,7 +135,7 @@ def test_tensor_core_attention_matches_simt_attention(B, S):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("tensor_core,tol", [(0, 2e-5), (1, 1e-2), (2, 2e-5)])      # SIMT fp32 | tcgen05 TF32 | tcgen05 3xTF32 split
+@pytest.mark.parametrize("tensor_core,tol", [(0, 2e-5), (1, 1e-2), (2, 1e-4)])      # SIMT fp32 | tcgen05 TF32 | tcgen05 bf16 (hi, lo) planes
 @pytest.mark.parametrize("B,S", [(3, 64), (4, 20)])
 def test_attention_kernels_against_torch(B, S, tensor_core, tol):
     """One BERT self-attention (12 heads x 64) through the C ABI against torch fp32: softmax(QK^T/8 + (1-mask)*-1e4) V."""
