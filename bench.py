@@ -386,6 +386,9 @@ def lookup_traffic(kernel, wl_name, nprobe, world):
                                               "limiter": ent.get("limiter")}
 
 
+OC_KEYS = ("queries", "identical_ids_and_fp32_scores", "max_abs_score_minus_fp64_decoded_dot", "all_labels_found", "cpu_seconds", "cores", "note")
+
+
 def oracle_check(cx, wl, nprobe, Qh_last, last_dev, nq):
     """Rank 0: `nq` sampled queries of the last timed batch through the CPU oracle (probed lists regenerated from the seed),
     compared bit for bit with what the GPUs returned.  Also the timed cpu_baseline at N=1."""
@@ -398,8 +401,16 @@ def oracle_check(cx, wl, nprobe, Qh_last, last_dev, nq):
     x = Qh_last[pick].numpy()
     times, Dr, Ir, note, gb = cpu_search(ref, x, wl["k"], nprobe)
     same = bits_equal(Dr, Ir, last_dev[0][pick], last_dev[1][pick])
+    # decoded-vector check (SURVEY 8c identity): every returned score equals <A x, centroid + decode(code)> in fp64 up to fp32 rounding
+    Dg, Ig = last_dev[0][pick], last_dev[1][pick]
+    ok = Ig >= 0
+    v, found = ref.reconstruct(Ig[ok])
+    xr64 = (ref.A.astype(np.float64) @ x.astype(np.float64).T).T                      # [nq, 768]
+    rows = np.nonzero(ok)[0]
+    dots = np.einsum("ij,ij->i", v.astype(np.float64), xr64[rows])
+    dec_err = float(np.abs(dots - Dg[ok].astype(np.float64)).max()) if len(dots) else 0.0
     return {"queries": int(len(pick)), "identical_ids_and_fp32_scores": same, "cpu_seconds": times[0], "cores": cores, "note": note,
-            "qps": len(pick) / times[0]}
+            "qps": len(pick) / times[0], "max_abs_score_minus_fp64_decoded_dot": dec_err, "all_labels_found": bool(found.all())}
 
 
 def run_ours(args):
@@ -495,13 +506,13 @@ def run_ours(args):
                                                   f"GPU results bit-identical: {oc['identical_ids_and_fp32_scores']}"}
             else:
                 line["cpu_baseline"] = None
-            line["oracle_check"] = {k_: oc[k_] for k_ in ("queries", "identical_ids_and_fp32_scores", "cpu_seconds", "cores", "note")}
+            line["oracle_check"] = {k_: oc[k_] for k_ in OC_KEYS}
         if second is not None:
             s2 = {k_: v for k_, v in second.items() if not k_.startswith("_") and k_ != "clocks"}
             s2["config"] = config_dict(wl, world, 32)
             if not args.no_cpu:
                 oc2 = oracle_check(cx, wl, 32, Qh[W + K - 1], second["_last"], 16)
-                s2["oracle_check"] = {k_: oc2[k_] for k_ in ("queries", "identical_ids_and_fp32_scores", "cpu_seconds", "cores", "note")}
+                s2["oracle_check"] = {k_: oc2[k_] for k_ in OC_KEYS}
             line["nprobe32"] = s2
     if world > 1:
         barrier()
@@ -582,7 +593,7 @@ def c4_single_gpu_leg(cx, build, queries, args):
             r["config"] = config_dict(wl, 1, nprobe)
             if not args.no_cpu:
                 oc = oracle_check(cx, wl, nprobe, Qh[cx.W + cx.K - 1], m["_last"], 16)
-                r["oracle_check"] = {k_: oc[k_] for k_ in ("queries", "identical_ids_and_fp32_scores", "cpu_seconds", "cores", "note")}
+                r["oracle_check"] = {k_: oc[k_] for k_ in OC_KEYS}
             out[f"nprobe{nprobe}"] = r
         del ix
         torch.cuda.empty_cache()

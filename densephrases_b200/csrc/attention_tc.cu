@@ -20,6 +20,7 @@
 //   5. tcgen05.ld -> 256-byte row segments of the context activation.
 // ~97 KB shared memory and 256 TMEM columns per CTA -> two CTAs per SM.
 #include "umma.cuh"
+#include <cuda_bf16.h>
 
 #define AT_H 768
 #define AT_DH 64
@@ -34,16 +35,15 @@ struct AttnTcMaps { CUtensorMap qkv[2]; };
 struct AttnTcArgs { const float* qkv[2]; float* ctx[2]; const long long* mask; int S;
                     unsigned short* ctx_hi[2]; unsigned short* ctx_lo[2]; };       // bx kernel only, nullable: bf16 (hi, lo) planes of the context
 
-__device__ __forceinline__ unsigned short bf16_bits_rn(float x) {            // round-to-nearest-even bf16 of a finite float
-    const unsigned u = __float_as_uint(x);
-    return (unsigned short)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
-}
-// x -> (hi, lo) bf16 bit patterns with x = hi + lo up to 2^-18 |x|; packs two elements per 32-bit word (element 0 in the low half)
+__device__ __forceinline__ unsigned short bf16_bits_rn(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
+// x -> (hi, lo) bf16 bit patterns with x = hi + lo up to 2^-18 |x|; two elements per 32-bit word (element 0 in the low half):
+// one packed convert for the hi parts, one for the remainders
 __device__ __forceinline__ void bx_split2(float x0, float x1, unsigned& hi, unsigned& lo) {
-    const unsigned short h0 = bf16_bits_rn(x0), h1 = bf16_bits_rn(x1);
-    const unsigned short l0 = bf16_bits_rn(x0 - __uint_as_float((unsigned)h0 << 16)), l1 = bf16_bits_rn(x1 - __uint_as_float((unsigned)h1 << 16));
-    hi = (unsigned)h0 | ((unsigned)h1 << 16);
-    lo = (unsigned)l0 | ((unsigned)l1 << 16);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+    hi = *reinterpret_cast<const unsigned*>(&h);
+    lo = *reinterpret_cast<const unsigned*>(&l);
 }
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -307,9 +307,9 @@ __global__ void __launch_bounds__(128, 2) attention_tc_bx_kernel(const __grid_co
             for (int t = 0; t < 4; t++) {
                 const unsigned d = (unsigned)(d4 * 4 + t);
                 const unsigned off = d * 128 + ((((kk >> 3) ^ (d & 7u)) << 4) | ((kk & 7u) << 1));
-                const unsigned short hb = bf16_bits_rn(e[t]);
-                *reinterpret_cast<unsigned short*>(vh + off) = hb;
-                *reinterpret_cast<unsigned short*>(vl + off) = bf16_bits_rn(e[t] - __uint_as_float((unsigned)hb << 16));
+                const __nv_bfloat16 hb = __float2bfloat16_rn(e[t]);
+                *reinterpret_cast<__nv_bfloat16*>(vh + off) = hb;
+                *reinterpret_cast<__nv_bfloat16*>(vl + off) = __float2bfloat16_rn(e[t] - __bfloat162float(hb));
             }
         }
     }

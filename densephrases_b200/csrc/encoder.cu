@@ -4,6 +4,7 @@
 // every GEMM is one launch of the tcgen05 TF32 kernel (gemm_tf32.cu) with blockIdx.z = tower.
 #include "common.cuh"
 #include "../../include/dph_b200.h"
+#include <cuda_bf16.h>
 
 #define ENC_H 768
 #define ENC_HEADS 12
@@ -89,14 +90,18 @@ __device__ __forceinline__ void ln_row_256(float v[3], const float* g, const flo
     out[t + 512] = d2 * rstd * g[t + 512] + b[t + 512];
 }
 
-// round-to-nearest-even bf16 bits of a finite float; (hi, lo) planes with x ~= hi + lo (gemm_bf16x3.cu)
-__device__ __forceinline__ unsigned short enc_bf16_rn(float x) {
-    const unsigned u = __float_as_uint(x);
-    return (unsigned short)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
-}
+// (hi, lo) bf16 planes with x ~= hi + lo (gemm_bf16x3.cu); hardware converts, round to nearest even
 __device__ __forceinline__ void enc_split(float x, unsigned short& hi, unsigned short& lo) {
-    hi = enc_bf16_rn(x);
-    lo = enc_bf16_rn(x - __uint_as_float((unsigned)hi << 16));
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(__float2bfloat16_rn(x - __bfloat162float(h)));
+}
+__device__ __forceinline__ void enc_split2(float x0, float x1, unsigned& hi, unsigned& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+    hi = *reinterpret_cast<const unsigned*>(&h);
+    lo = *reinterpret_cast<const unsigned*>(&l);
 }
 
 struct EmbedArgs { const long long* ids; const long long* tt; int S; const float* word[2]; const float* pos[2]; const float* type[2];
@@ -163,10 +168,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(LnArgs a) {
         const float4 r4 = make_float4(v[i].x * rstd * gg.x + bb.x, v[i].y * rstd * gg.y + bb.y, v[i].z * rstd * gg.z + bb.z, v[i].w * rstd * gg.w + bb.w);
         o[lane + 32 * i] = r4;
         if (a.out_hi[tw]) {
-            __align__(8) unsigned short h4[4], l4[4];
-            enc_split(r4.x, h4[0], l4[0]); enc_split(r4.y, h4[1], l4[1]); enc_split(r4.z, h4[2], l4[2]); enc_split(r4.w, h4[3], l4[3]);
-            reinterpret_cast<uint2*>(a.out_hi[tw] + row * ENC_H)[lane + 32 * i] = *reinterpret_cast<const uint2*>(h4);
-            reinterpret_cast<uint2*>(a.out_lo[tw] + row * ENC_H)[lane + 32 * i] = *reinterpret_cast<const uint2*>(l4);
+            uint2 h4, l4;
+            enc_split2(r4.x, r4.y, h4.x, l4.x); enc_split2(r4.z, r4.w, h4.y, l4.y);
+            reinterpret_cast<uint2*>(a.out_hi[tw] + row * ENC_H)[lane + 32 * i] = h4;
+            reinterpret_cast<uint2*>(a.out_lo[tw] + row * ENC_H)[lane + 32 * i] = l4;
         }
     }
 }

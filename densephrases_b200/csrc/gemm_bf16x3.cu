@@ -16,15 +16,16 @@
 #include <cuda_bf16.h>
 
 #define BX_BM 128
-#define BX_BN 256
 #define BX_BK 32                    // bf16 elements per stage row = 64 bytes = one SWIZZLE_64B row
 #define BX_STAGES 4
 #define BX_EPI_WARPS 12
 #define BX_THREADS (128 + 32 * BX_EPI_WARPS)
 #define BX_A_BYTES (BX_BM * BX_BK * 2)          // 8 KB per plane
-#define BX_B_BYTES (BX_BN * BX_BK * 2)          // 16 KB per plane
-#define BX_STAGE_BYTES (2 * BX_A_BYTES + 2 * BX_B_BYTES)   // 48 KB
+#define BX_B_BYTES(BN) ((BN) * BX_BK * 2)       // 16 KB per plane at BN = 256
+#define BX_STAGE_BYTES(BN) (2 * BX_A_BYTES + 2 * BX_B_BYTES(BN))   // 48 KB at BN = 256, 40 KB at BN = 192
 #define BX_MAX_GROUP 2
+// Tile width BN: 256 by default; 192 for N = 768 (the attention-output and FFN-output projections): 2 towers x 32 x 3 = 192 tiles of
+// 128 x 256 fill 148 SMs 1.3 times (65 % of two waves), 256 tiles of 128 x 192 fill them 1.73 times (86 %).
 
 struct BxMaps { CUtensorMap a_hi[BX_MAX_GROUP], a_lo[BX_MAX_GROUP], b_hi[BX_MAX_GROUP], b_lo[BX_MAX_GROUP]; };
 struct BxArgs {
@@ -41,11 +42,15 @@ __device__ __forceinline__ void bx_split(float x, __nv_bfloat16& hi, __nv_bfloat
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
+template <int BX_BN>
 __global__ void __launch_bounds__(BX_THREADS, 1) gemm_bf16x3_persist_kernel(const __grid_constant__ BxMaps maps, const BxArgs args, int tiles_m, int tiles_n,
                                                                         int total_tiles) {
+    constexpr int BX_STAGE = BX_STAGE_BYTES(BX_BN);
+    constexpr int BX_BB = BX_B_BYTES(BX_BN);
+    constexpr int CHUNKS = BX_BN / 32;                       // 32-column chunks of an accumulator: 8 or 6, shared by three epilogue warp groups
     extern __shared__ __align__(1024) unsigned char gsm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char* tail = gsm + BX_STAGES * BX_STAGE_BYTES;
+    unsigned char* tail = gsm + BX_STAGES * BX_STAGE;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(tail);        // full[4], empty[4], tfull[2], tempty[2]
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(tail + 128);
     const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + BX_STAGES), tfull0 = smem_u32(bars + 2 * BX_STAGES), tempty0 = smem_u32(bars + 2 * BX_STAGES + 2);
@@ -79,12 +84,12 @@ __global__ void __launch_bounds__(BX_THREADS, 1) gemm_bf16x3_persist_kernel(cons
                 for (int kb = 0; kb < num_k; kb++, it++) {
                     const unsigned s = it % BX_STAGES, ph = (it / BX_STAGES) & 1u;
                     mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                    mbar_expect_tx(full0 + 8 * s, BX_STAGE_BYTES);
-                    const unsigned dst = stage0 + s * BX_STAGE_BYTES;
+                    mbar_expect_tx(full0 + 8 * s, BX_STAGE);
+                    const unsigned dst = stage0 + s * BX_STAGE;
                     tma_load_2d(dst, &maps.a_hi[g], kb * BX_BK, m_blk * BX_BM, full0 + 8 * s);
                     tma_load_2d(dst + BX_A_BYTES, &maps.a_lo[g], kb * BX_BK, m_blk * BX_BM, full0 + 8 * s);
                     tma_load_2d(dst + 2 * BX_A_BYTES, &maps.b_hi[g], kb * BX_BK, n_blk * BX_BN, full0 + 8 * s);
-                    tma_load_2d(dst + 2 * BX_A_BYTES + BX_B_BYTES, &maps.b_lo[g], kb * BX_BK, n_blk * BX_BN, full0 + 8 * s);
+                    tma_load_2d(dst + 2 * BX_A_BYTES + BX_BB, &maps.b_lo[g], kb * BX_BK, n_blk * BX_BN, full0 + 8 * s);
                 }
             }
         }
@@ -96,15 +101,15 @@ __global__ void __launch_bounds__(BX_THREADS, 1) gemm_bf16x3_persist_kernel(cons
             const unsigned buf = i & 1u, use = i >> 1;
             mbar_wait(tempty0 + 8 * buf, (use & 1u) ^ 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const unsigned d_tmem = tmem_base + buf * BX_BN;
+            const unsigned d_tmem = tmem_base + buf * 256u;
             for (int kb = 0; kb < num_k; kb++, it++) {
                 const unsigned s = it % BX_STAGES, ph = (it / BX_STAGES) & 1u;
                 mbar_wait(full0 + 8 * s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
-                    const unsigned base = stage0 + s * BX_STAGE_BYTES;
+                    const unsigned base = stage0 + s * BX_STAGE;
                     const unsigned long long ahi = make_sw64_desc(base), alo = make_sw64_desc(base + BX_A_BYTES);
-                    const unsigned long long bhi = make_sw64_desc(base + 2 * BX_A_BYTES), blo = make_sw64_desc(base + 2 * BX_A_BYTES + BX_B_BYTES);
+                    const unsigned long long bhi = make_sw64_desc(base + 2 * BX_A_BYTES), blo = make_sw64_desc(base + 2 * BX_A_BYTES + BX_BB);
 #pragma unroll
                     for (int k = 0; k < BX_BK / 16; k++) {          // UMMA_K = 16 bf16 = 32 bytes: advance the start address inside the swizzle atom
                         const unsigned long long ko = (unsigned long long)(k * 2);
@@ -121,7 +126,7 @@ __global__ void __launch_bounds__(BX_THREADS, 1) gemm_bf16x3_persist_kernel(cons
     } else if (warp >= 4) {
         const int q = warp & 3;
         const int eg = (warp >> 2) - 1;
-        const int c_lo = eg * 3, c_hi = (eg == 2) ? 8 : c_lo + 3;
+        const int c_lo = eg * ((CHUNKS + 2) / 3), c_hi = (eg == 2) ? CHUNKS : c_lo + (CHUNKS + 2) / 3;
         unsigned i = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, i++) {
             const int g = t / per_group, r = t - g * per_group, m_blk = r / tiles_n, n_blk = r - m_blk * tiles_n;
@@ -137,7 +142,7 @@ __global__ void __launch_bounds__(BX_THREADS, 1) gemm_bf16x3_persist_kernel(cons
 #pragma unroll 1
             for (int c = c_lo; c < c_hi; c++) {
                 unsigned v[32];
-                tmem_ld32(tmem_base + ((unsigned)(q * 32) << 16) + buf * BX_BN + (unsigned)(c * 32), v);
+                tmem_ld32(tmem_base + ((unsigned)(q * 32) << 16) + buf * 256u + (unsigned)(c * 32), v);
                 if (c == c_hi - 1) {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
@@ -221,21 +226,29 @@ int dph_launch_gemm_bf16x3(int group, const void* const* A_hi, const void* const
                            const float* const* bias, const float* const* residual, float* const* out, void* const* out_hi, void* const* out_lo,
                            int M, int N, int K, int act, cudaStream_t st) {
     DPH_CHECK(group >= 1 && group <= BX_MAX_GROUP, "gemm group size");
-    DPH_CHECK(N % BX_BN == 0 && K % BX_BK == 0 && M >= 1, "gemm_bf16x3 needs N % 256 == 0 and K % 32 == 0");
-    const int smem = BX_STAGES * BX_STAGE_BYTES + 1024;
+    DPH_CHECK((N % 256 == 0 || N % 192 == 0) && K % BX_BK == 0 && M >= 1, "gemm_bf16x3 needs N % 256 == 0 (or N % 192 == 0) and K % 32 == 0");
     static DphPerDeviceOnce once;
-    if (once.first()) DPH_CUDA(cudaFuncSetAttribute(gemm_bf16x3_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (once.first()) {
+        DPH_CUDA(cudaFuncSetAttribute(gemm_bf16x3_persist_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, BX_STAGES * BX_STAGE_BYTES(256) + 1024));
+        DPH_CUDA(cudaFuncSetAttribute(gemm_bf16x3_persist_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, BX_STAGES * BX_STAGE_BYTES(192) + 1024));
+    }
     int dev = 0, num_sms = 0;
     DPH_CUDA(cudaGetDevice(&dev));
     DPH_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    // tile width: the one that wastes less of the last wave (ties -> 256, the higher arithmetic intensity)
+    const int tm = (M + BX_BM - 1) / BX_BM;
+    auto waste = [&](int bn) { const long long t = (long long)group * tm * (N / bn); const long long w = (t + num_sms - 1) / num_sms; return (double)(w * num_sms) * bn / ((double)t * bn) ; };
+    int BN = 256;
+    if (N % 256 != 0 || (N % 192 == 0 && waste(192) + 0.2 < waste(256))) BN = 192;
+    const int smem = BX_STAGES * BX_STAGE_BYTES(BN) + 1024;
     BxMaps mp;
     BxArgs ap;
     for (int g = 0; g < BX_MAX_GROUP; g++) {
         const int s = g < group ? g : 0;
         DPH_TRY(dph_make_map_bf16(&mp.a_hi[g], A_hi[s], M, K, K, BX_BM));
         DPH_TRY(dph_make_map_bf16(&mp.a_lo[g], A_lo[s], M, K, K, BX_BM));
-        DPH_TRY(dph_make_map_bf16(&mp.b_hi[g], W_hi[s], N, K, K, BX_BN));
-        DPH_TRY(dph_make_map_bf16(&mp.b_lo[g], W_lo[s], N, K, K, BX_BN));
+        DPH_TRY(dph_make_map_bf16(&mp.b_hi[g], W_hi[s], N, K, K, BN));
+        DPH_TRY(dph_make_map_bf16(&mp.b_lo[g], W_lo[s], N, K, K, BN));
         ap.bias[g] = bias ? bias[s] : nullptr;
         ap.residual[g] = residual ? residual[s] : nullptr;
         ap.out[g] = out ? out[s] : nullptr;
@@ -243,8 +256,9 @@ int dph_launch_gemm_bf16x3(int group, const void* const* A_hi, const void* const
         ap.out_lo[g] = out_lo ? (__nv_bfloat16*)out_lo[s] : nullptr;
     }
     ap.M = M; ap.N = N; ap.K = K; ap.act = act;
-    const int tiles_m = (M + BX_BM - 1) / BX_BM, tiles_n = N / BX_BN, total = group * tiles_m * tiles_n;
-    gemm_bf16x3_persist_kernel<<<total < num_sms ? total : num_sms, BX_THREADS, smem, st>>>(mp, ap, tiles_m, tiles_n, total);
+    const int tiles_m = tm, tiles_n = N / BN, total = group * tiles_m * tiles_n;
+    if (BN == 256) gemm_bf16x3_persist_kernel<256><<<total < num_sms ? total : num_sms, BX_THREADS, smem, st>>>(mp, ap, tiles_m, tiles_n, total);
+    else gemm_bf16x3_persist_kernel<192><<<total < num_sms ? total : num_sms, BX_THREADS, smem, st>>>(mp, ap, tiles_m, tiles_n, total);
     DPH_CUDA(cudaGetLastError());
     return 0;
 }

@@ -159,22 +159,24 @@ __global__ void __launch_bounds__(256) sgemm_nt_seq_small_kernel(const float* __
 // of every output is sequential by definition, so the only parallelism is across outputs: small row tiles put the batch on many
 // SMs (n = 64, m = 768: 48 CTAs instead of 12) and keep several CTAs resident per SM so that the LDS -> FFMA latency of one
 // warp is covered by the others.  Same arithmetic as the kernels above (one FFMA per k per output, k ascending, from +0).
+#define GRK 64                      // k tile of the row-tiled kernels: half as many global round trips and barriers as 32
 template <int TM>
 __global__ void __launch_bounds__(256) sgemm_nt_seq_rows_kernel(const float* __restrict__ X, long long n, const float* __restrict__ W,
                                                                  long long m, int K, float* __restrict__ out) {
     constexpr int BM = 16 * TM;
-    __shared__ __align__(16) float As[2][GSK][BM];
-    __shared__ __align__(16) float Bs[2][GSK][64];
+    constexpr int KQ = GRK / 4;                            // float4 slots along k per row and tile
+    __shared__ __align__(16) float As[2][GRK][BM];
+    __shared__ __align__(16) float Bs[2][GRK][64];
     const int tid = threadIdx.x;
     const long long row0 = (long long)blockIdx.y * BM, col0 = (long long)blockIdx.x * 64;
-    // A tile: BM rows x 8 float4 along k; thread -> (row = tid % BM, float4 slots tid / BM + i * (256 / BM))
-    constexpr int A_PER = (BM * 8 + 255) / 256;            // float4 loads per thread for the A tile (1 for TM <= 2, 2 for TM = 4)
-    constexpr int A_STEP = 256 / BM;                       // slots covered per pass
+    // thread -> (row = tid % rows, first float4 slot = tid / rows), further slots STEP apart
+    constexpr int A_STEP = 256 / BM, A_PER = KQ / A_STEP;  // TM = 1: 16 / 16 = 1;  TM = 2: 16 / 8 = 2
+    constexpr int B_STEP = 4, B_PER = KQ / B_STEP;         // 4
+    static_assert(A_PER >= 1 && A_PER * A_STEP == KQ, "tile shape");
     const int ar = tid % BM, aq = tid / BM;
     const int br = tid & 63, bq = tid >> 6;
-    const bool aok = (row0 + ar) < n && (A_PER * A_STEP >= 8 || aq < 8);
-    const bool bok = (col0 + br) < m;
-    const float4* ap = reinterpret_cast<const float4*>(X + ((row0 + ar) < n ? (row0 + ar) : 0) * K);
+    const bool aok = (row0 + ar) < n, bok = (col0 + br) < m;
+    const float4* ap = reinterpret_cast<const float4*>(X + (aok ? (row0 + ar) : 0) * K);
     const float4* bp = reinterpret_cast<const float4*>(W + (bok ? (col0 + br) : 0) * K);
     const int tx = tid & 15, ty = tid >> 4;
     float acc[TM][4];
@@ -183,23 +185,26 @@ __global__ void __launch_bounds__(256) sgemm_nt_seq_rows_kernel(const float* __r
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 ra[A_PER], rb[2];
+    float4 ra[A_PER], rb[B_PER];
     auto fetch = [&](int kt) {
 #pragma unroll
-        for (int i = 0; i < A_PER; i++) { const int q = aq + i * A_STEP; ra[i] = (aok && q < 8) ? __ldg(ap + kt * 8 + q) : z4; }
-        rb[0] = bok ? __ldg(bp + kt * 8 + bq) : z4;
-        rb[1] = bok ? __ldg(bp + kt * 8 + bq + 4) : z4;
+        for (int i = 0; i < A_PER; i++) ra[i] = aok ? __ldg(ap + kt * KQ + aq + i * A_STEP) : z4;
+#pragma unroll
+        for (int i = 0; i < B_PER; i++) rb[i] = bok ? __ldg(bp + kt * KQ + bq + i * B_STEP) : z4;
     };
     auto stash = [&](int b) {
 #pragma unroll
         for (int i = 0; i < A_PER; i++) {
             const int q = aq + i * A_STEP;
-            if (q < 8) { As[b][q * 4 + 0][ar] = ra[i].x; As[b][q * 4 + 1][ar] = ra[i].y; As[b][q * 4 + 2][ar] = ra[i].z; As[b][q * 4 + 3][ar] = ra[i].w; }
+            As[b][q * 4 + 0][ar] = ra[i].x; As[b][q * 4 + 1][ar] = ra[i].y; As[b][q * 4 + 2][ar] = ra[i].z; As[b][q * 4 + 3][ar] = ra[i].w;
         }
-        Bs[b][bq * 4 + 0][br] = rb[0].x; Bs[b][bq * 4 + 1][br] = rb[0].y; Bs[b][bq * 4 + 2][br] = rb[0].z; Bs[b][bq * 4 + 3][br] = rb[0].w;
-        Bs[b][16 + bq * 4 + 0][br] = rb[1].x; Bs[b][16 + bq * 4 + 1][br] = rb[1].y; Bs[b][16 + bq * 4 + 2][br] = rb[1].z; Bs[b][16 + bq * 4 + 3][br] = rb[1].w;
+#pragma unroll
+        for (int i = 0; i < B_PER; i++) {
+            const int q = bq + i * B_STEP;
+            Bs[b][q * 4 + 0][br] = rb[i].x; Bs[b][q * 4 + 1][br] = rb[i].y; Bs[b][q * 4 + 2][br] = rb[i].z; Bs[b][q * 4 + 3][br] = rb[i].w;
+        }
     };
-    const int ktiles = K / GSK;
+    const int ktiles = K / GRK;
     fetch(0);
     stash(0);
     __syncthreads();
@@ -207,7 +212,7 @@ __global__ void __launch_bounds__(256) sgemm_nt_seq_rows_kernel(const float* __r
     for (int kt = 0; kt < ktiles; kt++) {
         if (kt + 1 < ktiles) fetch(kt + 1);
 #pragma unroll
-        for (int k = 0; k < GSK; k++) {
+        for (int k = 0; k < GRK; k++) {
             float a[TM];
 #pragma unroll
             for (int i = 0; i < TM; i++) a[i] = As[buf][k][ty * TM + i];
@@ -242,6 +247,7 @@ __global__ void __launch_bounds__(256) sgemm_nt_seq_rows_kernel(const float* __r
 int dph_launch_sgemm_nt_seq(const float* X, int64_t n, const float* W, int64_t m, int K, float* out, cudaStream_t st) {
     DPH_CHECK(K % GSK == 0, "sgemm_nt_seq: K must be a multiple of 32");
     if (n == 0 || m == 0) return 0;
+    const bool k64 = (K % GRK) == 0;                       // the row-tiled kernels step k by 64
     dim3 grid((unsigned)((m + GBN - 1) / GBN), (unsigned)((n + GBM - 1) / GBM));
     if ((long long)grid.x * grid.y >= 2 * 148) {
         sgemm_nt_seq_kernel<<<grid, 256, 0, st>>>(X, n, W, m, K, out);
@@ -250,7 +256,7 @@ int dph_launch_sgemm_nt_seq(const float* X, int64_t n, const float* W, int64_t m
     }
     // pick the row tile so that the grid covers the SMs a few times over (all CTAs co-resident: <= 24 KB of shared memory each)
     const long long ct = (m + 63) / 64;
-    if (ct * ((n + 63) / 64) >= 3 * 148) {
+    if (!k64 || ct * ((n + 63) / 64) >= 3 * 148) {
         sgemm_nt_seq_small_kernel<<<dim3((unsigned)ct, (unsigned)((n + 63) / 64)), 256, 0, st>>>(X, n, W, m, K, out);
     } else if (ct * ((n + 31) / 32) >= 2 * 148) {
         sgemm_nt_seq_rows_kernel<2><<<dim3((unsigned)ct, (unsigned)((n + 31) / 32)), 256, 0, st>>>(X, n, W, m, K, out);
@@ -313,14 +319,35 @@ __global__ void __launch_bounds__(256) coarse_select_kernel(const float* __restr
 // same sequential-FMA scores for its own lists.
 __global__ void __launch_bounds__(256) coarse_merge_kernel(const unsigned long long* __restrict__ keys, int W, long long n, int nprobe,
                                                             int* __restrict__ key, float* __restrict__ cd) {
-    extern __shared__ unsigned long long cm[];
+    // W * nprobe candidate keys (distinct: the list id is part of the key; 0 = empty slot) -> the nprobe largest, sorted.
+    // Radix-select the nprobe-th key, gather, sort only the winners (a full bitonic sort of 8 x 256 keys was 90 us per 1024 queries).
+    extern __shared__ unsigned long long cm[];              // [tot] candidates, then [p2s] winners
+    __shared__ SelectScratch sc;
+    __shared__ int s_nz, s_cnt;
     const long long q = blockIdx.x;
-    const int tot = W * nprobe, p2 = dph_next_pow2(tot);
-    for (int i = threadIdx.x; i < p2; i += blockDim.x) cm[i] = i < tot ? keys[((long long)(i / nprobe) * n + q) * nprobe + (i % nprobe)] : 0ull;
+    const int tot = W * nprobe, p2s = dph_next_pow2(nprobe);
+    unsigned long long* sel = cm + tot;
+    if (threadIdx.x == 0) { s_nz = 0; s_cnt = 0; }
     __syncthreads();
-    block_bitonic_sort_desc(cm, p2);
+    int nz = 0;
+    for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+        const unsigned long long k = keys[((long long)(i / nprobe) * n + q) * nprobe + (i % nprobe)];
+        cm[i] = k;
+        nz += k != 0ull;
+    }
+    for (int i = threadIdx.x; i < p2s; i += blockDim.x) sel[i] = 0ull;
+    if (nz) atomicAdd(&s_nz, nz);
+    __syncthreads();
+    unsigned long long pivot = 1ull;                        // fewer real candidates than probes: take them all
+    if (s_nz > nprobe) pivot = block_radix_select([&](int i) { return cm[i]; }, tot, nprobe, &sc);
+    for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+        const unsigned long long k = cm[i];
+        if (k >= pivot) { const int p = atomicAdd(&s_cnt, 1); if (p < p2s) sel[p] = k; }
+    }
+    __syncthreads();
+    block_bitonic_sort_desc(sel, p2s);
     for (int r = threadIdx.x; r < nprobe; r += blockDim.x) {
-        const unsigned long long k = cm[r];
+        const unsigned long long k = sel[r];
         key[q * nprobe + r] = k ? (int)(0xFFFFFFFFu - (unsigned)k) : -1;
         cd[q * nprobe + r] = k ? dph_fkey_inv((unsigned)(k >> 32)) : DPH_NEUTRAL;
     }
@@ -328,10 +355,11 @@ __global__ void __launch_bounds__(256) coarse_merge_kernel(const unsigned long l
 int dph_launch_coarse_merge(const unsigned long long* keys, int W, int64_t n, int nprobe, int32_t* key, float* cd, cudaStream_t st) {
     DPH_CHECK((long long)W * nprobe <= 8192, "coarse merge: world * nprobe must be <= 8192");
     if (n == 0) return 0;
-    int p2 = 1; while (p2 < W * nprobe) p2 <<= 1;
+    int p2s = 1; while (p2s < nprobe) p2s <<= 1;
+    const size_t smem = (size_t)(W * nprobe + p2s) * 8;
     static DphPerDeviceOnce once;
-    if (once.first()) { DPH_CUDA(cudaFuncSetAttribute(coarse_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8)); }
-    coarse_merge_kernel<<<(unsigned)n, 256, p2 * 8, st>>>(keys, W, n, nprobe, key, cd);
+    if (once.first()) { DPH_CUDA(cudaFuncSetAttribute(coarse_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (8192 + 1024) * 8)); }
+    coarse_merge_kernel<<<(unsigned)n, 256, smem, st>>>(keys, W, n, nprobe, key, cd);
     DPH_CUDA(cudaGetLastError());
     return 0;
 }
@@ -465,51 +493,67 @@ int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprob
 }
 
 // =================================================================================================
-// lut: grid (n, 3), 256 threads.  Block (q, seg) computes LUT[m][j] for m in [32 seg, 32 seg + 32), j = tid, and writes the
+// lut: grid (ceil(n / 4), 3), 256 threads.  Block (query group, seg) computes LUT[m][j] for m in [32 seg, 32 seg + 32), j = tid, and writes the
 // canonical table in the layout of DPH_LUTC_IDX: lut_canon[q][seg][j][m % 32] (index_internal.cuh) -- 96 KB per query, the only
 // fp32 table that goes to memory.  lutmax[q][m] = max_j |LUT[m][j]|, lutmin / lutmaxv = min / max over j.
 // Each entry is the sequential FMA chain over the 8 sub-dimensions (compute_inner_prod_table).
 // =================================================================================================
-__global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ xr, const float* __restrict__ pq,
+// A CTA handles one 32-sub-quantizer segment for LQ = 4 queries: every codebook entry it fetches (2 float4 per thread and
+// sub-quantizer, from L2) is used for four queries, so the L2 -> SM stream is n/4 x 786 KB instead of n x 786 KB (at 1024 queries per
+// batch that stream -- 805 MB -- was what the kernel's 128 us were spent on, not the 100 MB of table writes).
+#define LQ 4
+#define LUT_TILE_LD 257                                  // [query][sub-quantizer][code] tile, code rows padded: conflict-free both ways
+__global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ xr, const float* __restrict__ pq, long long n,
                                                    float* __restrict__ lut_canon,
                                                    float* __restrict__ lutmax, float* __restrict__ lutmin, float* __restrict__ lutmaxv) {
-    __shared__ float tile[256 * 33];
-    __shared__ float xs[32 * 8];
-    __shared__ float wmax[8][32], wmin[8][32], wmxv[8][32];
-    const long long q = blockIdx.x;
+    extern __shared__ __align__(16) float lut_sm[];
+    float* tile = lut_sm;                                 // [LQ][32][LUT_TILE_LD]
+    float* xs = tile + LQ * 32 * LUT_TILE_LD;             // [LQ][256]
+    const long long q0 = (long long)blockIdx.x * LQ;
     const int seg = blockIdx.y, j = threadIdx.x, lane = j & 31, warp = j >> 5;
-    xs[j] = xr[q * DPH_D + seg * 256 + j];
+    const int nq = (int)((n - q0) < LQ ? (n - q0) : LQ);
+#pragma unroll
+    for (int qi = 0; qi < LQ; qi++) xs[qi * 256 + j] = qi < nq ? xr[(q0 + qi) * DPH_D + seg * 256 + j] : 0.0f;
     __syncthreads();
-#pragma unroll 4
+#pragma unroll 2
     for (int ml = 0; ml < 32; ml++) {
         const int m = seg * 32 + ml;
         const float4* cb = reinterpret_cast<const float4*>(pq + ((size_t)m * 256 + j) * 8);
-        float4 c0 = __ldg(cb), c1 = __ldg(cb + 1);
-        const float* x = xs + ml * 8;
-        float acc = 0.0f;
-        acc = fmaf(x[0], c0.x, acc); acc = fmaf(x[1], c0.y, acc); acc = fmaf(x[2], c0.z, acc); acc = fmaf(x[3], c0.w, acc);
-        acc = fmaf(x[4], c1.x, acc); acc = fmaf(x[5], c1.y, acc); acc = fmaf(x[6], c1.z, acc); acc = fmaf(x[7], c1.w, acc);
-        tile[j * 33 + ml] = acc;
-        float a = fabsf(acc), lo = acc, hi = acc;
+        const float4 c0 = __ldg(cb), c1 = __ldg(cb + 1);
+#pragma unroll
+        for (int qi = 0; qi < LQ; qi++) {
+            const float4 x0 = *reinterpret_cast<const float4*>(xs + qi * 256 + ml * 8);
+            const float4 x1 = *reinterpret_cast<const float4*>(xs + qi * 256 + ml * 8 + 4);
+            float acc = 0.0f;                            // one sequential FMA chain over the 8 sub-dimensions (compute_inner_prod_table)
+            acc = fmaf(x0.x, c0.x, acc); acc = fmaf(x0.y, c0.y, acc); acc = fmaf(x0.z, c0.z, acc); acc = fmaf(x0.w, c0.w, acc);
+            acc = fmaf(x1.x, c1.x, acc); acc = fmaf(x1.y, c1.y, acc); acc = fmaf(x1.z, c1.z, acc); acc = fmaf(x1.w, c1.w, acc);
+            tile[(qi * 32 + ml) * LUT_TILE_LD + j] = acc;
+        }
+    }
+    __syncthreads();
+    // per (query, sub-quantizer): max |entry|, min, max over the 256 codes -- one warp per pair, 8 entries per lane
+    for (int p = warp; p < nq * 32; p += 8) {
+        const float* row = tile + p * LUT_TILE_LD;
+        float a = 0.0f, lo = row[lane], hi = lo;
+#pragma unroll
+        for (int e = 0; e < 8; e++) { const float v = row[lane + 32 * e]; a = fmaxf(a, fabsf(v)); lo = fminf(lo, v); hi = fmaxf(hi, v); }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, off));
             lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
             hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
         }
-        if (lane == 0) { wmax[warp][ml] = a; wmin[warp][ml] = lo; wmxv[warp][ml] = hi; }
+        if (lane == 0) {
+            const long long o = (q0 + (p >> 5)) * DPH_M + seg * 32 + (p & 31);
+            lutmax[o] = a; lutmin[o] = lo; lutmaxv[o] = hi;
+        }
     }
-    __syncthreads();
-    if (j < 32) {
-        float a = wmax[0][j], lo = wmin[0][j], hi = wmxv[0][j];
-#pragma unroll
-        for (int w = 1; w < 8; w++) { a = fmaxf(a, wmax[w][j]); lo = fminf(lo, wmin[w][j]); hi = fmaxf(hi, wmxv[w][j]); }
-        lutmax[q * DPH_M + seg * 32 + j] = a;
-        lutmin[q * DPH_M + seg * 32 + j] = lo;
-        lutmaxv[q * DPH_M + seg * 32 + j] = hi;
+    // canonical table rows [code][m % 32]: consecutive threads -> consecutive m (coalesced stores, conflict-free tile reads)
+    for (int qi = 0; qi < nq; qi++) {
+        float* dst = lut_canon + (size_t)(q0 + qi) * DPH_LUT_CANON_FLOATS + (size_t)seg * (256 * 32);
+        const float* t = tile + qi * 32 * LUT_TILE_LD;
+        for (int idx = j; idx < 256 * 32; idx += 256) dst[idx] = t[(idx & 31) * LUT_TILE_LD + (idx >> 5)];
     }
-    float* dst = lut_canon + (size_t)q * DPH_LUT_CANON_FLOATS + (size_t)seg * (256 * 32);
-    for (int idx = j; idx < 256 * 32; idx += 256) dst[idx] = tile[(idx >> 5) * 33 + (idx & 31)];      // row = code, column = m % 32: coalesced
 }
 
 // Quantised LUT for the pair-packed scan: qv[m][j] = round((LUT[m][j] - min_m) / step) in [0, 682], one step per query
@@ -522,7 +566,8 @@ template <class T, int QMAX>
 __global__ void __launch_bounds__(256) lutq_kernel(const float* __restrict__ lut_canon, const float* __restrict__ lutmin,
                                                     const float* __restrict__ lutmaxv, T* __restrict__ lutq,
                                                     float2* __restrict__ qparams) {
-    __shared__ T tile[256 * 34];
+    __shared__ float tile[256 * 33];                 // the canonical segment [256 codes][32], rows padded to 33
+    __shared__ float s_min[32];
     __shared__ float s_step, s_base;
     const long long q = blockIdx.x;
     const int seg = blockIdx.y, j = threadIdx.x, lane = j & 31;
@@ -532,21 +577,18 @@ __global__ void __launch_bounds__(256) lutq_kernel(const float* __restrict__ lut
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) { r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, off)); b += __shfl_xor_sync(0xffffffffu, b, off); }
         if (lane == 0) { s_step = fmaxf(r / (float)QMAX, 1e-30f); s_base = b; }
+        s_min[lane] = lutmin[q * DPH_M + seg * 32 + lane];
     }
+    const float* src = lut_canon + (size_t)q * DPH_LUT_CANON_FLOATS + (size_t)seg * (256 * 32);
+    for (int idx = j; idx < 256 * 32; idx += 256) tile[(idx >> 5) * 33 + (idx & 31)] = __ldg(src + idx);      // coalesced
     __syncthreads();
     const float inv = 1.0f / s_step;
-    for (int ml = 0; ml < 32; ml++) {
-        const int m = seg * 32 + ml;
-        const float v = lut_canon[(size_t)q * DPH_LUT_CANON_FLOATS + DPH_LUTC_IDX(m, j)];
-        int qv = (int)((v - lutmin[q * DPH_M + m]) * inv + 0.5f);
-        qv = qv < 0 ? 0 : (qv > QMAX ? QMAX : qv);
-        tile[j * 34 + ml] = (T)qv;
-    }
-    __syncthreads();
     T* dst = lutq + ((size_t)q * 3 + seg) * (256 * 64);
     for (int idx = j; idx < 256 * 64; idx += 256) {
-        const int row = idx >> 6, w = idx & 63;
-        dst[idx] = (w < 63) ? tile[row * 34 + (w & 31)] : (T)0;
+        const int row = idx >> 6, w = idx & 63, ml = w & 31;
+        int qv = (int)((tile[row * 33 + ml] - s_min[ml]) * inv + 0.5f);
+        qv = qv < 0 ? 0 : (qv > QMAX ? QMAX : qv);
+        dst[idx] = (w < 63) ? (T)qv : (T)0;
     }
     if (seg == 0 && j == 0) qparams[q] = make_float2(s_step, s_base);
 }
@@ -554,7 +596,10 @@ __global__ void __launch_bounds__(256) lutq_kernel(const float* __restrict__ lut
 int dph_launch_lut(const float* xr, int64_t n, const float* pq, float* lut_canon, float* lutmax, float* lutmin, float* lutmaxv,
                    void* lutq, float2* qparams, cudaStream_t st, int group) {
     if (n == 0) return 0;
-    lut_kernel<<<dim3((unsigned)n, 3), 256, 0, st>>>(xr, pq, lut_canon, lutmax, lutmin, lutmaxv);
+    const size_t lut_smem = (size_t)(LQ * 32 * LUT_TILE_LD + LQ * 256) * 4;
+    static DphPerDeviceOnce lut_once;
+    if (lut_once.first()) { DPH_CUDA(cudaFuncSetAttribute(lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_smem)); }
+    lut_kernel<<<dim3((unsigned)((n + LQ - 1) / LQ), 3), 256, lut_smem, st>>>(xr, pq, n, lut_canon, lutmax, lutmin, lutmaxv);
     DPH_CUDA(cudaGetLastError());
     if (lutq) {
         if (group == 4) lutq_kernel<unsigned char, DPH_QMAX8><<<dim3((unsigned)n, 3), 256, 0, st>>>(lut_canon, lutmin, lutmaxv, (unsigned char*)lutq, qparams);

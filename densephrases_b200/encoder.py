@@ -47,7 +47,7 @@ def tower_blob(sd, prefix, config):
 
 
 class Encoder(object):
-    def __init__(self, config, tokenizer=None, state_dict=None, device=0, precise=False):
+    def __init__(self, config, tokenizer=None, state_dict=None, device=0, precise='bf16x3'):
         self.config = config if isinstance(config, BertGeometry) else BertGeometry(**{k: getattr(config, k) for k in
                                                                                      ('vocab_size', 'max_position_embeddings', 'type_vocab_size', 'hidden_size',
                                                                                       'num_hidden_layers', 'num_attention_heads', 'intermediate_size')})
@@ -70,7 +70,8 @@ class Encoder(object):
     MODES = {'tf32': 0, '3xtf32': 1, 'bf16x3': 2}      # name -> dph_encoder_set_precision argument
 
     def set_precision(self, precise):
-        """'tf32' / False (default): 1xTF32 GEMMs (== torch 1.9's default for fp32 matmuls on Ampere+);
+        """'bf16x3' (default of this class): meets the north star's 1e-3 tolerance on the query vectors at nearly the speed of 'tf32';
+        'tf32' / False: 1xTF32 GEMMs (== torch 1.9's default for fp32 matmuls on Ampere+), fastest, ~2e-2;
         '3xtf32' / True: 3xTF32 split, fp32-accurate; 'bf16x3': bf16 (hi, lo) planes, three bf16 MMAs per product -- both meet
         the 1e-3 tolerance of the north star, bf16x3 at the speed of 'tf32'."""
         mode = precise if isinstance(precise, str) else ('3xtf32' if precise else 'tf32')

@@ -108,6 +108,8 @@ def test_densephrases_search_and_evaluate_end_to_end(oracle, tmp_path):
     args.test_path, args.top_k, args.aggregate = str(p), 5, True
     res = evaluate(args, mips=mips, query_encoder=model.model, tokenizer=model.tokenizer)
     assert res["exact_match_top1"] == 1.0 and res["exact_match_top5"] == 1.0
+    res2 = model.evaluate(str(p), top_k=5, aggregate=True)             # DensePhrases.evaluate (model.py:118-128): same loop through the model object
+    assert res2["exact_match_top1"] == 1.0 and res2["predictions"] == res["predictions"]
 
 
 @pytest.mark.parametrize("lower", [False, True])
@@ -322,3 +324,28 @@ def test_option_flags_and_defaults_equal_reference_parser():
     argv = ["--cuda", "--top_k", "40", "--nprobe", "64", "--index_name", "start/1048576_flat_OPQ96", "--eval_batch_size", "32", "--agg_strat", "opt2"]
     got2 = vars(ours.parse(argv))
     assert {k: got2[k] for k in want} == vars(theirs.parser.parse_args(argv))
+
+
+def test_synthetic_dump_spec_objects(tmp_path):
+    """densephrases_b200/synthetic_dump.py: the spec files land where load_phrase_index looks (open_utils.py:28-31), idx2id lookups are
+    arithmetic, documents are a pure function of (seed, doc) -- every rank of a sharded job sees the same corpus."""
+    import os
+    from densephrases_b200 import synthetic_dump as SD
+    ntotal = SD.write_synthetic_dump(str(tmp_path), "start/64_flat_OPQ96", 128 * 50 + 3, 64, tokens_per_doc=128, seed=7)
+    assert ntotal == 128 * 50
+    for rel in ("start/64_flat_OPQ96/index.dph.json", "start/64_flat_OPQ96/idx2id.dph.json", "meta_dph.json", "phrase"):
+        assert os.path.exists(tmp_path / rel)
+    idx = SD.synthetic_idx2id(ntotal, 128)
+    rows = np.array([0, 127, 128, 6399])
+    assert idx["0"]["doc"][rows].tolist() == [0, 0, 1, 49] and idx["0"]["word"][rows].tolist() == [0, 127, 0, 127]
+    a, b = SD.LazyDocs(128, 7), SD.LazyDocs(128, 7)
+    ra, rb = a["13"], b[13]
+    assert ra["context"] == rb["context"] and np.array_equal(ra["word2char_end"], rb["word2char_end"]) and ra["title"] == "Doc 13"
+    assert len(ra["f2o_start"]) == 128 and ra["word2char_end"][-1] == len(ra["context"])
+    w = 17
+    assert ra["context"][ra["word2char_start"][w]:ra["word2char_end"][w]] in SD._WORDS
+    assert SD.LazyDocs(128, 8)["13"]["context"] != ra["context"]
+    assert SD.uniform_list_lengths(10, 4).tolist() == [3, 3, 2, 2]
+    qa = SD.write_synthetic_questions(str(tmp_path / "q.json"), 5)
+    import json as _json
+    assert len(_json.load(open(qa))["data"]) == 5

@@ -20,10 +20,10 @@ done
 
 timeout 600 $NCU --set full --import-source on -k regex:scan_quad_kernel -s 4 -c 1 -o $OUT/${TAG}_scan_quad_c2 $B > $OUT/ncu1.log 2>&1
 timeout 600 $NCU --set full --import-source on -k regex:scan_quad_kernel -s 12 -c 1 -o $OUT/${TAG}_scan_quad_c4shard python tools/bench_shard.py c4 256 > $OUT/ncu2.log 2>&1
-timeout 600 $NCU --set full --import-source on -k regex:"scan_kernel<0>|scan_kernel<\(int\)0>" -s 12 -c 1 -o $OUT/${TAG}_scan_single_c4shard python tools/bench_shard.py c4 32 > $OUT/ncu3.log 2>&1
+timeout 600 $NCU --set full --import-source on -k regex:^scan_kernel$ -s 12 -c 1 -o $OUT/${TAG}_scan_single_c4shard python tools/bench_shard.py c4 32 > $OUT/ncu3.log 2>&1
 # QKV projection of the second forward (48 GEMM launches per forward) and one attention launch, bf16x3 mode
 timeout 600 $NCU --set full --import-source on -k regex:gemm_bf16x3_persist_kernel -s 48 -c 1 -o $OUT/${TAG}_gemm_bf16x3 python tools/bench_encoder.py 64 64 bf16x3 2 > $OUT/ncu4.log 2>&1
-timeout 600 $NCU --set full --import-source on -k regex:attention_tc_kernel -s 12 -c 1 -o $OUT/${TAG}_attention_tc_split python tools/bench_encoder.py 64 64 bf16x3 2 > $OUT/ncu5.log 2>&1
+timeout 600 $NCU --set full --import-source on -k regex:attention_tc_bx_kernel -s 12 -c 1 -o $OUT/${TAG}_attention_tc_bx python tools/bench_encoder.py 64 64 bf16x3 2 > $OUT/ncu5.log 2>&1
 timeout 600 $NCU --set full --import-source on -k regex:gemm_tf32_persist_kernel -s 48 -c 1 -o $OUT/${TAG}_gemm_tf32_persist python tools/bench_encoder.py 64 64 tf32 2 > $OUT/ncu6.log 2>&1
 
 ARGS=""
@@ -32,7 +32,7 @@ ARGS=""
 [ -f $OUT/${TAG}_scan_single_c4shard.ncu-rep ] && ARGS="$ARGS scan_kernel<FAST>|C4|nprobe32|n8=$OUT/${TAG}_scan_single_c4shard.ncu-rep"
 python tools/make_traffic.py $ARGS
 cp profiles/traffic.json $OUT/${TAG}_traffic.json
-for rep in scan_quad_c2 scan_quad_c4shard scan_single_c4shard gemm_bf16x3 attention_tc_split gemm_tf32_persist; do
+for rep in scan_quad_c2 scan_quad_c4shard scan_single_c4shard gemm_bf16x3 attention_tc_bx gemm_tf32_persist; do
   [ -f $OUT/${TAG}_${rep}.ncu-rep ] && python tools/ncu_summary.py $OUT/${TAG}_${rep}.ncu-rep $OUT/${TAG}_${rep}_ncu_summary.txt > /dev/null
 done
 ls -la $OUT | tail -30
