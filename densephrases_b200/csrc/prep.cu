@@ -28,11 +28,14 @@ __global__ void __launch_bounds__(256) sgemm_nt_seq_kernel(const float* __restri
     const float4* ap = reinterpret_cast<const float4*>(X + (aok ? arow : 0) * K) + lk4;
     const float4* bp = reinterpret_cast<const float4*>(W + (bok ? brow : 0) * K) + lk4;
     const int tx = tid & 15, ty = tid >> 4;
-    float acc[8][8];
+    // accumulators as float2 pairs along the output column: one packed FFMA2 (fma.rn.f32x2, two independent IEEE fp32 FMAs)
+    // advances two outputs -- the SIMT fp32 pipe issues a 3-register FFMA every other cycle, so this doubles the FMA rate while
+    // every output still sees exactly one fused multiply-add per k, k ascending (bit-identical to the scalar chain).
+    float2 acc[8][4];
 #pragma unroll
     for (int i = 0; i < 8; i++)
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[i][j] = 0.0f;
+        for (int j = 0; j < 4; j++) acc[i][j] = make_float2(0.0f, 0.0f);
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 ra = aok ? __ldg(ap) : z4, rb = bok ? __ldg(bp) : z4;
     const int ktiles = K / GBK;
@@ -51,12 +54,14 @@ __global__ void __launch_bounds__(256) sgemm_nt_seq_kernel(const float* __restri
             float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
             float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
             float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
-            float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float2 b[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 0; i < 8; i++) {
+                const float2 a2 = make_float2(a[i], a[i]);
 #pragma unroll
-                for (int j = 0; j < 8; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < 4; j++) acc[i][j] = __ffma2_rn(a2, b[j], acc[i][j]);
+            }
         }
         if (kt + 1 < ktiles) {
             int nb = buf ^ 1;
@@ -75,11 +80,12 @@ __global__ void __launch_bounds__(256) sgemm_nt_seq_kernel(const float* __restri
             long long c = col0 + jh * 64 + tx * 4;
             float* o = out + r * m + c;
             if (c + 3 < m && ((m & 3) == 0)) {
-                *reinterpret_cast<float4*>(o) = make_float4(acc[i][jh * 4 + 0], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]);
+                *reinterpret_cast<float4*>(o) = make_float4(acc[i][jh * 2].x, acc[i][jh * 2].y, acc[i][jh * 2 + 1].x, acc[i][jh * 2 + 1].y);
             } else {
+                const float v[4] = {acc[i][jh * 2].x, acc[i][jh * 2].y, acc[i][jh * 2 + 1].x, acc[i][jh * 2 + 1].y};
 #pragma unroll
                 for (int j = 0; j < 4; j++)
-                    if (c + j < m) o[j] = acc[i][jh * 4 + j];
+                    if (c + j < m) o[j] = v[j];
             }
         }
     }
@@ -101,11 +107,9 @@ __global__ void __launch_bounds__(256) sgemm_nt_seq_small_kernel(const float* __
     const float4* ap = reinterpret_cast<const float4*>(X + (aok ? arow : 0) * K) + q4;
     const float4* bp = reinterpret_cast<const float4*>(W + (bok ? brow : 0) * K) + q4;
     const int tx = tid & 15, ty = tid >> 4;
-    float acc[4][4];
+    float2 acc[4][2];                        // packed FFMA2 along the output column (see sgemm_nt_seq_kernel)
 #pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+    for (int i = 0; i < 4; i++) { acc[i][0] = make_float2(0.0f, 0.0f); acc[i][1] = make_float2(0.0f, 0.0f); }
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 ra0 = aok ? __ldg(ap) : z4, ra1 = aok ? __ldg(ap + 4) : z4, rb0 = bok ? __ldg(bp) : z4, rb1 = bok ? __ldg(bp + 4) : z4;
     const int ktiles = K / GSK;
@@ -128,11 +132,14 @@ __global__ void __launch_bounds__(256) sgemm_nt_seq_small_kernel(const float* __
         for (int k = 0; k < GSK; k++) {
             const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
             const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float2 b01 = make_float2(b4.x, b4.y), b23 = make_float2(b4.z, b4.w);
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            for (int i = 0; i < 4; i++) {
+                const float2 a2 = make_float2(a[i], a[i]);
+                acc[i][0] = __ffma2_rn(a2, b01, acc[i][0]);
+                acc[i][1] = __ffma2_rn(a2, b23, acc[i][1]);
+            }
         }
         if (kt + 1 < ktiles) {
             stash(buf ^ 1);
@@ -146,11 +153,12 @@ __global__ void __launch_bounds__(256) sgemm_nt_seq_small_kernel(const float* __
         if (rr >= n) continue;
         const long long c = col0 + tx * 4;
         float* o = out + rr * m + c;
-        if (c + 3 < m && ((m & 3) == 0)) *reinterpret_cast<float4*>(o) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        const float v[4] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y};
+        if (c + 3 < m && ((m & 3) == 0)) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
         else {
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                if (c + j < m) o[j] = acc[i][j];
+                if (c + j < m) o[j] = v[j];
         }
     }
 }
@@ -179,11 +187,9 @@ __global__ void __launch_bounds__(256) sgemm_nt_seq_rows_kernel(const float* __r
     const float4* ap = reinterpret_cast<const float4*>(X + (aok ? (row0 + ar) : 0) * K);
     const float4* bp = reinterpret_cast<const float4*>(W + (bok ? (col0 + br) : 0) * K);
     const int tx = tid & 15, ty = tid >> 4;
-    float acc[TM][4];
+    float2 acc[TM][2];                       // float2 pairs along the output column, advanced by packed FFMA2 (see sgemm_nt_seq_kernel)
 #pragma unroll
-    for (int i = 0; i < TM; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+    for (int i = 0; i < TM; i++) { acc[i][0] = make_float2(0.0f, 0.0f); acc[i][1] = make_float2(0.0f, 0.0f); }
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 ra[A_PER], rb[B_PER];
     auto fetch = [&](int kt) {
@@ -217,11 +223,13 @@ __global__ void __launch_bounds__(256) sgemm_nt_seq_rows_kernel(const float* __r
 #pragma unroll
             for (int i = 0; i < TM; i++) a[i] = As[buf][k][ty * TM + i];
             const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-            const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+            const float2 b01 = make_float2(b4.x, b4.y), b23 = make_float2(b4.z, b4.w);
 #pragma unroll
-            for (int i = 0; i < TM; i++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            for (int i = 0; i < TM; i++) {
+                const float2 a2 = make_float2(a[i], a[i]);
+                acc[i][0] = __ffma2_rn(a2, b01, acc[i][0]);
+                acc[i][1] = __ffma2_rn(a2, b23, acc[i][1]);
+            }
         }
         if (kt + 1 < ktiles) {
             stash(buf ^ 1);
@@ -235,11 +243,12 @@ __global__ void __launch_bounds__(256) sgemm_nt_seq_rows_kernel(const float* __r
         if (rr >= n) continue;
         const long long c = col0 + tx * 4;
         float* o = out + rr * m + c;
-        if (c + 3 < m && ((m & 3) == 0)) *reinterpret_cast<float4*>(o) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        const float v[4] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y};
+        if (c + 3 < m && ((m & 3) == 0)) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
         else {
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                if (c + j < m) o[j] = acc[i][j];
+                if (c + j < m) o[j] = v[j];
         }
     }
 }
@@ -507,28 +516,47 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ xr, 
                                                    float* __restrict__ lut_canon,
                                                    float* __restrict__ lutmax, float* __restrict__ lutmin, float* __restrict__ lutmaxv) {
     extern __shared__ __align__(16) float lut_sm[];
-    float* tile = lut_sm;                                 // [LQ][32][LUT_TILE_LD]
-    float* xs = tile + LQ * 32 * LUT_TILE_LD;             // [LQ][256]
+    float* __restrict__ tile = lut_sm;                    // [LQ][32][LUT_TILE_LD]
+    __shared__ __align__(16) float xs[LQ * 256];          // a separate object: stores to `tile` cannot alias it, loads can be hoisted
     const long long q0 = (long long)blockIdx.x * LQ;
     const int seg = blockIdx.y, j = threadIdx.x, lane = j & 31, warp = j >> 5;
     const int nq = (int)((n - q0) < LQ ? (n - q0) : LQ);
 #pragma unroll
     for (int qi = 0; qi < LQ; qi++) xs[qi * 256 + j] = qi < nq ? xr[(q0 + qi) * DPH_D + seg * 256 + j] : 0.0f;
     __syncthreads();
-#pragma unroll 2
-    for (int ml = 0; ml < 32; ml++) {
-        const int m = seg * 32 + ml;
-        const float4* cb = reinterpret_cast<const float4*>(pq + ((size_t)m * 256 + j) * 8);
-        const float4 c0 = __ldg(cb), c1 = __ldg(cb + 1);
+    // software pipeline over batches of 8 sub-quantizers: the 16 codebook loads of batch b + 1 are issued before batch b is consumed
+    // (loop-carried, so the scheduler cannot sink them next to their uses); the loop is otherwise L2-latency bound (one CTA per SM)
+    float4 c0[8], c1[8];
 #pragma unroll
-        for (int qi = 0; qi < LQ; qi++) {
-            const float4 x0 = *reinterpret_cast<const float4*>(xs + qi * 256 + ml * 8);
-            const float4 x1 = *reinterpret_cast<const float4*>(xs + qi * 256 + ml * 8 + 4);
-            float acc = 0.0f;                            // one sequential FMA chain over the 8 sub-dimensions (compute_inner_prod_table)
-            acc = fmaf(x0.x, c0.x, acc); acc = fmaf(x0.y, c0.y, acc); acc = fmaf(x0.z, c0.z, acc); acc = fmaf(x0.w, c0.w, acc);
-            acc = fmaf(x1.x, c1.x, acc); acc = fmaf(x1.y, c1.y, acc); acc = fmaf(x1.z, c1.z, acc); acc = fmaf(x1.w, c1.w, acc);
-            tile[(qi * 32 + ml) * LUT_TILE_LD + j] = acc;
+    for (int u = 0; u < 8; u++) {
+        const float4* cb = reinterpret_cast<const float4*>(pq + ((size_t)(seg * 32 + u) * 256 + j) * 8);
+        c0[u] = __ldg(cb); c1[u] = __ldg(cb + 1);
+    }
+#pragma unroll 1
+    for (int ml0 = 0; ml0 < 32; ml0 += 8) {
+        float4 n0[8], n1[8];
+        if (ml0 + 8 < 32) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const float4* cb = reinterpret_cast<const float4*>(pq + ((size_t)(seg * 32 + ml0 + 8 + u) * 256 + j) * 8);
+                n0[u] = __ldg(cb); n1[u] = __ldg(cb + 1);
+            }
         }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int ml = ml0 + u;
+#pragma unroll
+            for (int qi = 0; qi < LQ; qi++) {
+                const float4 x0 = *reinterpret_cast<const float4*>(xs + qi * 256 + ml * 8);
+                const float4 x1 = *reinterpret_cast<const float4*>(xs + qi * 256 + ml * 8 + 4);
+                float acc = 0.0f;                        // one sequential FMA chain over the 8 sub-dimensions (compute_inner_prod_table)
+                acc = fmaf(x0.x, c0[u].x, acc); acc = fmaf(x0.y, c0[u].y, acc); acc = fmaf(x0.z, c0[u].z, acc); acc = fmaf(x0.w, c0[u].w, acc);
+                acc = fmaf(x1.x, c1[u].x, acc); acc = fmaf(x1.y, c1[u].y, acc); acc = fmaf(x1.z, c1[u].z, acc); acc = fmaf(x1.w, c1[u].w, acc);
+                tile[(qi * 32 + ml) * LUT_TILE_LD + j] = acc;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) { c0[u] = n0[u]; c1[u] = n1[u]; }
     }
     __syncthreads();
     // per (query, sub-quantizer): max |entry|, min, max over the 256 codes -- one warp per pair, 8 entries per lane
@@ -596,7 +624,7 @@ __global__ void __launch_bounds__(256) lutq_kernel(const float* __restrict__ lut
 int dph_launch_lut(const float* xr, int64_t n, const float* pq, float* lut_canon, float* lutmax, float* lutmin, float* lutmaxv,
                    void* lutq, float2* qparams, cudaStream_t st, int group) {
     if (n == 0) return 0;
-    const size_t lut_smem = (size_t)(LQ * 32 * LUT_TILE_LD + LQ * 256) * 4;
+    const size_t lut_smem = (size_t)(LQ * 32 * LUT_TILE_LD) * 4;
     static DphPerDeviceOnce lut_once;
     if (lut_once.first()) { DPH_CUDA(cudaFuncSetAttribute(lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_smem)); }
     lut_kernel<<<dim3((unsigned)((n + LQ - 1) / LQ), 3), 256, lut_smem, st>>>(xr, pq, n, lut_canon, lutmax, lutmin, lutmaxv);

@@ -66,18 +66,22 @@ template <int IMM> __device__ __forceinline__ float lds_imm(unsigned addr) {
     asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(IMM));
     return v;
 }
-template <int T0> __device__ __forceinline__ void fast_word(unsigned wv, unsigned y, float& a0, float& a1, float& a2, float& a3) {
+// The four running sums live in two float2 registers and advance with packed FADD2 (add.rn.f32x2: two independent IEEE fp32 adds per
+// instruction) -- the same per-component summation order as four scalar accumulators, half the FP32-pipe instructions.
+template <int T0> __device__ __forceinline__ void fast_word(unsigned wv, unsigned y, float2& a01, float2& a23) {
     constexpr int TB = DPH_DYN_SMEM_BASE + (T0 >> 5) * 65536 + (T0 & 31) * 4;   // T0 % 4 == 0: the 4 bytes share a table
-    a0 += lds_imm<TB + 0>(__byte_perm(wv, y, 0x7504));
-    a1 += lds_imm<TB + 4>(__byte_perm(wv, y, 0x7514));
-    a2 += lds_imm<TB + 8>(__byte_perm(wv, y, 0x7524));
-    a3 += lds_imm<TB + 12>(__byte_perm(wv, y, 0x7534));
+    const float v0 = lds_imm<TB + 0>(__byte_perm(wv, y, 0x7504));
+    const float v1 = lds_imm<TB + 4>(__byte_perm(wv, y, 0x7514));
+    const float v2 = lds_imm<TB + 8>(__byte_perm(wv, y, 0x7524));
+    const float v3 = lds_imm<TB + 12>(__byte_perm(wv, y, 0x7534));
+    a01 = __fadd2_rn(a01, make_float2(v0, v1));
+    a23 = __fadd2_rn(a23, make_float2(v2, v3));
 }
-template <int C> __device__ __forceinline__ void fast_chunk(const uint4& v, unsigned y, float& a0, float& a1, float& a2, float& a3) {
-    fast_word<C * 16 + 0>(v.x, y, a0, a1, a2, a3);
-    fast_word<C * 16 + 4>(v.y, y, a0, a1, a2, a3);
-    fast_word<C * 16 + 8>(v.z, y, a0, a1, a2, a3);
-    fast_word<C * 16 + 12>(v.w, y, a0, a1, a2, a3);
+template <int C> __device__ __forceinline__ void fast_chunk(const uint4& v, unsigned y, float2& a01, float2& a23) {
+    fast_word<C * 16 + 0>(v.x, y, a01, a23);
+    fast_word<C * 16 + 4>(v.y, y, a01, a23);
+    fast_word<C * 16 + 8>(v.z, y, a01, a23);
+    fast_word<C * 16 + 12>(v.w, y, a01, a23);
 }
 
 // Segment cursor: blocks are visited in increasing order, so a forward-only cursor finds the segment of work block b
@@ -220,14 +224,14 @@ __global__ void __launch_bounds__(NT, 1) scan_kernel(ScanArgs a) {
                 }
                 float score;
                 if (MODE == DPH_SCAN_FAST) {
-                    float acc0 = c_dis0, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-                    fast_chunk<0>(cur[0], ywin, acc0, acc1, acc2, acc3);
-                    fast_chunk<1>(cur[1], ywin, acc0, acc1, acc2, acc3);
-                    fast_chunk<2>(cur[2], ywin, acc0, acc1, acc2, acc3);
-                    fast_chunk<3>(cur[3], ywin, acc0, acc1, acc2, acc3);
-                    fast_chunk<4>(cur[4], ywin, acc0, acc1, acc2, acc3);
-                    fast_chunk<5>(cur[5], ywin, acc0, acc1, acc2, acc3);
-                    score = (acc0 + acc1) + (acc2 + acc3);
+                    float2 a01 = make_float2(c_dis0, 0.f), a23 = make_float2(0.f, 0.f);
+                    fast_chunk<0>(cur[0], ywin, a01, a23);
+                    fast_chunk<1>(cur[1], ywin, a01, a23);
+                    fast_chunk<2>(cur[2], ywin, a01, a23);
+                    fast_chunk<3>(cur[3], ywin, a01, a23);
+                    fast_chunk<4>(cur[4], ywin, a01, a23);
+                    fast_chunk<5>(cur[5], ywin, a01, a23);
+                    score = (a01.x + a01.y) + (a23.x + a23.y);
                 } else {
                     unsigned char* stage = smem + DPH_LUT_CANON_FLOATS * 4 + warp * DPH_BLK_BYTES;
                     const float* lutc = reinterpret_cast<const float*>(smem);
@@ -501,6 +505,7 @@ struct QuadShared {
     unsigned long long cbuf[4][QCAP];
     SelectScratch sc;
     int cnt[4]; unsigned thr[4]; int base[4]; int ndone; int ndone_snap; int unit; int full;
+    long long qs[4];                 // the group's queries (shared copy: indexed by thread id in the publish step)
 };
 template <int T0> __device__ __forceinline__ void quad_word(unsigned wv, unsigned y, unsigned (&sr)[4], unsigned (&ab)[4]) {
     constexpr int TB = DPH_DYN_SMEM_BASE + (T0 >> 5) * 65536 + (T0 & 31) * 4;
@@ -544,11 +549,15 @@ __global__ void __launch_bounds__(NT, 1) scan_quad_kernel(PairScanArgs a) {
     const unsigned ywin = (((unsigned)__cvta_generic_to_shared(dph_smem)) & 0xFF000000u) | ((unsigned)lane * 4u);
     const unsigned char* lut8 = reinterpret_cast<const unsigned char*>(a.lutq);
 
+    // Unit queue: the index of the NEXT unit is requested while the current one is being scanned (the L2 atomic's round trip, like
+    // the four candidate-count atomics of the publish step below, would otherwise sit on every item's critical path).
+    if (tid == 0) sh->unit = atomicAdd(a.next_unit, 1);
+    __syncthreads();
     while (true) {
-        if (tid == 0) sh->unit = atomicAdd(a.next_unit, 1);
-        __syncthreads();
         const int u = sh->unit;
         if (u >= total_units) break;
+        int next_u = 0;
+        if (tid == 0) next_u = atomicAdd(a.next_unit, 1);          // consumed at the end of this item
         const unsigned long long ud = a.units[u];
         const long long l = (long long)(ud & 0xFFFFFFFFull);
         const int it = (int)((ud >> 32) & 0xFFFFull);
@@ -571,7 +580,7 @@ __global__ void __launch_bounds__(NT, 1) scan_quad_kernel(PairScanArgs a) {
             const unsigned* T2p = reinterpret_cast<const unsigned*>(lut8 + (size_t)qv[2] * DPH_LUT_SCAN_FLOATS);
             const unsigned* T3p = reinterpret_cast<const unsigned*>(lut8 + (size_t)qv[3] * DPH_LUT_SCAN_FLOATS);
             uint4* dst = reinterpret_cast<uint4*>(smem);
-#pragma unroll 4
+#pragma unroll 8
             for (int i = tid; i < DPH_LUT_SCAN_FLOATS / 4; i += NT) {
                 const unsigned va = __ldg(T0p + i);
                 const unsigned vb = nq > 1 ? __ldg(T1p + i) : 0u;
@@ -588,7 +597,7 @@ __global__ void __launch_bounds__(NT, 1) scan_quad_kernel(PairScanArgs a) {
         if (tid == 0) {
             sh->ndone = 0; sh->ndone_snap = 0; sh->full = 0;
 #pragma unroll
-            for (int i = 0; i < 4; i++) { sh->cnt[i] = 0; sh->thr[i] = i < nq ? *((volatile unsigned*)(a.gthr + qv[i])) : 0xFFFFFFFFu; }
+            for (int i = 0; i < 4; i++) { sh->cnt[i] = 0; sh->qs[i] = qv[i]; sh->thr[i] = i < nq ? *((volatile unsigned*)(a.gthr + qv[i])) : 0xFFFFFFFFu; }
         }
         __syncthreads();
         float stepv[4], basev[4]; unsigned gsv[4];
@@ -672,18 +681,20 @@ __global__ void __launch_bounds__(NT, 1) scan_quad_kernel(PairScanArgs a) {
             tf0 = thr_f(thr0); tf1 = thr_f(thr1); tf2 = thr_f(thr2); tf3 = thr_f(thr3);
             if (sh->ndone_snap == NW) break;
         }
-        // ---- publish the candidate sets ----
+        // ---- publish the candidate sets: the (up to) four region reservations go out together, one barrier ----
+        if (tid < nq) sh->base[tid] = atomicAdd(a.cand_cnt + sh->qs[tid], sh->cnt[tid]);
+        if (tid == 0) sh->unit = next_u;
+        __syncthreads();
 #pragma unroll 1
         for (int i = 0; i < nq; i++) {
-            const long long q = qv[i];
+            const long long q = sh->qs[i];
             const int cnt = sh->cnt[i];
-            if (tid == 0) sh->base[i] = atomicAdd(a.cand_cnt + q, cnt);
-            __syncthreads();
             const long long off = a.cand_off[q], cap = a.cand_off[q + 1] - off;
             const int basep = sh->base[i];
             for (int c = tid; c < cnt; c += NT)
                 if (basep + c < cap) a.cand[off + basep + c] = sh->cbuf[i][c];
         }
+        __syncthreads();             // buffers, counters and sh->unit are reused by the next item
     }
 }
 
