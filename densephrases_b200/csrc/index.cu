@@ -13,6 +13,12 @@ static thread_local std::string g_err;
 void dph_set_error(const std::string& msg) { g_err = msg; }
 DPH_API const char* dph_last_error(void) { return g_err.c_str(); }
 DPH_API int dph_version(void) { return 100; }
+int g_dph_tune[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+DPH_API int dph_set_tuning(int knob, int value) {
+    DPH_CHECK(knob >= 0 && knob < 8, "dph_set_tuning: unknown knob");
+    g_dph_tune[knob] = value;
+    return 0;
+}
 
 int DevBuf::ensure(size_t bytes) {
     if (bytes <= cap) return 0;
@@ -126,7 +132,7 @@ DPH_API void dph_index_free(dph_index* ix) {
     for (void* p : ptrs) if (p) cudaFree(p);
     DevBuf* bufs[] = {&ix->xdev, &ix->xr, &ix->S, &ix->key, &ix->cd, &ix->lut_canon, &ix->lutmax, &ix->segs, &ix->wpre, &ix->qinfo,
                       &ix->cand, &ix->cand_off, &ix->cand_cnt, &ix->gthr, &ix->flags, &ix->work, &ix->Dp, &ix->Ip, &ix->Gp, &ix->Dh, &ix->Ih, &ix->eps, &ix->nseg, &ix->lutmin, &ix->lutmaxv, &ix->lutq, &ix->qparams, &ix->gdense,
-                      &ix->pl_cnt, &ix->pl_fill, &ix->pl_off, &ix->pl_blockpre, &ix->pl_entries, &ix->pl_unitpre, &ix->pl_units, &ix->pairwork, &ix->csplit, &ix->xsplit, &ix->candkeys, &ix->cflags,
+                      &ix->pl_cnt, &ix->pl_fill, &ix->pl_off, &ix->pl_blockpre, &ix->pl_entries, &ix->pl_unitpre, &ix->pl_units, &ix->pl_udesc, &ix->pairwork, &ix->csplit, &ix->xsplit, &ix->candkeys, &ix->cflags,
                       &ix->rb_ids, &ix->rb_out, &ix->rb_found, &ix->ws_q, &ix->ws_id, &ix->ws_out, &ix->ws_xq};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < DPH_PROF_RING; i++) { if (ix->ev0[i]) cudaEventDestroy(ix->ev0[i]); if (ix->ev1[i]) cudaEventDestroy(ix->ev1[i]); }
@@ -398,6 +404,7 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
         DPH_TRY(ix->pl_unitpre.ensure((size_t)(ix->nlist + 1) * 4));
         // units <= sum_l items_l * (blocks_l / seg + 1) <= total_blocks / seg + items <= UNITS_PER_CTA * grid + n * nprobe
         DPH_TRY(ix->pl_units.ensure((size_t)(n * nprobe + DPH_PAIR_UNITS_PER_CTA * grid + 16) * 8));
+        if (group == 4) DPH_TRY(ix->pl_udesc.ensure((size_t)(n * nprobe + DPH_PAIR_UNITS_PER_CTA * grid + 16) * sizeof(DphUnit)));
         DPH_TRY(ix->pairwork.ensure(sizeof(DphPairWork)));
     }
     ix->last_n = n;

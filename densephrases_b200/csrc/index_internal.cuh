@@ -65,7 +65,7 @@ struct dph_index {
     // per-batch workspace
     DevBuf xdev, xr, S, key, cd, lut_canon, lutmax, segs, wpre, qinfo, cand, cand_off, cand_cnt, gthr, flags,
         work, Dp, Ip, Gp, Dh, Ih, eps, nseg,
-        lutmin, lutmaxv, lutq, qparams, gdense, pl_cnt, pl_fill, pl_off, pl_blockpre, pl_entries, pl_unitpre, pl_units, pairwork,
+        lutmin, lutmaxv, lutq, qparams, gdense, pl_cnt, pl_fill, pl_off, pl_blockpre, pl_entries, pl_unitpre, pl_units, pl_udesc, pairwork,
         csplit, xsplit, candkeys, cflags,
         rb_ids, rb_out, rb_found, ws_q, ws_id, ws_out, ws_xq;        // reconstruct_batch / window_scores staging (host-buffer calls)
     int64_t csplit_lo = -1, csplit_nl = -1;
@@ -78,6 +78,8 @@ struct dph_index {
     int64_t prof_n = 0;
 };
 
+// process-wide variant selection (dph_set_tuning, measurement hook): [0] quad-scan IMAD level, [1] SGEMM tile, [2] LUT kernel
+extern int g_dph_tune[8];
 // ---- prep.cu ----
 int dph_launch_sgemm_nt_seq(const float* X, int64_t n, const float* W, int64_t m, int K, float* out, cudaStream_t st);
 int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprobe, int32_t* key, float* cd, cudaStream_t st,

@@ -258,16 +258,17 @@ int dph_launch_sgemm_nt_seq(const float* X, int64_t n, const float* W, int64_t m
     if (n == 0 || m == 0) return 0;
     const bool k64 = (K % GRK) == 0;                       // the row-tiled kernels step k by 64
     dim3 grid((unsigned)((m + GBN - 1) / GBN), (unsigned)((n + GBM - 1) / GBM));
-    if ((long long)grid.x * grid.y >= 2 * 148) {
+    const int variant = g_dph_tune[1];
+    if (variant == 1 || (variant == 0 && (long long)grid.x * grid.y >= 2 * 148)) {
         sgemm_nt_seq_kernel<<<grid, 256, 0, st>>>(X, n, W, m, K, out);
         DPH_CUDA(cudaGetLastError());
         return 0;
     }
     // pick the row tile so that the grid covers the SMs a few times over (all CTAs co-resident: <= 24 KB of shared memory each)
     const long long ct = (m + 63) / 64;
-    if (!k64 || ct * ((n + 63) / 64) >= 3 * 148) {
+    if (!k64 || variant == 2 || (variant == 0 && ct * ((n + 63) / 64) >= 3 * 148)) {
         sgemm_nt_seq_small_kernel<<<dim3((unsigned)ct, (unsigned)((n + 63) / 64)), 256, 0, st>>>(X, n, W, m, K, out);
-    } else if (ct * ((n + 31) / 32) >= 2 * 148) {
+    } else if (variant == 3 || (variant == 0 && ct * ((n + 31) / 32) >= 2 * 148)) {
         sgemm_nt_seq_rows_kernel<2><<<dim3((unsigned)ct, (unsigned)((n + 31) / 32)), 256, 0, st>>>(X, n, W, m, K, out);
     } else {
         sgemm_nt_seq_rows_kernel<1><<<dim3((unsigned)ct, (unsigned)((n + 15) / 16)), 256, 0, st>>>(X, n, W, m, K, out);
@@ -584,6 +585,68 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ xr, 
     }
 }
 
+// Large batches (n >= 512): a CTA handles LW = 16 queries x 8 sub-quantizers.  Thread j keeps the 8 codebook entries of code j
+// (8 x 8 floats) in registers for all 16 queries, so the L2 -> SM codebook stream is n/16 x 786 KB (C4, 1024 queries: 50 MB instead of
+// 201 MB); its 8 table entries of a query are 32 contiguous bytes of the canonical row [code][m % 32] and go straight to global
+// memory (one full sector per thread), so the only shared memory is the 8 KB tile of the min / max reduction and several CTAs
+// share an SM (the 4-query kernel above needs 131 KB and runs one latency-bound CTA per SM).  Same arithmetic: one sequential FMA
+// chain over the 8 sub-dimensions per entry.
+#define LW 16
+__global__ void __launch_bounds__(256, 2) lut_wide_kernel(const float* __restrict__ xr, const float* __restrict__ pq, long long n,
+                                                           float* __restrict__ lut_canon,
+                                                           float* __restrict__ lutmax, float* __restrict__ lutmin, float* __restrict__ lutmaxv) {
+    __shared__ float tile[8 * 257];
+    __shared__ __align__(16) float xs[LW * 64];
+    const long long q0 = (long long)blockIdx.x * LW;
+    const int sb = blockIdx.y;                             // sub-quantizers [8 sb, 8 sb + 8)
+    const int j = threadIdx.x, lane = j & 31, warp = j >> 5;
+    const int nq = (int)((n - q0) < LW ? (n - q0) : LW);
+    for (int i = j; i < LW * 64; i += 256) { const int qi = i >> 6; xs[i] = qi < nq ? xr[(q0 + qi) * DPH_D + sb * 64 + (i & 63)] : 0.0f; }
+    float4 c0[8], c1[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const float4* cb = reinterpret_cast<const float4*>(pq + ((size_t)(sb * 8 + u) * 256 + j) * 8);
+        c0[u] = __ldg(cb); c1[u] = __ldg(cb + 1);
+    }
+    __syncthreads();
+    const int seg = sb >> 2, mo = (sb & 3) * 8;
+#pragma unroll 1
+    for (int qi = 0; qi < nq; qi++) {
+        float e[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const float4 x0 = *reinterpret_cast<const float4*>(xs + qi * 64 + u * 8);
+            const float4 x1 = *reinterpret_cast<const float4*>(xs + qi * 64 + u * 8 + 4);
+            float acc = 0.0f;
+            acc = fmaf(x0.x, c0[u].x, acc); acc = fmaf(x0.y, c0[u].y, acc); acc = fmaf(x0.z, c0[u].z, acc); acc = fmaf(x0.w, c0[u].w, acc);
+            acc = fmaf(x1.x, c1[u].x, acc); acc = fmaf(x1.y, c1[u].y, acc); acc = fmaf(x1.z, c1[u].z, acc); acc = fmaf(x1.w, c1[u].w, acc);
+            e[u] = acc;
+            tile[u * 257 + j] = acc;
+        }
+        float4* dst = reinterpret_cast<float4*>(lut_canon + (size_t)(q0 + qi) * DPH_LUT_CANON_FLOATS + (size_t)seg * (256 * 32) + j * 32 + mo);
+        dst[0] = make_float4(e[0], e[1], e[2], e[3]);
+        dst[1] = make_float4(e[4], e[5], e[6], e[7]);
+        __syncthreads();
+        {   // warp u: max |entry|, min, max of sub-quantizer 8 sb + u over the 256 codes
+            const float* row = tile + warp * 257;
+            float a = 0.0f, lo = row[lane], hi = lo;
+#pragma unroll
+            for (int t = 0; t < 8; t++) { const float v = row[lane + 32 * t]; a = fmaxf(a, fabsf(v)); lo = fminf(lo, v); hi = fmaxf(hi, v); }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, off));
+                lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+                hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+            }
+            if (lane == 0) {
+                const long long o = (q0 + qi) * DPH_M + sb * 8 + warp;
+                lutmax[o] = a; lutmin[o] = lo; lutmaxv[o] = hi;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // Quantised LUT for the pair-packed scan: qv[m][j] = round((LUT[m][j] - min_m) / step) in [0, 682], one step per query
 // (step = max_m range_m / 682) so that 96 entries sum below 2^16 and two queries' tables can share one 32-bit word.
 // Written in the scan layout ([3][256][64] u16); qparams[q] = (step, sum_m min_m).
@@ -627,7 +690,9 @@ int dph_launch_lut(const float* xr, int64_t n, const float* pq, float* lut_canon
     const size_t lut_smem = (size_t)(LQ * 32 * LUT_TILE_LD) * 4;
     static DphPerDeviceOnce lut_once;
     if (lut_once.first()) { DPH_CUDA(cudaFuncSetAttribute(lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_smem)); }
-    lut_kernel<<<dim3((unsigned)((n + LQ - 1) / LQ), 3), 256, lut_smem, st>>>(xr, pq, n, lut_canon, lutmax, lutmin, lutmaxv);
+    const int lv = g_dph_tune[2];
+    if (lv == 2 || (lv == 0 && n >= 512)) lut_wide_kernel<<<dim3((unsigned)((n + LW - 1) / LW), 12), 256, 0, st>>>(xr, pq, n, lut_canon, lutmax, lutmin, lutmaxv);
+    else lut_kernel<<<dim3((unsigned)((n + LQ - 1) / LQ), 3), 256, lut_smem, st>>>(xr, pq, n, lut_canon, lutmax, lutmin, lutmaxv);
     DPH_CUDA(cudaGetLastError());
     if (lutq) {
         if (group == 4) lutq_kernel<unsigned char, DPH_QMAX8><<<dim3((unsigned)n, 3), 256, 0, st>>>(lut_canon, lutmin, lutmaxv, (unsigned char*)lutq, qparams);
@@ -796,6 +861,8 @@ struct PairPlanArgs {
     int* cnt; int* fill; int* off; long long* blockpre; unsigned* entries; DphPairWork* work;
     int* unitpre; unsigned long long* units;
     int gsz;                       // queries per work item: 2 (pair-packed scan) or 4 (quad-packed scan)
+    DphUnit* udesc;                // quad mode (nullable): resolved unit descriptors, parallel to `units`
+    const long long* blk_off; const float* cd; const unsigned* gdense; const float2* qparams;
 };
 __global__ void pair_count_kernel(PairPlanArgs a) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -880,18 +947,42 @@ __global__ void __launch_bounds__(1024) pair_scan_kernel(PairPlanArgs a) {
     }
     if (tid == 0) { a.work->total_units = (int)ca; a.work->next_unit = 0; }
 }
-// one thread per list: unit = list | item << 32 | segment << 48, ordered (segment, item) inside the list
+// one thread per list: unit = list | item << 32 | segment << 48, ordered (segment, item) inside the list; quad mode also gets the
+// resolved descriptor of every unit (DphUnit)
 __global__ void pair_units_kernel(PairPlanArgs a) {
     const long long l = a.list_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= a.list_hi) return;
-    const int items = (a.cnt[l] + a.gsz - 1) / a.gsz;
+    const int cnt = a.cnt[l];
+    const int items = (cnt + a.gsz - 1) / a.gsz;
     if (items == 0) return;
     const long long segb = a.work->per, nb = (a.list_len[l] + 31) >> 5;
     const int nsegs = (int)((nb + segb - 1) / segb);
-    unsigned long long* u = a.units + a.unitpre[l];
-    for (int s = 0; s < nsegs; s++)
-        for (int it = 0; it < items; it++)
-            *u++ = (unsigned long long)l | ((unsigned long long)it << 32) | ((unsigned long long)s << 48);
+    const long long u0 = a.unitpre[l];
+    for (int it = 0; it < items; it++) {
+        DphUnit d;
+        if (a.udesc) {
+            d.blk = a.blk_off[l]; d.len = a.list_len[l]; d.list = (int)l; d.pad = 0;
+            d.nq = min(4, cnt - 4 * it);
+            const int e0 = a.off[l] + 4 * it;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const unsigned e = a.entries[e0 + (i < d.nq ? i : 0)];
+                const long long q = e >> 10; const int r = (int)(e & 1023u);
+                const float2 pp = a.qparams[q];
+                d.q[i] = (unsigned)q; d.gs[i] = a.gdense[q * a.nprobe + r];
+                d.base[i] = a.cd[q * a.nprobe + r] + pp.y; d.step[i] = pp.x;
+            }
+        }
+        for (int s = 0; s < nsegs; s++) {
+            const long long u = u0 + (long long)s * items + it;
+            a.units[u] = (unsigned long long)l | ((unsigned long long)it << 32) | ((unsigned long long)s << 48);
+            if (a.udesc) {
+                d.bi0 = (unsigned)(s * segb);
+                d.bend = (unsigned)((nb - (long long)d.bi0 < segb) ? nb : (long long)d.bi0 + segb);
+                a.udesc[u] = d;
+            }
+        }
+    }
 }
 __global__ void pair_fill_kernel(PairPlanArgs a) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -921,6 +1012,8 @@ int dph_launch_plan(dph_index* ix, int64_t n, int k, int keep, int grid, const i
         p.off = ix->pl_off.as<int>(); p.blockpre = ix->pl_blockpre.as<long long>(); p.entries = ix->pl_entries.as<unsigned>();
         p.work = ix->pairwork.as<DphPairWork>(); p.unitpre = ix->pl_unitpre.as<int>(); p.units = ix->pl_units.as<unsigned long long>();
         p.gsz = group;
+        p.udesc = group == 4 ? ix->pl_udesc.as<DphUnit>() : nullptr;
+        p.blk_off = (const long long*)ix->blk_off; p.cd = ix->cd.as<float>(); p.gdense = ix->gdense.as<unsigned>(); p.qparams = ix->qparams.as<float2>();
         DPH_CUDA(cudaMemsetAsync(p.cnt, 0, (size_t)ix->nlist * 4, st));
         DPH_CUDA(cudaMemsetAsync(p.fill, 0, (size_t)ix->nlist * 4, st));
         const unsigned nb = (unsigned)((p.nq_probes + 255) / 256);

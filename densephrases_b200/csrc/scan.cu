@@ -145,29 +145,6 @@ __global__ void __launch_bounds__(NT, 1) scan_kernel(ScanArgs a) {
         const long long gend = (a.qpre[q + 1] < g1) ? a.qpre[q + 1] : g1;
         const unsigned b0 = (unsigned)(g - qstart), b1 = (unsigned)(gend - qstart);
         __syncthreads();
-        // ---- stage this query's LUT into shared memory ----
-        {
-            const float4* src = reinterpret_cast<const float4*>(a.lut_canon + (size_t)q * DPH_LUT_CANON_FLOATS);
-            if (MODE == DPH_SCAN_FAST) {
-                // canonical rows [seg][code][32] -> scan rows [seg][code][64]: words 0..31 = the row, words 32..62 = its first 31
-                // entries again (the wrap copies that let lane l read word l + t without a modulo), word 63 unused.  One thread
-                // moves one float4; a quarter-warp writes 128 contiguous bytes of one row -> conflict-free.
-                float* dstf = reinterpret_cast<float*>(smem);
-#pragma unroll 4
-                for (int i = tid; i < DPH_LUT_CANON_FLOATS / 4; i += NT) {
-                    const float4 v = __ldg(src + i);
-                    const int row = i >> 3, w = (i & 7) * 4;              // row = seg * 256 + code
-                    float* r = dstf + row * 64;
-                    *reinterpret_cast<float4*>(r + w) = v;
-                    if (w < 28) *reinterpret_cast<float4*>(r + 32 + w) = v;
-                    else { r[60] = v.x; r[61] = v.y; r[62] = v.z; r[63] = 0.0f; }
-                }
-            } else {
-                float4* dst = reinterpret_cast<float4*>(smem);
-#pragma unroll 8
-                for (int i = tid; i < DPH_LUT_CANON_FLOATS / 4; i += NT) dst[i] = __ldg(src + i);
-            }
-        }
         {
             const int nsg0 = a.nseg[q];
             if (nsg0 <= DPH_SEG_SMEM) {
@@ -187,6 +164,7 @@ __global__ void __launch_bounds__(NT, 1) scan_kernel(ScanArgs a) {
         unsigned bp = b0 + warp;                          // next block this warp prefetches into L2
         uint4 nxt[6];
         int n_len = 0; unsigned n_gstart = 0, n_j0 = 0; float n_dis0 = 0.f;
+        // the first code blocks are requested BEFORE the LUT is staged: their HBM latency overlaps the staging
 #pragma unroll 1
         for (int r = 0; r < DPH_L2_PREFETCH_ROUNDS && bp < b1; r++, bp += NW) {
             pc.seek(tab, bp, a.codes);
@@ -200,6 +178,39 @@ __global__ void __launch_bounds__(NT, 1) scan_kernel(ScanArgs a) {
             for (int c6 = 0; c6 < 6; c6++) nxt[c6] = ldg_stream(p + c6 * 32);
             n_len = cc.len; n_gstart = cc.gstart; n_dis0 = cc.dis0; n_j0 = (b - cc.wrel) * 32u;
         }
+        // ---- stage this query's LUT into shared memory (twelve 16-byte loads in flight per thread) ----
+        {
+            const float4* src = reinterpret_cast<const float4*>(a.lut_canon + (size_t)q * DPH_LUT_CANON_FLOATS);
+            constexpr int PER_T = DPH_LUT_CANON_FLOATS / 4 / NT;      // 12
+            constexpr int LB = 12;
+            static_assert(PER_T % LB == 0, "LUT staging batches");
+            if (MODE == DPH_SCAN_FAST) {
+                // canonical rows [seg][code][32] -> scan rows [seg][code][64]: words 0..31 = the row, words 32..62 = its first 31
+                // entries again (the wrap copies that let lane l read word l + t without a modulo), word 63 unused.  One thread
+                // moves one float4; a quarter-warp writes 128 contiguous bytes of one row -> conflict-free.
+                float* dstf = reinterpret_cast<float*>(smem);
+#pragma unroll 1
+                for (int i0 = tid; i0 < DPH_LUT_CANON_FLOATS / 4; i0 += NT * LB) {
+                    float4 v[LB];
+#pragma unroll
+                    for (int e = 0; e < LB; e++) v[e] = __ldg(src + i0 + e * NT);
+#pragma unroll
+                    for (int e = 0; e < LB; e++) {
+                        const int i = i0 + e * NT;
+                        const int row = i >> 3, w = (i & 7) * 4;              // row = seg * 256 + code
+                        float* r = dstf + row * 64;
+                        *reinterpret_cast<float4*>(r + w) = v[e];
+                        if (w < 28) *reinterpret_cast<float4*>(r + 32 + w) = v[e];
+                        else { r[60] = v[e].x; r[61] = v[e].y; r[62] = v[e].z; r[63] = 0.0f; }
+                    }
+                }
+            } else {
+                float4* dst = reinterpret_cast<float4*>(smem);
+#pragma unroll 8
+                for (int i = tid; i < DPH_LUT_CANON_FLOATS / 4; i += NT) dst[i] = __ldg(src + i);
+            }
+        }
+        __syncthreads();
         bool counted = false;
         while (true) {      // epochs: run until the candidate buffer may overflow or this warp is out of blocks, then meet
             while (more) {
@@ -303,6 +314,8 @@ struct PairScanArgs {
     const unsigned short* lutq; const float2* qparams; const float* cd; const unsigned* gdense;
     unsigned* gthr; unsigned long long* cand; const long long* cand_off; int* cand_cnt;
     long long list_lo, list_hi; int nprobe; int keep;
+    const DphUnit* udesc;          // quad mode: resolved unit records (plan)
+    unsigned one;                  // the constant 1, as a run-time value (imad_add)
 };
 #define PCAP 1536
 struct PairShared {
@@ -504,10 +517,21 @@ __global__ void __launch_bounds__(NT, 1) scan_pair_kernel(PairScanArgs a) {
 struct QuadShared {
     unsigned long long cbuf[4][QCAP];
     SelectScratch sc;
+    DphUnit desc[2];                 // current item / next item (fetched with cp.async while the current one is scanned)
     int cnt[4]; unsigned thr[4]; int base[4]; int ndone; int ndone_snap; int unit; int full;
     long long qs[4];                 // the group's queries (shared copy: indexed by thread id in the publish step)
 };
-template <int T0> __device__ __forceinline__ void quad_word(unsigned wv, unsigned y, unsigned (&sr)[4], unsigned (&ab)[4]) {
+// 32-bit add on the FMA pipe: d = a * one + c with `one` a kernel parameter holding 1 (opaque to ptxas, so the multiply-add is not
+// folded back into an IADD3).  The quad scan is bound by the ALU pipe (PRMT + IADD3, one warp instruction per two cycles per
+// sub-partition, B300_MICROARCH "fma vs alu split"); IMAD issues on the otherwise idle FMA pipe at the same rate.
+__device__ __forceinline__ unsigned imad_add(unsigned x, unsigned one, unsigned c) {
+    unsigned d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(one), "r"(c));
+    return d;
+}
+// IMADL: how many of the running-sum additions go to the FMA pipe: 0 = none (all IADD3), 1 = the raw sums, 2 = the raw sums and
+// half of the odd-byte sums, 3 = all of them.
+template <int T0, int IMADL> __device__ __forceinline__ void quad_word(unsigned wv, unsigned y, unsigned one, unsigned (&sr)[4], unsigned (&ab)[4]) {
     constexpr int TB = DPH_DYN_SMEM_BASE + (T0 >> 5) * 65536 + (T0 & 31) * 4;
     constexpr int A = (T0 >> 2) & 1;                  // two accumulator sets, alternating per code word
     const unsigned w0 = lds_imm_u32<TB + 0>(__byte_perm(wv, y, 0x7504));
@@ -515,18 +539,30 @@ template <int T0> __device__ __forceinline__ void quad_word(unsigned wv, unsigne
     const unsigned w2 = lds_imm_u32<TB + 8>(__byte_perm(wv, y, 0x7524));
     const unsigned w3 = lds_imm_u32<TB + 12>(__byte_perm(wv, y, 0x7534));
     // 8-bit entries: the odd bytes are widened per gather (a lane-wise add of two words could carry).  A 7-bit variant that widens
-    // once per TWO gathers is 11 % faster (ncu r2d: the INT pipe -- PRMT, IADD3 at half rate -- bounds this kernel) but doubles eps,
-    // and then the exactness proof fails for ~10 % of the queries at C2 (measured); the exact fallback costs far more than it saves.
-    sr[2 * A] += w0 + w1;
-    sr[2 * A + 1] += w2 + w3;
-    ab[2 * A] += __byte_perm(w0, 0u, 0x4341) + __byte_perm(w1, 0u, 0x4341);
-    ab[2 * A + 1] += __byte_perm(w2, 0u, 0x4341) + __byte_perm(w3, 0u, 0x4341);
+    // once per TWO gathers is 11 % faster (ncu r2d) but doubles eps, and then the exactness proof fails for ~10 % of the queries at
+    // C2 (measured); the exact fallback costs far more than it saves.
+    if (IMADL >= 1) {
+        sr[2 * A] = imad_add(w1, one, imad_add(w0, one, sr[2 * A]));
+        sr[2 * A + 1] = imad_add(w3, one, imad_add(w2, one, sr[2 * A + 1]));
+    } else {
+        sr[2 * A] += w0 + w1;
+        sr[2 * A + 1] += w2 + w3;
+    }
+    const unsigned e0 = __byte_perm(w0, 0u, 0x4341), e1 = __byte_perm(w1, 0u, 0x4341);
+    const unsigned e2 = __byte_perm(w2, 0u, 0x4341), e3 = __byte_perm(w3, 0u, 0x4341);
+    if (IMADL >= 3 || (IMADL == 2 && A == 1)) {
+        ab[2 * A] = imad_add(e1, one, imad_add(e0, one, ab[2 * A]));
+        ab[2 * A + 1] = imad_add(e3, one, imad_add(e2, one, ab[2 * A + 1]));
+    } else {
+        ab[2 * A] += e0 + e1;
+        ab[2 * A + 1] += e2 + e3;
+    }
 }
-template <int C> __device__ __forceinline__ void quad_chunk(const uint4& v, unsigned y, unsigned (&sr)[4], unsigned (&ab)[4]) {
-    quad_word<C * 16 + 0>(v.x, y, sr, ab);
-    quad_word<C * 16 + 4>(v.y, y, sr, ab);
-    quad_word<C * 16 + 8>(v.z, y, sr, ab);
-    quad_word<C * 16 + 12>(v.w, y, sr, ab);
+template <int C, int IMADL> __device__ __forceinline__ void quad_chunk(const uint4& v, unsigned y, unsigned one, unsigned (&sr)[4], unsigned (&ab)[4]) {
+    quad_word<C * 16 + 0, IMADL>(v.x, y, one, sr, ab);
+    quad_word<C * 16 + 4, IMADL>(v.y, y, one, sr, ab);
+    quad_word<C * 16 + 8, IMADL>(v.z, y, one, sr, ab);
+    quad_word<C * 16 + 12, IMADL>(v.w, y, one, sr, ab);
 }
 // append with an overflow latch: the round loop polls ONE flag instead of every buffer's counter
 __device__ __forceinline__ void warp_append_latch(bool pass, unsigned long long key, unsigned long long* cb, int* cnt, int* full, int lane) {
@@ -539,79 +575,46 @@ __device__ __forceinline__ void warp_append_latch(bool pass, unsigned long long 
         if (pass) { int p = basep + __popc(pm & ((1u << lane) - 1u)); if (p < QCAP) cb[p] = key; }
     }
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
 
+// Item start-up is kept off the critical path (at C2 / C4 list lengths an item is only 30-50 rounds long): the plan resolves every
+// unit into one DphUnit record; the record of the NEXT unit is fetched into shared memory with cp.async while the current one is
+// scanned (its queue index was requested at the start of the current item); the first code blocks of an item are requested BEFORE the
+// packed LUT is built, so the HBM latency overlaps the build; the build reads only the 32 real bytes of every 64-byte table row and
+// writes the wrap copy itself (half the L2 traffic).
+template <int IMADL>
 __global__ void __launch_bounds__(NT, 1) scan_quad_kernel(PairScanArgs a) {
     unsigned char* const smem = dph_smem;
     QuadShared* sh = reinterpret_cast<QuadShared*>(smem + SMEM_LUT_FAST);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int total_units = a.work->total_units;
-    const unsigned segb = (unsigned)a.work->per;
     const unsigned ywin = (((unsigned)__cvta_generic_to_shared(dph_smem)) & 0xFF000000u) | ((unsigned)lane * 4u);
     const unsigned char* lut8 = reinterpret_cast<const unsigned char*>(a.lutq);
+    const unsigned one = a.one;
 
-    // Unit queue: the index of the NEXT unit is requested while the current one is being scanned (the L2 atomic's round trip, like
-    // the four candidate-count atomics of the publish step below, would otherwise sit on every item's critical path).
     if (tid == 0) sh->unit = atomicAdd(a.next_unit, 1);
     __syncthreads();
-    while (true) {
+    {
         const int u = sh->unit;
-        if (u >= total_units) break;
+        if (u >= total_units) return;
+        if (tid < (int)(sizeof(DphUnit) / 16)) reinterpret_cast<uint4*>(&sh->desc[0])[tid] = __ldg(reinterpret_cast<const uint4*>(a.udesc + u) + tid);
+    }
+    __syncthreads();
+    int cur = 0;
+    while (true) {
         int next_u = 0;
-        if (tid == 0) next_u = atomicAdd(a.next_unit, 1);          // consumed at the end of this item
-        const unsigned long long ud = a.units[u];
-        const long long l = (long long)(ud & 0xFFFFFFFFull);
-        const int it = (int)((ud >> 32) & 0xFFFFull);
-        const int len = a.list_len[l];
-        const unsigned nb = (unsigned)((len + 31) >> 5);
-        const unsigned bi0 = (unsigned)(ud >> 48) * segb;
-        const unsigned bend = (nb - bi0 < segb) ? nb : bi0 + segb;
-        const int e0 = a.pl_off[l] + 4 * it;
-        const int nq = min(4, a.pl_cnt[l] - 4 * it);          // queries in this group (1..4)
-        long long qv[4]; int rv[4];
+        if (tid == 0) next_u = atomicAdd(a.next_unit, 1);          // consumed after the LUT build (fetch of the next record)
+        const DphUnit* dsc = &sh->desc[cur];
+        const int len = dsc->len, nq = dsc->nq;
+        const unsigned bi0 = dsc->bi0, bend = dsc->bend;
+        const uint4* lbase = reinterpret_cast<const uint4*>(a.codes + dsc->blk * DPH_BLK_BYTES);
+        unsigned qv[4], gsv[4]; float stepv[4], basev[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const unsigned e = a.entries[e0 + (i < nq ? i : 0)];
-            qv[i] = e >> 10; rv[i] = (int)(e & 1023u);
-        }
-        __syncthreads();
-        {   // ---- packed LUT: byte i of every word = query i's 8-bit entry, same [3][256][64] scan layout ----
-            const unsigned* T0p = reinterpret_cast<const unsigned*>(lut8 + (size_t)qv[0] * DPH_LUT_SCAN_FLOATS);
-            const unsigned* T1p = reinterpret_cast<const unsigned*>(lut8 + (size_t)qv[1] * DPH_LUT_SCAN_FLOATS);
-            const unsigned* T2p = reinterpret_cast<const unsigned*>(lut8 + (size_t)qv[2] * DPH_LUT_SCAN_FLOATS);
-            const unsigned* T3p = reinterpret_cast<const unsigned*>(lut8 + (size_t)qv[3] * DPH_LUT_SCAN_FLOATS);
-            uint4* dst = reinterpret_cast<uint4*>(smem);
-#pragma unroll 8
-            for (int i = tid; i < DPH_LUT_SCAN_FLOATS / 4; i += NT) {
-                const unsigned va = __ldg(T0p + i);
-                const unsigned vb = nq > 1 ? __ldg(T1p + i) : 0u;
-                const unsigned vc = nq > 2 ? __ldg(T2p + i) : 0u;
-                const unsigned vd = nq > 3 ? __ldg(T3p + i) : 0u;
-                const unsigned t0 = __byte_perm(va, vb, 0x5140), t1 = __byte_perm(va, vb, 0x7362);     // [a0 b0 a1 b1], [a2 b2 a3 b3]
-                const unsigned u0 = __byte_perm(vc, vd, 0x5140), u1 = __byte_perm(vc, vd, 0x7362);
-                uint4 o;
-                o.x = __byte_perm(t0, u0, 0x5410); o.y = __byte_perm(t0, u0, 0x7632);
-                o.z = __byte_perm(t1, u1, 0x5410); o.w = __byte_perm(t1, u1, 0x7632);
-                dst[i] = o;
-            }
-        }
-        if (tid == 0) {
-            sh->ndone = 0; sh->ndone_snap = 0; sh->full = 0;
-#pragma unroll
-            for (int i = 0; i < 4; i++) { sh->cnt[i] = 0; sh->qs[i] = qv[i]; sh->thr[i] = i < nq ? *((volatile unsigned*)(a.gthr + qv[i])) : 0xFFFFFFFFu; }
-        }
-        __syncthreads();
-        float stepv[4], basev[4]; unsigned gsv[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const float2 pp = a.qparams[qv[i]];
-            stepv[i] = pp.x; basev[i] = a.cd[qv[i] * a.nprobe + rv[i]] + pp.y; gsv[i] = a.gdense[qv[i] * a.nprobe + rv[i]];
-        }
-        const uint4* lbase = reinterpret_cast<const uint4*>(a.codes + a.blk_off[l] * DPH_BLK_BYTES);
-        unsigned thr0 = sh->thr[0], thr1 = sh->thr[1], thr2 = sh->thr[2], thr3 = sh->thr[3];     // refreshed after every barrier
-        // float images of the thresholds (0xFFFFFFFF = "never passes" for the empty slots of a short group -> +inf)
-        auto thr_f = [](unsigned t) { return t == 0xFFFFFFFFu ? __int_as_float(0x7f800000) : (t == 0u ? -__int_as_float(0x7f800000) : dph_fkey_inv(t)); };
-        float tf0 = thr_f(thr0), tf1 = thr_f(thr1), tf2 = thr_f(thr2), tf3 = thr_f(thr3);
+        for (int i = 0; i < 4; i++) { qv[i] = dsc->q[i]; gsv[i] = dsc->gs[i]; basev[i] = dsc->base[i]; stepv[i] = dsc->step[i]; }
 
+        // ---- first code blocks: L2 prefetch + this warp's first block into registers, in flight during the LUT build ----
         unsigned b = bi0 + warp, bp = bi0 + warp;
         uint4 nxt[6];
 #pragma unroll 1
@@ -623,13 +626,59 @@ __global__ void __launch_bounds__(NT, 1) scan_quad_kernel(PairScanArgs a) {
 #pragma unroll
             for (int c6 = 0; c6 < 6; c6++) nxt[c6] = ldg_stream(p + c6 * 32);
         }
+        unsigned g4[4] = {0u, 0u, 0u, 0u};
+        if (tid == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) g4[i] = i < nq ? *((volatile unsigned*)(a.gthr + qv[i])) : 0xFFFFFFFFu;
+        }
+        {   // ---- packed LUT: byte i of every word = query i's 8-bit entry, [3][256][64] scan layout (words 32..62 = words 0..30) ----
+            const unsigned* T0p = reinterpret_cast<const unsigned*>(lut8 + (size_t)qv[0] * DPH_LUT_SCAN_FLOATS);
+            const unsigned* T1p = reinterpret_cast<const unsigned*>(lut8 + (size_t)qv[1] * DPH_LUT_SCAN_FLOATS);
+            const unsigned* T2p = reinterpret_cast<const unsigned*>(lut8 + (size_t)qv[2] * DPH_LUT_SCAN_FLOATS);
+            const unsigned* T3p = reinterpret_cast<const unsigned*>(lut8 + (size_t)qv[3] * DPH_LUT_SCAN_FLOATS);
+            uint4* dst = reinterpret_cast<uint4*>(smem);
+#pragma unroll 6
+            for (int i = tid; i < 768 * 8; i += NT) {              // (row, group of four real words): a quarter-warp moves one row
+                const int row = i >> 3, cg = i & 7;
+                const int src = row * 16 + cg;
+                const unsigned va = __ldg(T0p + src);
+                const unsigned vb = nq > 1 ? __ldg(T1p + src) : 0u;
+                const unsigned vc = nq > 2 ? __ldg(T2p + src) : 0u;
+                const unsigned vd = nq > 3 ? __ldg(T3p + src) : 0u;
+                const unsigned t0 = __byte_perm(va, vb, 0x5140), t1 = __byte_perm(va, vb, 0x7362);     // [a0 b0 a1 b1], [a2 b2 a3 b3]
+                const unsigned u0 = __byte_perm(vc, vd, 0x5140), u1 = __byte_perm(vc, vd, 0x7362);
+                uint4 o;
+                o.x = __byte_perm(t0, u0, 0x5410); o.y = __byte_perm(t0, u0, 0x7632);
+                o.z = __byte_perm(t1, u1, 0x5410); o.w = __byte_perm(t1, u1, 0x7632);
+                dst[row * 16 + cg] = o;
+                dst[row * 16 + 8 + cg] = o;                        // wrap copy (word 63 = word 31: never read)
+            }
+        }
+        if (tid == 0) {
+            sh->ndone = 0; sh->ndone_snap = 0; sh->full = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) { sh->cnt[i] = 0; sh->qs[i] = (long long)qv[i]; sh->thr[i] = g4[i]; }
+        }
+        __syncthreads();
+        if (warp == 0) {          // the next unit's record -> the other descriptor slot (waited for at the end of this item)
+            const int nu = __shfl_sync(0xffffffffu, next_u, 0);
+            if (lane == 0) sh->unit = nu;
+            if (nu < total_units && lane < (int)(sizeof(DphUnit) / 16))
+                cp_async16(reinterpret_cast<unsigned char*>(&sh->desc[cur ^ 1]) + lane * 16, reinterpret_cast<const unsigned char*>(a.udesc + nu) + lane * 16);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        unsigned thr0 = sh->thr[0], thr1 = sh->thr[1], thr2 = sh->thr[2], thr3 = sh->thr[3];     // refreshed after every barrier
+        // float images of the thresholds (0xFFFFFFFF = "never passes" for the empty slots of a short group -> +inf)
+        auto thr_f = [](unsigned t) { return t == 0xFFFFFFFFu ? __int_as_float(0x7f800000) : (t == 0u ? -__int_as_float(0x7f800000) : dph_fkey_inv(t)); };
+        float tf0 = thr_f(thr0), tf1 = thr_f(thr1), tf2 = thr_f(thr2), tf3 = thr_f(thr3);
+
         bool counted = false;
         while (true) {
             while (more) {
                 if (*((volatile int*)&sh->full)) break;
-                uint4 cur[6];
+                uint4 cur6[6];
 #pragma unroll
-                for (int c6 = 0; c6 < 6; c6++) cur[c6] = nxt[c6];
+                for (int c6 = 0; c6 < 6; c6++) cur6[c6] = nxt[c6];
                 const unsigned bcur = b;
                 if (bp < bend) { if (lane == 0) l2_prefetch_block(lbase + (size_t)bp * (DPH_BLK_BYTES / 16)); bp += NW; }
                 b += NW;
@@ -640,12 +689,12 @@ __global__ void __launch_bounds__(NT, 1) scan_quad_kernel(PairScanArgs a) {
                     for (int c6 = 0; c6 < 6; c6++) nxt[c6] = ldg_stream(p + c6 * 32);
                 }
                 unsigned sr[4] = {0u, 0u, 0u, 0u}, ab[4] = {0u, 0u, 0u, 0u};
-                quad_chunk<0>(cur[0], ywin, sr, ab);
-                quad_chunk<1>(cur[1], ywin, sr, ab);
-                quad_chunk<2>(cur[2], ywin, sr, ab);
-                quad_chunk<3>(cur[3], ywin, sr, ab);
-                quad_chunk<4>(cur[4], ywin, sr, ab);
-                quad_chunk<5>(cur[5], ywin, sr, ab);
+                quad_chunk<0, IMADL>(cur6[0], ywin, one, sr, ab);
+                quad_chunk<1, IMADL>(cur6[1], ywin, one, sr, ab);
+                quad_chunk<2, IMADL>(cur6[2], ywin, one, sr, ab);
+                quad_chunk<3, IMADL>(cur6[3], ywin, one, sr, ab);
+                quad_chunk<4, IMADL>(cur6[4], ywin, one, sr, ab);
+                quad_chunk<5, IMADL>(cur6[5], ywin, one, sr, ab);
                 const unsigned SR = (sr[0] + sr[1]) + (sr[2] + sr[3]);
                 const unsigned AB = (ab[0] + ab[1]) + (ab[2] + ab[3]);          // S1 | S3 << 16
                 const unsigned AE = SR - (AB << 8);                             // S0 | S2 << 16
@@ -670,9 +719,9 @@ __global__ void __launch_bounds__(NT, 1) scan_quad_kernel(PairScanArgs a) {
             __syncthreads();
 #pragma unroll 1
             for (int i = 0; i < nq; i++)
-                if (sh->cnt[i] > a.keep) compact_buffer<QCAP>(sh->cbuf[i], &sh->cnt[i], &sh->thr[i], a.keep, a.gthr + qv[i], &sh->sc);
+                if (sh->cnt[i] > a.keep) compact_buffer<QCAP>(sh->cbuf[i], &sh->cnt[i], &sh->thr[i], a.keep, a.gthr + sh->qs[i], &sh->sc);
             if (tid == 0) {
-                for (int i = 0; i < nq; i++) { unsigned g = *((volatile unsigned*)(a.gthr + qv[i])); if (g > sh->thr[i]) sh->thr[i] = g; }
+                for (int i = 0; i < nq; i++) { unsigned g = *((volatile unsigned*)(a.gthr + sh->qs[i])); if (g > sh->thr[i]) sh->thr[i] = g; }
                 sh->ndone_snap = sh->ndone;
                 sh->full = 0;
             }
@@ -683,7 +732,7 @@ __global__ void __launch_bounds__(NT, 1) scan_quad_kernel(PairScanArgs a) {
         }
         // ---- publish the candidate sets: the (up to) four region reservations go out together, one barrier ----
         if (tid < nq) sh->base[tid] = atomicAdd(a.cand_cnt + sh->qs[tid], sh->cnt[tid]);
-        if (tid == 0) sh->unit = next_u;
+        if (warp == 0) asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
 #pragma unroll 1
         for (int i = 0; i < nq; i++) {
@@ -694,7 +743,10 @@ __global__ void __launch_bounds__(NT, 1) scan_quad_kernel(PairScanArgs a) {
             for (int c = tid; c < cnt; c += NT)
                 if (basep + c < cap) a.cand[off + basep + c] = sh->cbuf[i][c];
         }
-        __syncthreads();             // buffers, counters and sh->unit are reused by the next item
+        const int un = sh->unit;
+        __syncthreads();             // buffers, counters, sh->unit and the descriptor slots are reused by the next item
+        if (un >= total_units) break;
+        cur ^= 1;
     }
 }
 
@@ -714,7 +766,10 @@ int dph_scan_setup_attrs() {
     DPH_CUDA(cudaFuncSetAttribute(scan_kernel<DPH_SCAN_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LUT_FAST + (int)sizeof(ScanShared)));
     DPH_CUDA(cudaFuncSetAttribute(scan_kernel<DPH_SCAN_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LUT_EXACT + (int)sizeof(ScanShared)));
     DPH_CUDA(cudaFuncSetAttribute(scan_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LUT_FAST + (int)sizeof(PairShared)));
-    DPH_CUDA(cudaFuncSetAttribute(scan_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LUT_FAST + (int)sizeof(QuadShared)));
+    DPH_CUDA(cudaFuncSetAttribute(scan_quad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LUT_FAST + (int)sizeof(QuadShared)));
+    DPH_CUDA(cudaFuncSetAttribute(scan_quad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LUT_FAST + (int)sizeof(QuadShared)));
+    DPH_CUDA(cudaFuncSetAttribute(scan_quad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LUT_FAST + (int)sizeof(QuadShared)));
+    DPH_CUDA(cudaFuncSetAttribute(scan_quad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LUT_FAST + (int)sizeof(QuadShared)));
     return 0;
 }
 
@@ -745,7 +800,16 @@ int dph_launch_scan_pair(dph_index* ix, int64_t n, int keep, int grid, cudaStrea
     a.cd = ix->cd.as<float>(); a.gdense = ix->gdense.as<unsigned>(); a.gthr = ix->gthr.as<unsigned>();
     a.cand = ix->cand.as<unsigned long long>(); a.cand_off = ix->cand_off.as<long long>(); a.cand_cnt = ix->cand_cnt.as<int>();
     a.list_lo = ix->list_lo; a.list_hi = ix->list_hi; a.nprobe = ix->nprobe; a.keep = keep;
-    if (group == 4) scan_quad_kernel<<<grid, NT, SMEM_LUT_FAST + sizeof(QuadShared), st>>>(a);
+    a.udesc = ix->pl_udesc.as<DphUnit>(); a.one = 1u;
+    if (group == 4) {
+        const size_t sm = SMEM_LUT_FAST + sizeof(QuadShared);
+        switch (g_dph_tune[0]) {
+            case 0: scan_quad_kernel<0><<<grid, NT, sm, st>>>(a); break;
+            case 2: scan_quad_kernel<2><<<grid, NT, sm, st>>>(a); break;
+            case 3: scan_quad_kernel<3><<<grid, NT, sm, st>>>(a); break;
+            default: scan_quad_kernel<1><<<grid, NT, sm, st>>>(a); break;
+        }
+    }
     else scan_pair_kernel<<<grid, NT, SMEM_LUT_FAST + sizeof(PairShared), st>>>(a);
     DPH_CUDA(cudaGetLastError());
     return 0;

@@ -22,8 +22,10 @@ from .encoder import BertGeometry, Encoder, random_state_dict
 from .mips import MIPS
 from .options import Options
 from .tokenization import WordPieceTokenizer
+from .truecase import TrueCaser, truecase_questions
 
 logger = logging.getLogger(__name__)
+_truecaser = None          # open_utils.py:23: one truecaser per process, loaded on first use
 
 
 # ---- eval_utils ------------------------------------------------------------------------------------------
@@ -192,7 +194,16 @@ def load_qa_pairs(data_path, args, q_idx=None, draft_num_examples=100, shuffle=F
         q_ids, questions, answers, titles = map(list, zip(*pack))
     if getattr(args, 'draft', False):
         q_ids, questions, answers, titles = (x[:draft_num_examples] for x in (q_ids, questions, answers, titles))
-    # truecasing needs $DATA_DIR/truecase/english_with_questions.dist (options.py:83); the reference swallows its absence too
+    if getattr(args, 'truecase', False):            # open_utils.py:147-156: a missing statistics file is reported, not fatal
+        try:
+            global _truecaser
+            if _truecaser is None:
+                logger.info('loading truecaser')
+                _truecaser = TrueCaser(os.path.join(os.environ['DATA_DIR'], args.truecase_path))
+            logger.info('Truecasing queries')
+            questions = truecase_questions(_truecaser, questions)
+        except Exception as e:
+            print(e)
     logger.info(f'Loading {len(questions)} questions from {data_path}')
     return q_ids, questions, answers, titles
 
@@ -248,7 +259,12 @@ class DensePhrases(object):
         self.args.__dict__.update(kwargs)
         self.set_encoder(load_dir, device)
         self.mips = mips if mips is not None else load_phrase_index(self.args, ignore_logging=not verbose)
-        self.truecase = None                     # TrueCaser needs $DATA_DIR/truecase/*.dist, absent offline (model.py:52)
+        # model.py:52 loads $DATA_DIR/<truecase_path> unconditionally; here a missing statistics file only disables truecasing
+        # (search(truecase=True) then leaves the queries as typed) -- pass truecase_path=... / set DATA_DIR to enable it
+        tc_path = os.path.join(os.environ.get('DATA_DIR', ''), self.args.truecase_path)
+        self.truecase = TrueCaser(tc_path) if os.path.exists(tc_path) else None
+        if self.truecase is None:
+            logger.warning(f'truecaser statistics {tc_path} not found: lower-case queries are searched as typed')
 
     def set_encoder(self, load_dir, device='cuda'):
         self.args.load_dir = load_dir
@@ -276,6 +292,11 @@ class DensePhrases(object):
         assert isinstance(batch_query, list)
         if retrieval_unit not in self._AGG:
             raise NotImplementedError(f'"{retrieval_unit}" not supported. Choose one of {self._AGG.keys()}.')
+        if truecase and self.truecase is not None:
+            # model.py:66-70 binds the truecased list to `query` and then encodes `batch_query`: in the reference the truecased text
+            # never reaches the encoder or the result dicts.  Reproduced as is (same results on the same inputs); the evaluation
+            # path (load_qa_pairs, open_utils.py:147-154) does use the truecased questions.
+            query = truecase_questions(self.truecase, batch_query)
         outs = self.query2vec(batch_query)
         query_vec = np.concatenate([np.concatenate([o[0] for o in outs], 0), np.concatenate([o[1] for o in outs], 0)], 1)
         search_top_k = top_k * 2 if retrieval_unit in ('sentence', 'paragraph', 'document') else top_k

@@ -171,6 +171,11 @@ int dph_gemm_tf32_nt(const float* A, const float* W, const float* bias, const fl
  * multicast (N/128 even);  2 (default): persistent CTAs walking 128x256 tiles with double-buffered TMEM accumulators and twelve
  * epilogue warps (N % 256 == 0, else mode 0). */
 int dph_gemm_tf32_set_mode(int mode);
+/* Measurement hook (process-wide): choose between kernel variants that compute bit-identical results, for A/B timing on hardware
+ * (tools/bench_variants.py).  knob 0: additions of the quad scan issued on the FMA pipe (0 none .. 3 all; default 1);
+ * knob 1: tile shape of the sequential-k SGEMM (0 auto, 1: 128x128, 2: 64x64, 3: 32x64, 4: 16x64);
+ * knob 2: PQ table kernel (0 auto, 1: 4 queries x 32 sub-quantizers per CTA, 2: 16 queries x 8 sub-quantizers per CTA). */
+int dph_set_tuning(int knob, int value);
 
 #ifdef __cplusplus
 }

@@ -349,3 +349,53 @@ def test_synthetic_dump_spec_objects(tmp_path):
     qa = SD.write_synthetic_questions(str(tmp_path / "q.json"), 5)
     import json as _json
     assert len(_json.load(open(qa))["data"]) == 5
+
+
+# ---- truecaser (squad_utils.py:1452-1585, model.py:52,66-67) ------------------------------------------------------
+def test_truecaser_matches_reference_golden():
+    """tests/golden/truecase.json was produced by the UNMODIFIED reference TrueCaser class on tests/golden/truecase.dist."""
+    import json
+    from densephrases_b200.truecase import TrueCaser, truecase_questions
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    tc = TrueCaser(os.path.join(here, "truecase.dist"))
+    gold = json.load(open(os.path.join(here, "truecase.json")))
+    for c in gold["cases"]:
+        assert tc.get_true_case(c["sentence"], c["oov"]) == c["truecased"], c
+    for s in gold["scores"]:
+        assert tc.get_score(s["prev"], s["token"], s["next"]) == s["score"], s          # same float, not approximately
+    assert truecase_questions(tc, ["who is the president of france ?", "Already Cased"])[1] == "Already Cased"
+
+
+def test_truecaser_rejects_other_pickles(tmp_path):
+    import pickle
+    from densephrases_b200.truecase import TrueCaser
+    p = tmp_path / "x.dist"
+    pickle.dump({"uni_dist": {}}, open(p, "wb"))
+    with pytest.raises(KeyError):
+        TrueCaser(str(p))
+    with pytest.raises(FileNotFoundError):
+        TrueCaser(str(tmp_path / "missing.dist"))
+
+
+def test_load_qa_pairs_truecases_lower_case_questions(tmp_path, monkeypatch, capsys):
+    """open_utils.py:147-156: with args.truecase the all-lower-case questions are re-cased from $DATA_DIR/<truecase_path>; a missing
+    statistics file is printed and ignored."""
+    import densephrases_b200.runtime as rt
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gold = {c["sentence"]: c["truecased"] for c in json.load(open(os.path.join(here, "truecase.json")))["cases"] if c["oov"] == "title"}
+
+    class A:
+        do_lower_case = False; draft = False; truecase = True; truecase_path = "truecase.dist"
+    p = tmp_path / "qa.json"
+    json.dump({"data": [{"id": "1", "question": "who is the president of france ?", "answers": ["x"]},
+                        {"id": "2", "question": "Who is the President?", "answers": ["y"]}]}, open(p, "w"))
+    monkeypatch.setenv("DATA_DIR", here)
+    monkeypatch.setattr(rt, "_truecaser", None)
+    _, qs, _, _ = rt.load_qa_pairs(str(p), A())
+    assert qs == [gold["who is the president of france ?"[:-1]] if "who is the president of france " in gold else rt._truecaser.get_true_case("who is the president of france "),
+                  "Who is the President"]
+    assert qs[0] != "who is the president of france "           # it was re-cased
+    monkeypatch.setenv("DATA_DIR", str(tmp_path))                # no statistics file there
+    monkeypatch.setattr(rt, "_truecaser", None)
+    _, qs2, _, _ = rt.load_qa_pairs(str(p), A())
+    assert qs2[0] == "who is the president of france " and "truecase.dist" in capsys.readouterr().out
