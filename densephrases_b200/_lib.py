@@ -45,6 +45,9 @@ _SIGS = {
     "dph_index_search_partial": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "dph_index_coarse_local": (_i32, [_vp, _vp, _i64, _vp]),
     "dph_index_search_preassigned": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
+    "dph_index_record_floats": (_i32, [_vp]),
+    "dph_index_coarse_split": (_i32, [_vp, _vp, _i64, _vp]),
+    "dph_index_search_assigned": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "dph_merge_shards": (_i32, [_vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
     "dph_pack_topk": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "dph_merge_shards_packed": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _vp]),

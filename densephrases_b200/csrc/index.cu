@@ -132,7 +132,7 @@ DPH_API void dph_index_free(dph_index* ix) {
     for (void* p : ptrs) if (p) cudaFree(p);
     DevBuf* bufs[] = {&ix->xdev, &ix->xr, &ix->S, &ix->key, &ix->cd, &ix->lut_canon, &ix->lutmax, &ix->segs, &ix->wpre, &ix->qinfo,
                       &ix->cand, &ix->cand_off, &ix->cand_cnt, &ix->gthr, &ix->flags, &ix->work, &ix->Dp, &ix->Ip, &ix->Gp, &ix->Dh, &ix->Ih, &ix->eps, &ix->nseg, &ix->lutmin, &ix->lutmaxv, &ix->lutq, &ix->qparams, &ix->gdense,
-                      &ix->pl_cnt, &ix->pl_fill, &ix->pl_off, &ix->pl_blockpre, &ix->pl_entries, &ix->pl_unitpre, &ix->pl_units, &ix->pl_udesc, &ix->pairwork, &ix->csplit, &ix->xsplit, &ix->candkeys, &ix->cflags,
+                      &ix->pl_cnt, &ix->pl_fill, &ix->pl_off, &ix->pl_blockpre, &ix->pl_entries, &ix->pl_unitpre, &ix->pl_units, &ix->pl_udesc, &ix->pairwork, &ix->csplit, &ix->xsplit, &ix->candkeys, &ix->cflags, &ix->selkeys, &ix->recbuf,
                       &ix->rb_ids, &ix->rb_out, &ix->rb_found, &ix->ws_q, &ix->ws_id, &ix->ws_out, &ix->ws_xq};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < DPH_PROF_RING; i++) { if (ix->ev0[i]) cudaEventDestroy(ix->ev0[i]); if (ix->ev1[i]) cudaEventDestroy(ix->ev1[i]); }
@@ -344,7 +344,8 @@ DPH_API int dph_index_copy_last(dph_index* ix, int which, void* dst_host, int64_
 // search
 // -------------------------------------------------------------------------------------------------
 // stage: 0 = whole search; 1 = only rotation + this shard's coarse candidates (keys64 out); 2 = everything after the coarse
-// quantizer, probes (key, cd) already in ix->key / ix->cd and rotated queries in ix->xr (sharded coarse quantizer, see sharded.py)
+// quantizer, probes (key, cd) already in ix->key / ix->cd and rotated queries in ix->xr (sharded coarse quantizer, see sharded.py);
+// 3 = only rotation + the coarse quantizer over ALL lists (query-split sharded search: this rank's slice of the batch)
 static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, float* D, int64_t* I, uint32_t* G, int stage = 0,
                         unsigned long long* keys64 = nullptr) {
     cudaStream_t st = ix->stream;
@@ -408,7 +409,7 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
         DPH_TRY(ix->pairwork.ensure(sizeof(DphPairWork)));
     }
     ix->last_n = n;
-    if (stage != 1) ix->last_group = group;
+    if (stage != 1 && stage != 3) ix->last_group = group;
     if (stage == 1) ix->last_coarse_n = n;
 
     if (stage == 1) {
@@ -423,14 +424,16 @@ static int search_chunk(dph_index* ix, const float* x_dev, int64_t n, int k, flo
         DPH_TRY(dph_launch_coarse_select(ix->S.as<float>(), n, nl, nprobe, nullptr, nullptr, st, keys64, (unsigned)ix->list_lo));
         return 0;
     }
-    if (stage == 0) {
+    if (stage == 0 || stage == 3) {
         DPH_TRY(dph_launch_sgemm_nt_seq(x_dev, n, ix->A, ix->d, ix->d, ix->xr.as<float>(), st));                   // OPQ rotation
         int rc = ix->coarse_tc ? dph_coarse_tc(ix, n, 0, ix->nlist, nprobe, nullptr, ix->key.as<int32_t>(), ix->cd.as<float>(), st) : 1;
         if (rc > 1) return rc;
         if (rc == 1) {
             DPH_TRY(dph_launch_sgemm_nt_seq(ix->xr.as<float>(), n, ix->C, ix->nlist, ix->d, ix->S.as<float>(), st));   // coarse scores
-            DPH_TRY(dph_launch_coarse_select(ix->S.as<float>(), n, ix->nlist, nprobe, ix->key.as<int32_t>(), ix->cd.as<float>(), st));
+            DPH_TRY(dph_launch_coarse_select(ix->S.as<float>(), n, ix->nlist, nprobe, ix->key.as<int32_t>(), ix->cd.as<float>(), st, nullptr, 0u, nullptr, 0,
+                                             &ix->selkeys));
         }
+        if (stage == 3) return 0;
     }
     DPH_TRY(dph_launch_lut(ix->xr.as<float>(), n, ix->pq, ix->lut_canon.as<float>(), ix->lutmax.as<float>(),
                            ix->lutmin.as<float>(), ix->lutmaxv.as<float>(), pair ? ix->lutq.p : nullptr,
@@ -495,6 +498,51 @@ DPH_API int dph_index_search_preassigned(dph_index* ix, const uint64_t* keys_gat
     DPH_TRY(ix->cd.ensure((size_t)n * ix->nprobe * 4));
     DPH_TRY(dph_launch_coarse_merge((const unsigned long long*)keys_gathered_dev, nshards, n, ix->nprobe, ix->key.as<int32_t>(), ix->cd.as<float>(),
                                     ix->stream));
+    return search_chunk(ix, nullptr, n, k, D_dev, I_dev, G_dev, 2, nullptr);
+}
+
+// ---- query-split sharded search (sharded.py): every rank rotates and assigns ITS SLICE of the batch over ALL lists, the ranks
+// exchange one record per query -- [768 f32 rotated query | nprobe i32 lists | nprobe f32 coarse scores] -- and then scan their own
+// lists.  Against the list-split coarse quantizer above it removes the replicated rotation and exact re-rank (each done for n / W
+// queries instead of n) and the merge of per-shard candidates; it needs the full centroid table on every rank (it is replicated).
+__global__ void pack_records_kernel(const float* __restrict__ xr, const int* __restrict__ key, const float* __restrict__ cd, int nprobe, float* __restrict__ rec) {
+    const long long q = blockIdx.x;
+    const int R = DPH_D + 2 * nprobe;
+    float* o = rec + q * R;
+    for (int t = threadIdx.x; t < R; t += blockDim.x)
+        o[t] = t < DPH_D ? xr[q * DPH_D + t] : (t < DPH_D + nprobe ? __int_as_float(key[q * nprobe + t - DPH_D]) : cd[q * nprobe + t - DPH_D - nprobe]);
+}
+__global__ void unpack_records_kernel(const float* __restrict__ rec, int nprobe, float* __restrict__ xr, int* __restrict__ key, float* __restrict__ cd) {
+    const long long q = blockIdx.x;
+    const int R = DPH_D + 2 * nprobe;
+    const float* r = rec + q * R;
+    for (int t = threadIdx.x; t < R; t += blockDim.x) {
+        const float v = r[t];
+        if (t < DPH_D) xr[q * DPH_D + t] = v;
+        else if (t < DPH_D + nprobe) key[q * nprobe + t - DPH_D] = __float_as_int(v);
+        else cd[q * nprobe + t - DPH_D - nprobe] = v;
+    }
+}
+DPH_API int dph_index_record_floats(const dph_index* ix) { return ix->d + 2 * ix->nprobe; }
+DPH_API int dph_index_coarse_split(dph_index* ix, const float* x_dev, int64_t n_local, float* rec_dev) {
+    DPH_TRY(check_ready(ix, 1));
+    DPH_CUDA(cudaSetDevice(ix->device));
+    if (n_local == 0) return 0;
+    DPH_CHECK(n_local <= chunk_size(ix, n_local), "coarse_split: slice too large for one chunk");
+    DPH_TRY(search_chunk(ix, x_dev, n_local, 1, nullptr, nullptr, nullptr, 3, nullptr));
+    pack_records_kernel<<<(unsigned)n_local, 256, 0, ix->stream>>>(ix->xr.as<float>(), ix->key.as<int>(), ix->cd.as<float>(), ix->nprobe, rec_dev);
+    DPH_CUDA(cudaGetLastError());
+    return 0;
+}
+DPH_API int dph_index_search_assigned(dph_index* ix, const float* rec_dev, int64_t n, int k, float* D_dev, int64_t* I_dev, uint32_t* G_dev) {
+    DPH_TRY(check_ready(ix, k));
+    DPH_CUDA(cudaSetDevice(ix->device));
+    if (n == 0) return 0;
+    DPH_TRY(ix->xr.ensure((size_t)n * ix->d * 4));
+    DPH_TRY(ix->key.ensure((size_t)n * ix->nprobe * 4));
+    DPH_TRY(ix->cd.ensure((size_t)n * ix->nprobe * 4));
+    unpack_records_kernel<<<(unsigned)n, 256, 0, ix->stream>>>(rec_dev, ix->nprobe, ix->xr.as<float>(), ix->key.as<int>(), ix->cd.as<float>());
+    DPH_CUDA(cudaGetLastError());
     return search_chunk(ix, nullptr, n, k, D_dev, I_dev, G_dev, 2, nullptr);
 }
 

@@ -66,7 +66,7 @@ struct dph_index {
     DevBuf xdev, xr, S, key, cd, lut_canon, lutmax, segs, wpre, qinfo, cand, cand_off, cand_cnt, gthr, flags,
         work, Dp, Ip, Gp, Dh, Ih, eps, nseg,
         lutmin, lutmaxv, lutq, qparams, gdense, pl_cnt, pl_fill, pl_off, pl_blockpre, pl_entries, pl_unitpre, pl_units, pl_udesc, pairwork,
-        csplit, xsplit, candkeys, cflags,
+        csplit, xsplit, candkeys, cflags, selkeys, recbuf,
         rb_ids, rb_out, rb_found, ws_q, ws_id, ws_out, ws_xq;        // reconstruct_batch / window_scores staging (host-buffer calls)
     int64_t csplit_lo = -1, csplit_nl = -1;
     int coarse_tc = 1;                 // tensor-core coarse quantizer with exact re-rank (0: always the SIMT sequential-k GEMM)
@@ -78,14 +78,16 @@ struct dph_index {
     int64_t prof_n = 0;
 };
 
-// process-wide variant selection (dph_set_tuning, measurement hook): [0] quad-scan IMAD level, [1] SGEMM tile, [2] LUT kernel
+// process-wide variant selection (dph_set_tuning, measurement hook): [0] quad-scan IMAD level, [1] SGEMM tile
 extern int g_dph_tune[8];
 // ---- prep.cu ----
 int dph_launch_sgemm_nt_seq(const float* X, int64_t n, const float* W, int64_t m, int K, float* out, cudaStream_t st);
 int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprobe, int32_t* key, float* cd, cudaStream_t st,
-                             unsigned long long* keys64 = nullptr, unsigned list_base = 0, const int* only_rows = nullptr, int64_t ld = 0);
+                             unsigned long long* keys64 = nullptr, unsigned list_base = 0, const int* only_rows = nullptr, int64_t ld = 0,
+                             DevBuf* tmp = nullptr);      // tmp: scratch for the chunked selection of long rows (nullptr: one CTA per row)
 int dph_coarse_tc(dph_index* ix, int64_t n, int64_t lo, int64_t nl, int nprobe, unsigned long long* keys64, int32_t* key, float* cd, cudaStream_t st);
-int dph_launch_coarse_merge(const unsigned long long* keys, int W, int64_t n, int nprobe, int32_t* key, float* cd, cudaStream_t st);
+int dph_launch_coarse_merge(const unsigned long long* keys, int W, int64_t n, int nprobe, int32_t* key, float* cd, cudaStream_t st,
+                            unsigned long long* keys64 = nullptr);
 int dph_launch_lut(const float* xr, int64_t n, const float* pq, float* lut_canon, float* lutmax, float* lutmin, float* lutmaxv,
                    void* lutq, float2* qparams, cudaStream_t st, int group);
 // group: queries per gather of the scan -- 1 (fp32 LUT, one query), 2 (pair-packed u16 LUTs), 4 (quad-packed u8 LUTs)

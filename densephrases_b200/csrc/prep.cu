@@ -264,11 +264,12 @@ int dph_launch_sgemm_nt_seq(const float* X, int64_t n, const float* W, int64_t m
         DPH_CUDA(cudaGetLastError());
         return 0;
     }
-    // pick the row tile so that the grid covers the SMs a few times over (all CTAs co-resident: <= 24 KB of shared memory each)
+    // pick the LARGEST tile that still gives >= 128 CTAs (measured on B200, tools/bench_variants.py sgemm: n x m = 1024 x 768: 64x64 76 us,
+    // 32x64 87, 16x64 160;  64 x 4096: 32x64 34 us, 64x64 43, 16x64 58;  64 x 768 and 128 x 768: 16x64 31 us, 32x64 33, 64x64 43)
     const long long ct = (m + 63) / 64;
-    if (!k64 || variant == 2 || (variant == 0 && ct * ((n + 63) / 64) >= 3 * 148)) {
+    if (!k64 || variant == 2 || (variant == 0 && ct * ((n + 63) / 64) >= 128)) {
         sgemm_nt_seq_small_kernel<<<dim3((unsigned)ct, (unsigned)((n + 63) / 64)), 256, 0, st>>>(X, n, W, m, K, out);
-    } else if (variant == 3 || (variant == 0 && ct * ((n + 31) / 32) >= 2 * 148)) {
+    } else if (variant == 3 || (variant == 0 && ct * ((n + 31) / 32) >= 128)) {
         sgemm_nt_seq_rows_kernel<2><<<dim3((unsigned)ct, (unsigned)((n + 31) / 32)), 256, 0, st>>>(X, n, W, m, K, out);
     } else {
         sgemm_nt_seq_rows_kernel<1><<<dim3((unsigned)ct, (unsigned)((n + 15) / 16)), 256, 0, st>>>(X, n, W, m, K, out);
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(256) coarse_select_kernel(const float* __restr
 // (score desc, list asc) -- bit-identical to selecting over all lists at once, because every shard computes the
 // same sequential-FMA scores for its own lists.
 __global__ void __launch_bounds__(256) coarse_merge_kernel(const unsigned long long* __restrict__ keys, int W, long long n, int nprobe,
-                                                            int* __restrict__ key, float* __restrict__ cd) {
+                                                            int* __restrict__ key, float* __restrict__ cd, unsigned long long* __restrict__ keys64) {
     // W * nprobe candidate keys (distinct: the list id is part of the key; 0 = empty slot) -> the nprobe largest, sorted.
     // Radix-select the nprobe-th key, gather, sort only the winners (a full bitonic sort of 8 x 256 keys was 90 us per 1024 queries).
     extern __shared__ unsigned long long cm[];              // [tot] candidates, then [p2s] winners
@@ -358,18 +359,20 @@ __global__ void __launch_bounds__(256) coarse_merge_kernel(const unsigned long l
     block_bitonic_sort_desc(sel, p2s);
     for (int r = threadIdx.x; r < nprobe; r += blockDim.x) {
         const unsigned long long k = sel[r];
+        if (keys64) { keys64[q * nprobe + r] = k; continue; }       // chunked selection of tensor-core candidates: keys stay packed
         key[q * nprobe + r] = k ? (int)(0xFFFFFFFFu - (unsigned)k) : -1;
         cd[q * nprobe + r] = k ? dph_fkey_inv((unsigned)(k >> 32)) : DPH_NEUTRAL;
     }
 }
-int dph_launch_coarse_merge(const unsigned long long* keys, int W, int64_t n, int nprobe, int32_t* key, float* cd, cudaStream_t st) {
+int dph_launch_coarse_merge(const unsigned long long* keys, int W, int64_t n, int nprobe, int32_t* key, float* cd, cudaStream_t st,
+                            unsigned long long* keys64) {
     DPH_CHECK((long long)W * nprobe <= 8192, "coarse merge: world * nprobe must be <= 8192");
     if (n == 0) return 0;
     int p2s = 1; while (p2s < nprobe) p2s <<= 1;
     const size_t smem = (size_t)(W * nprobe + p2s) * 8;
     static DphPerDeviceOnce once;
     if (once.first()) { DPH_CUDA(cudaFuncSetAttribute(coarse_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (8192 + 1024) * 8)); }
-    coarse_merge_kernel<<<(unsigned)n, 256, smem, st>>>(keys, W, n, nprobe, key, cd);
+    coarse_merge_kernel<<<(unsigned)n, 256, smem, st>>>(keys, W, n, nprobe, key, cd, keys64);
     DPH_CUDA(cudaGetLastError());
     return 0;
 }
@@ -380,19 +383,26 @@ int dph_launch_coarse_merge(const unsigned long long* keys, int W, int64_t n, in
 // Same result as coarse_select_kernel (score desc, list asc).
 #define CS_MAX_ROW 16384
 #define CS_BINS 2048
-__global__ void __launch_bounds__(256) coarse_select_smem_kernel(const float* __restrict__ S, int nlist, int nprobe,
+// gridDim.y > 1: the row is cut into chunks of `chunk_len` lists, block (q, c) selects inside chunk c and writes row c * n + q of
+// keys64 ([chunks, n, nprobe], the layout coarse_merge_kernel reads) with GLOBAL list numbers -- long rows (IVF65536 on one GPU, or
+// the query-split coarse quantizer of the sharded search) are selected by many CTAs per query instead of one.
+__global__ void __launch_bounds__(256) coarse_select_smem_kernel(const float* __restrict__ S, int nlist_total, int nprobe,
                                                                   int* __restrict__ key, float* __restrict__ cd,
                                                                   unsigned long long* __restrict__ keys64, unsigned list_base, const int* __restrict__ only_rows,
-                                                                  long long ld) {
+                                                                  long long ld, int chunk_len) {
     if (only_rows && only_rows[blockIdx.x] == 0) return;
+    const int chunk0 = (int)blockIdx.y * chunk_len;
+    const int nlist = (nlist_total - chunk0) < chunk_len ? (nlist_total - chunk0) : chunk_len;
+    list_base += (unsigned)chunk0;
     extern __shared__ unsigned cs_sm[];
     unsigned* row = cs_sm;                         // [nlist] fkey(score)
     unsigned* hist = row + ((nlist + 1) & ~1);     // [2048]   (keeps `sel` 8-byte aligned)
     unsigned long long* sel = reinterpret_cast<unsigned long long*>(hist + CS_BINS);   // [1024]
     __shared__ unsigned s_min, s_max, s_digit, s_rem, s_cnt, s_ties;
     const long long q = blockIdx.x;
+    const long long orow = (long long)blockIdx.y * gridDim.x + q;        // output row
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* src = S + q * ld;
+    const float* src = S + q * ld + chunk0;
     unsigned lmin = 0xFFFFFFFFu, lmax = 0u;
     for (int i = tid; i < nlist; i += 256) { const unsigned u = dph_fkey(__ldg(src + i)); row[i] = u; lmin = min(lmin, u); lmax = max(lmax, u); }
     if (tid == 0) { s_min = 0xFFFFFFFFu; s_max = 0u; s_cnt = 0; s_ties = 0; }
@@ -474,17 +484,17 @@ __global__ void __launch_bounds__(256) coarse_select_smem_kernel(const float* __
         if (keys64) {
             unsigned long long k = r < take ? sel[r] : 0ull;
             if (k) k = (k & 0xFFFFFFFF00000000ull) | (unsigned long long)(0xFFFFFFFFu - ((0xFFFFFFFFu - (unsigned)k) + list_base));
-            keys64[q * nprobe + r] = k;
+            keys64[orow * nprobe + r] = k;
         } else if (r < take) {
             const unsigned long long k = sel[r];
-            key[q * nprobe + r] = (int)(0xFFFFFFFFu - (unsigned)k);
-            cd[q * nprobe + r] = dph_fkey_inv((unsigned)(k >> 32));
-        } else { key[q * nprobe + r] = -1; cd[q * nprobe + r] = DPH_NEUTRAL; }
+            key[orow * nprobe + r] = (int)(0xFFFFFFFFu - (unsigned)k);
+            cd[orow * nprobe + r] = dph_fkey_inv((unsigned)(k >> 32));
+        } else { key[orow * nprobe + r] = -1; cd[orow * nprobe + r] = DPH_NEUTRAL; }
     }
 }
 
 int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprobe, int32_t* key, float* cd, cudaStream_t st,
-                             unsigned long long* keys64, unsigned list_base, const int* only_rows, int64_t ld) {
+                             unsigned long long* keys64, unsigned list_base, const int* only_rows, int64_t ld, DevBuf* tmp) {
     if (ld <= 0) ld = nlist;
     DPH_CHECK(nprobe >= 1 && nprobe <= DPH_MAX_NPROBE, "nprobe out of range [1,1024]");
     DPH_CHECK(nlist < (1ll << 31), "nlist too large");
@@ -493,9 +503,23 @@ int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprob
         const size_t smem = (size_t)((nlist + 1) & ~1) * 4 + CS_BINS * 4 + DPH_MAX_NPROBE * 8;
         static DphPerDeviceOnce once;
         if (once.first()) { DPH_CUDA(cudaFuncSetAttribute(coarse_select_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_MAX_ROW * 4 + CS_BINS * 4 + DPH_MAX_NPROBE * 8)); }
-        coarse_select_smem_kernel<<<(unsigned)n, 256, smem, st>>>(S, (int)nlist, nprobe, key, cd, keys64, list_base, only_rows, ld);
+        coarse_select_smem_kernel<<<(unsigned)n, 256, smem, st>>>(S, (int)nlist, nprobe, key, cd, keys64, list_base, only_rows, ld, (int)nlist);
         DPH_CUDA(cudaGetLastError());
         return 0;
+    }
+    // long rows: chunks of 8192 lists selected by one CTA each, then the per-chunk winners merged per query (same keys, same order:
+    // every key carries its global list number, so the merge of the chunk winners IS the selection over the whole row)
+    const int chunk_len = 8192;
+    const int64_t nchunks = (nlist + chunk_len - 1) / chunk_len;
+    if (tmp && !only_rows && nchunks * nprobe <= 8192 && nprobe <= chunk_len) {
+        DPH_TRY(tmp->ensure((size_t)nchunks * n * nprobe * 8));
+        const size_t smem = (size_t)chunk_len * 4 + CS_BINS * 4 + DPH_MAX_NPROBE * 8;
+        static DphPerDeviceOnce once2;
+        if (once2.first()) { DPH_CUDA(cudaFuncSetAttribute(coarse_select_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_MAX_ROW * 4 + CS_BINS * 4 + DPH_MAX_NPROBE * 8)); }
+        coarse_select_smem_kernel<<<dim3((unsigned)n, (unsigned)nchunks), 256, smem, st>>>(S, (int)nlist, nprobe, nullptr, nullptr, tmp->as<unsigned long long>(),
+                                                                                       list_base, nullptr, ld, chunk_len);
+        DPH_CUDA(cudaGetLastError());
+        return dph_launch_coarse_merge(tmp->as<unsigned long long>(), (int)nchunks, n, nprobe, key, cd, st, keys64);
     }
     coarse_select_kernel<<<(unsigned)n, 256, 0, st>>>(S, nlist, nprobe, key, cd, keys64, list_base, only_rows, ld);
     DPH_CUDA(cudaGetLastError());
@@ -585,68 +609,6 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ xr, 
     }
 }
 
-// Large batches (n >= 512): a CTA handles LW = 16 queries x 8 sub-quantizers.  Thread j keeps the 8 codebook entries of code j
-// (8 x 8 floats) in registers for all 16 queries, so the L2 -> SM codebook stream is n/16 x 786 KB (C4, 1024 queries: 50 MB instead of
-// 201 MB); its 8 table entries of a query are 32 contiguous bytes of the canonical row [code][m % 32] and go straight to global
-// memory (one full sector per thread), so the only shared memory is the 8 KB tile of the min / max reduction and several CTAs
-// share an SM (the 4-query kernel above needs 131 KB and runs one latency-bound CTA per SM).  Same arithmetic: one sequential FMA
-// chain over the 8 sub-dimensions per entry.
-#define LW 16
-__global__ void __launch_bounds__(256, 2) lut_wide_kernel(const float* __restrict__ xr, const float* __restrict__ pq, long long n,
-                                                           float* __restrict__ lut_canon,
-                                                           float* __restrict__ lutmax, float* __restrict__ lutmin, float* __restrict__ lutmaxv) {
-    __shared__ float tile[8 * 257];
-    __shared__ __align__(16) float xs[LW * 64];
-    const long long q0 = (long long)blockIdx.x * LW;
-    const int sb = blockIdx.y;                             // sub-quantizers [8 sb, 8 sb + 8)
-    const int j = threadIdx.x, lane = j & 31, warp = j >> 5;
-    const int nq = (int)((n - q0) < LW ? (n - q0) : LW);
-    for (int i = j; i < LW * 64; i += 256) { const int qi = i >> 6; xs[i] = qi < nq ? xr[(q0 + qi) * DPH_D + sb * 64 + (i & 63)] : 0.0f; }
-    float4 c0[8], c1[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-        const float4* cb = reinterpret_cast<const float4*>(pq + ((size_t)(sb * 8 + u) * 256 + j) * 8);
-        c0[u] = __ldg(cb); c1[u] = __ldg(cb + 1);
-    }
-    __syncthreads();
-    const int seg = sb >> 2, mo = (sb & 3) * 8;
-#pragma unroll 1
-    for (int qi = 0; qi < nq; qi++) {
-        float e[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const float4 x0 = *reinterpret_cast<const float4*>(xs + qi * 64 + u * 8);
-            const float4 x1 = *reinterpret_cast<const float4*>(xs + qi * 64 + u * 8 + 4);
-            float acc = 0.0f;
-            acc = fmaf(x0.x, c0[u].x, acc); acc = fmaf(x0.y, c0[u].y, acc); acc = fmaf(x0.z, c0[u].z, acc); acc = fmaf(x0.w, c0[u].w, acc);
-            acc = fmaf(x1.x, c1[u].x, acc); acc = fmaf(x1.y, c1[u].y, acc); acc = fmaf(x1.z, c1[u].z, acc); acc = fmaf(x1.w, c1[u].w, acc);
-            e[u] = acc;
-            tile[u * 257 + j] = acc;
-        }
-        float4* dst = reinterpret_cast<float4*>(lut_canon + (size_t)(q0 + qi) * DPH_LUT_CANON_FLOATS + (size_t)seg * (256 * 32) + j * 32 + mo);
-        dst[0] = make_float4(e[0], e[1], e[2], e[3]);
-        dst[1] = make_float4(e[4], e[5], e[6], e[7]);
-        __syncthreads();
-        {   // warp u: max |entry|, min, max of sub-quantizer 8 sb + u over the 256 codes
-            const float* row = tile + warp * 257;
-            float a = 0.0f, lo = row[lane], hi = lo;
-#pragma unroll
-            for (int t = 0; t < 8; t++) { const float v = row[lane + 32 * t]; a = fmaxf(a, fabsf(v)); lo = fminf(lo, v); hi = fmaxf(hi, v); }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, off));
-                lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
-                hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
-            }
-            if (lane == 0) {
-                const long long o = (q0 + qi) * DPH_M + sb * 8 + warp;
-                lutmax[o] = a; lutmin[o] = lo; lutmaxv[o] = hi;
-            }
-        }
-        __syncthreads();
-    }
-}
-
 // Quantised LUT for the pair-packed scan: qv[m][j] = round((LUT[m][j] - min_m) / step) in [0, 682], one step per query
 // (step = max_m range_m / 682) so that 96 entries sum below 2^16 and two queries' tables can share one 32-bit word.
 // Written in the scan layout ([3][256][64] u16); qparams[q] = (step, sum_m min_m).
@@ -690,9 +652,7 @@ int dph_launch_lut(const float* xr, int64_t n, const float* pq, float* lut_canon
     const size_t lut_smem = (size_t)(LQ * 32 * LUT_TILE_LD) * 4;
     static DphPerDeviceOnce lut_once;
     if (lut_once.first()) { DPH_CUDA(cudaFuncSetAttribute(lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_smem)); }
-    const int lv = g_dph_tune[2];
-    if (lv == 2 || (lv == 0 && n >= 512)) lut_wide_kernel<<<dim3((unsigned)((n + LW - 1) / LW), 12), 256, 0, st>>>(xr, pq, n, lut_canon, lutmax, lutmin, lutmaxv);
-    else lut_kernel<<<dim3((unsigned)((n + LQ - 1) / LQ), 3), 256, lut_smem, st>>>(xr, pq, n, lut_canon, lutmax, lutmin, lutmaxv);
+    lut_kernel<<<dim3((unsigned)((n + LQ - 1) / LQ), 3), 256, lut_smem, st>>>(xr, pq, n, lut_canon, lutmax, lutmin, lutmaxv);
     DPH_CUDA(cudaGetLastError());
     if (lutq) {
         if (group == 4) lutq_kernel<unsigned char, DPH_QMAX8><<<dim3((unsigned)n, 3), 256, 0, st>>>(lut_canon, lutmin, lutmaxv, (unsigned char*)lutq, qparams);

@@ -637,21 +637,29 @@ __global__ void __launch_bounds__(NT, 1) scan_quad_kernel(PairScanArgs a) {
             const unsigned* T2p = reinterpret_cast<const unsigned*>(lut8 + (size_t)qv[2] * DPH_LUT_SCAN_FLOATS);
             const unsigned* T3p = reinterpret_cast<const unsigned*>(lut8 + (size_t)qv[3] * DPH_LUT_SCAN_FLOATS);
             uint4* dst = reinterpret_cast<uint4*>(smem);
-#pragma unroll 6
-            for (int i = tid; i < 768 * 8; i += NT) {              // (row, group of four real words): a quarter-warp moves one row
-                const int row = i >> 3, cg = i & 7;
-                const int src = row * 16 + cg;
-                const unsigned va = __ldg(T0p + src);
-                const unsigned vb = nq > 1 ? __ldg(T1p + src) : 0u;
-                const unsigned vc = nq > 2 ? __ldg(T2p + src) : 0u;
-                const unsigned vd = nq > 3 ? __ldg(T3p + src) : 0u;
-                const unsigned t0 = __byte_perm(va, vb, 0x5140), t1 = __byte_perm(va, vb, 0x7362);     // [a0 b0 a1 b1], [a2 b2 a3 b3]
-                const unsigned u0 = __byte_perm(vc, vd, 0x5140), u1 = __byte_perm(vc, vd, 0x7362);
-                uint4 o;
-                o.x = __byte_perm(t0, u0, 0x5410); o.y = __byte_perm(t0, u0, 0x7632);
-                o.z = __byte_perm(t1, u1, 0x5410); o.w = __byte_perm(t1, u1, 0x7632);
-                dst[row * 16 + cg] = o;
-                dst[row * 16 + 8 + cg] = o;                        // wrap copy (word 63 = word 31: never read)
+            // (row, group of four real words): a quarter-warp moves one row.  The empty slots of a short group repeat query 0 (their
+            // byte lanes are summed like the others and never pass: threshold +inf), so all four loads are unconditional and a
+            // thread keeps 24 of them in flight.
+            constexpr int LB = 6;
+#pragma unroll 1
+            for (int i0 = tid; i0 < 768 * 8; i0 += NT * LB) {
+                unsigned va[LB], vb[LB], vc[LB], vd[LB];
+#pragma unroll
+                for (int e = 0; e < LB; e++) {
+                    const int i = i0 + e * NT, src = (i >> 3) * 16 + (i & 7);
+                    va[e] = __ldg(T0p + src); vb[e] = __ldg(T1p + src); vc[e] = __ldg(T2p + src); vd[e] = __ldg(T3p + src);
+                }
+#pragma unroll
+                for (int e = 0; e < LB; e++) {
+                    const int i = i0 + e * NT, row = i >> 3, cg = i & 7;
+                    const unsigned t0 = __byte_perm(va[e], vb[e], 0x5140), t1 = __byte_perm(va[e], vb[e], 0x7362);     // [a0 b0 a1 b1], [a2 b2 a3 b3]
+                    const unsigned u0 = __byte_perm(vc[e], vd[e], 0x5140), u1 = __byte_perm(vc[e], vd[e], 0x7362);
+                    uint4 o;
+                    o.x = __byte_perm(t0, u0, 0x5410); o.y = __byte_perm(t0, u0, 0x7632);
+                    o.z = __byte_perm(t1, u1, 0x5410); o.w = __byte_perm(t1, u1, 0x7632);
+                    dst[row * 16 + cg] = o;
+                    dst[row * 16 + 8 + cg] = o;                        // wrap copy (word 63 = word 31: never read)
+                }
             }
         }
         if (tid == 0) {

@@ -189,6 +189,28 @@ class IvfPqIndex:
         L.check(L.lib().dph_index_search_preassigned(self._h, keys_gathered.data_ptr(), W, n, k, D.data_ptr(), I.data_ptr(), G.data_ptr()))
         return D, I, G
 
+    def coarse_split(self, x_local):
+        """torch cuda [n_local,d] (this rank's slice of the batch) -> records [n_local, 768 + 2 nprobe] f32: rotated query, probed
+        lists (int32 bits) and coarse scores over ALL lists (dph_index_coarse_split)."""
+        import torch
+        n = x_local.shape[0]
+        rec = torch.empty((n, L.lib().dph_index_record_floats(self._h)), dtype=torch.float32, device=x_local.device)
+        self.set_stream(torch.cuda.current_stream(x_local.device).cuda_stream)
+        L.check(L.lib().dph_index_coarse_split(self._h, x_local.data_ptr(), n, rec.data_ptr()))
+        return rec
+
+    def search_assigned(self, rec, k):
+        """all-gathered records [n, 768 + 2 nprobe] (batch order) -> this shard's partial (D, I, G)."""
+        import torch
+        assert rec.is_cuda and rec.dtype == torch.float32 and rec.is_contiguous()
+        n = rec.shape[0]
+        D = torch.empty((n, k), dtype=torch.float32, device=rec.device)
+        I = torch.empty((n, k), dtype=torch.int64, device=rec.device)
+        G = torch.empty((n, k), dtype=torch.int32, device=rec.device)
+        self.set_stream(torch.cuda.current_stream(rec.device).cuda_stream)
+        L.check(L.lib().dph_index_search_assigned(self._h, rec.data_ptr(), n, k, D.data_ptr(), I.data_ptr(), G.data_ptr()))
+        return D, I, G
+
     def _last(self, which, shape, dtype):
         out = np.empty(shape, dtype=dtype)
         L.check(L.lib().dph_index_copy_last(self._h, which, _np_ptr(out), out.nbytes))

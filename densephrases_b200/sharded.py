@@ -60,12 +60,45 @@ def sharded_search(x, k, world, group, coarse_local, search_preassigned, pack, m
     return merge_packed(Pg.view(world, n, k, 2), k)
 
 
+def sharded_search_qsplit(x, k, world, rank, group, coarse_split, search_assigned, pack, merge_packed):
+    """The query-split protocol (large batches): the coarse quantizer is replicated, so rank r rotates and assigns queries
+    [r P, (r+1) P) of the batch (P = ceil(n / W), zero rows pad the last slice) over ALL lists and the ranks exchange the results:
+        rec    = coarse_split(x[r P : (r+1) P])      [P, 768 + 2 nprobe]  rotated query | probed lists | coarse scores
+        rec_g  = all_gather(rec)[:n]                 [n, ...]             exchange 1 (batch order: slices are contiguous)
+        D,I,G  = search_assigned(rec_g, k)           per-shard partial top-k over the global probe set
+        P_g    = all_gather(pack(D, I, G))           [W, n, k, 2]         exchange 2
+        return merge_packed(P_g, k)
+    Same probes, same scores as sharded_search; the per-query work before the scan is done once instead of once per rank."""
+    import torch.distributed as dist
+    n = x.shape[0]
+    per = (n + world - 1) // world
+    lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+    xl = x[lo:hi]
+    if hi - lo < per:
+        xl = torch.cat([xl, torch.zeros((per - (hi - lo), x.shape[1]), dtype=x.dtype, device=x.device)])
+    rec = coarse_split(xl.contiguous())
+    rec_g = torch.empty((world * per, rec.shape[1]), dtype=rec.dtype, device=rec.device)
+    dist.all_gather_into_tensor(rec_g, rec.contiguous(), group=group)
+    D, I, G = search_assigned(rec_g[:n], k)
+    P = pack(D, I, G)
+    Pg = torch.empty((world * n, k, 2), dtype=torch.int64, device=P.device)
+    dist.all_gather_into_tensor(Pg, P.contiguous(), group=group)
+    return merge_packed(Pg.view(world, n, k, 2), k)
+
+
+def use_query_split(n, world, nlist, d=768):
+    """Query-split pays when every rank's slice still fills tensor-core tiles and streaming the WHOLE centroid table (fp32 hi/lo planes)
+    per batch is cheap next to the scan: C4 (1024 queries, IVF65536: 400 MB of planes) yes; C5 (128 vectors, IVF1048576: 6.4 GB) no."""
+    return world > 1 and n >= 32 * world and nlist * d * 8 <= (1 << 30)
+
+
 class ShardedIvfPq:
     def __init__(self, nlist, rank=0, world=1, device=0, group=None, local=None):
         self.rank, self.world, self.device, self.group = rank, world, device, group
         self.local = local if local is not None else IvfPqIndex(nlist, device=device)      # `local`: any object with the IvfPqIndex API (tests)
         self._pinned_in = None
         self._pinned_out = None
+        self.query_split = None          # None: use_query_split() decides per batch; True / False force one protocol (tests, measurements)
 
     def build_synthetic(self, A, list_len, seed, centroid_sigma=0.5, pq_sigma=0.25):
         lo, hi = shard_ranges(list_len, self.world)[self.rank]
@@ -151,6 +184,9 @@ class ShardedIvfPq:
         if n > 4096:        # one chunk per collective round
             parts = [self.search_device(x[i:i + 4096], k) for i in range(0, n, 4096)]
             return torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
+        if self.query_split is True or (self.query_split is None and use_query_split(n, self.world, self.local.nlist)):
+            return sharded_search_qsplit(x, k, self.world, self.rank, self.group, self.local.coarse_split, self.local.search_assigned, pack_topk,
+                                         merge_shards_packed)
         return sharded_search(x, k, self.world, self.group, self.local.coarse_local, self.local.search_preassigned, pack_topk, merge_shards_packed)
 
     def search(self, x, k):

@@ -98,6 +98,15 @@ int dph_index_search_partial(dph_index* ix, const float* x_dev, int64_t n, int k
 int dph_index_coarse_local(dph_index* ix, const float* x_dev, int64_t n, uint64_t* keys_dev);
 int dph_index_search_preassigned(dph_index* ix, const uint64_t* keys_gathered_dev, int nshards, int64_t n, int k, float* D_dev,
                                  int64_t* I_dev, uint32_t* G_dev);
+/* Query-split variant of the same step (large batches): every shard rotates and assigns only ITS SLICE of the batch (n_local queries),
+ * but over ALL lists (the coarse quantizer is replicated, index.py:200 runs it once per batch), and emits one record per query:
+ * rec [n_local, dph_index_record_floats()] = [768 f32 rotated query | nprobe i32 list numbers | nprobe f32 coarse scores].  After an
+ * all-gather of the records, search_assigned (rec [n, ...], all queries in batch order) runs the rest of the search on this shard's
+ * lists.  Same probes and scores as the unsharded search; the rotation and the exact re-rank of the tensor-core coarse quantizer are
+ * done once per query instead of once per query and shard. */
+int dph_index_record_floats(const dph_index* ix);
+int dph_index_coarse_split(dph_index* ix, const float* x_dev, int64_t n_local, float* rec_dev);
+int dph_index_search_assigned(dph_index* ix, const float* rec_dev, int64_t n, int k, float* D_dev, int64_t* I_dev, uint32_t* G_dev);
 /* Dg/Ig/Gg [nshards,n,k] (all-gathered, device) -> D/I [n,k] (device).  Order: score desc, scan position asc. */
 int dph_merge_shards(const float* Dg, const int64_t* Ig, const uint32_t* Gg, int nshards, int64_t n, int k, float* D,
                      int64_t* I, void* cuda_stream);
@@ -173,8 +182,7 @@ int dph_gemm_tf32_nt(const float* A, const float* W, const float* bias, const fl
 int dph_gemm_tf32_set_mode(int mode);
 /* Measurement hook (process-wide): choose between kernel variants that compute bit-identical results, for A/B timing on hardware
  * (tools/bench_variants.py).  knob 0: additions of the quad scan issued on the FMA pipe (0 none .. 3 all; default 1);
- * knob 1: tile shape of the sequential-k SGEMM (0 auto, 1: 128x128, 2: 64x64, 3: 32x64, 4: 16x64);
- * knob 2: PQ table kernel (0 auto, 1: 4 queries x 32 sub-quantizers per CTA, 2: 16 queries x 8 sub-quantizers per CTA). */
+ * knob 1: tile shape of the sequential-k SGEMM (0 auto, 1: 128x128, 2: 64x64, 3: 32x64, 4: 16x64). */
 int dph_set_tuning(int knob, int value);
 
 #ifdef __cplusplus

@@ -151,7 +151,7 @@ def test_golden_fixture_on_gpu():
         assert np.array_equal(ix.reconstruct_batch(g["I"][0])[0].view(np.int32), g["recon0"].view(np.int32))
 
 
-@pytest.mark.parametrize("nshards", [2, 5])
+@pytest.mark.parametrize("nshards", [2, 5, 3])
 def test_list_range_shards_on_one_device(oracle, nshards):
     """The multi-GPU data path (per-shard partial top-k + merge_shards) exercised with all shards on cuda:0."""
     import torch
@@ -174,6 +174,14 @@ def test_list_range_shards_on_one_device(oracle, nshards):
         shards.append(sh)
     if nshards == 2:      # replicated coarse quantizer: every shard selects the global probes itself
         parts = [sh.search_partial(xt, k) for sh in shards]
+    elif nshards == 3:    # query-split coarse quantizer: shard r assigns ITS SLICE of the batch over all lists -> "all-gather" of records
+        per = (len(x) + nshards - 1) // nshards
+        rec = torch.cat([sh.coarse_split(xt[r * per:(r + 1) * per].contiguous()) for r, sh in enumerate(shards)]).contiguous()
+        assert rec.shape == (len(x), 768 + 2 * nprobe)
+        parts = [sh.search_assigned(rec, k) for sh in shards]
+        keyr = ref.search(x, k, nprobe, return_key=True)[2].astype(np.int32)
+        assert np.array_equal(shards[0].last_probes(len(x)), keyr) and np.array_equal(shards[2].last_probes(len(x)), keyr)
+        assert np.array_equal(shards[1].last_xr(len(x)).view(np.int32), ref.rotate(x).view(np.int32))
     else:                 # sharded coarse quantizer: per-shard candidates -> "all-gather" -> merge -> preassigned search
         keys_g = torch.stack([sh.coarse_local(xt) for sh in shards]).contiguous()
         parts = [sh.search_preassigned(keys_g, k) for sh in shards]
@@ -244,6 +252,32 @@ def test_large_nlist_uses_generic_coarse_select(oracle):
     Dr, Ir, keyr = ref.search(x, 10, 40, return_key=True)
     assert np.array_equal(gpu.last_probes(6), keyr.astype(np.int32))
     assert_topk_equal(D, I, Dr, Ir)
+
+
+@pytest.mark.parametrize("nprobe", [24, 300])
+def test_long_rows_chunked_select_both_coarse_paths(oracle, nprobe):
+    """Rows longer than the shared-memory select (nlist > 16384) are selected chunk by chunk (8192 lists per CTA) and merged per query:
+    the tensor-core candidate keys and the exact SIMT scores both go through it and must reproduce the oracle's probes and scores."""
+    nlist = 20000
+    lens = np.full(nlist, 2, dtype=np.int64)
+    ref, gpu = make_pair(oracle, nlist, lens)
+    gpu.nprobe = nprobe
+    x = np.concatenate([near_queries(ref, 30, 5), 0.5 * np.random.default_rng(3).standard_normal((10, 768)).astype(np.float32)])
+    Dr, Ir, keyr = ref.search(x, 10, nprobe, return_key=True)
+    cdr, _ = ref.coarse(ref.rotate(x), nprobe)
+    for tc in (1, 0):
+        gpu.set_coarse_tc(tc)
+        D, I = gpu.search(x, 10)
+        pr = gpu.last_probes(len(x))
+        # exact score ties between two lists do occur at this size: the CUDA order is canonical (score desc, list asc), faiss' / the
+        # oracle's is heap-dependent -> compare the probe SETS and the (sorted) scores bit for bit
+        assert all(set(pr[i].tolist()) == set(keyr[i].tolist()) for i in range(len(x))), f"probes differ (tc={tc})"
+        assert np.array_equal(gpu.last_coarse(len(x)).view(np.int32), cdr.view(np.int32)), f"coarse scores differ (tc={tc})"
+        if tc == 1:
+            pr_tc = pr.copy()
+        else:
+            assert np.array_equal(pr, pr_tc), "tensor-core and SIMT coarse paths order the probes differently"
+        assert_topk_equal(D, I, Dr, Ir, f"tc={tc}")
 
 
 @pytest.mark.parametrize("nprobe", [8, 256])

@@ -108,8 +108,45 @@ def _worker2(rank, world, port, out):
         return torch.from_numpy(D), torch.from_numpy(I)
 
     Dm, Im = sharded_search(torch.from_numpy(x), k, world, None, coarse_local, search_preassigned, pack, merge_packed)
+
+    # ---- the query-split protocol on the same batch: this rank assigns only its slice of the queries, over ALL lists ----
+    from densephrases_b200.sharded import sharded_search_qsplit
+    R_ = 768 + 2 * nprobe
+    qstate = {}
+
+    def coarse_split(xl):
+        xl = xl.numpy()
+        xrl = ix.rotate(xl)
+        S = R.np_matmul_nt_seq(xrl, ix.centroids())
+        rec = np.zeros((len(xl), R_), dtype=np.float32)
+        for q in range(len(xl)):
+            order = sorted(range(nlist), key=lambda j: (-float(S[q, j]), j))[:nprobe]
+            rec[q, :768] = xrl[q]
+            rec[q, 768:768 + nprobe] = np.array(order, dtype=np.int32).view(np.float32)
+            rec[q, 768 + nprobe:] = S[q, order]
+        return torch.from_numpy(rec)
+
+    def search_assigned(rec_g, kk):
+        rec = rec_g.numpy()
+        assert rec.shape == (len(x), R_)                                    # padded rows of the last slice were cut off
+        xr_g = np.ascontiguousarray(rec[:, :768])
+        key = np.ascontiguousarray(rec[:, 768:768 + nprobe]).view(np.int32).astype(np.int64)
+        qstate["key"], qstate["xr"] = key, xr_g
+        state["key"] = key
+        D, I = ix.search_preassigned(xr_g, np.where((key >= lo) & (key < hi), key, -1), kk)
+        G = np.zeros_like(I)
+        for q in range(len(x)):
+            starts = np.concatenate([[0], np.cumsum([lens[l] if l >= 0 else 0 for l in key[q]])])
+            for r in range(kk):
+                if I[q, r] >= 0:
+                    l, off = ix.locate(np.array([I[q, r]]))
+                    G[q, r] = starts[list(key[q]).index(int(l[0]))] + int(off[0])
+        return torch.from_numpy(D), torch.from_numpy(I), torch.from_numpy(G.astype(np.int32))
+
+    Dq, Iq = sharded_search_qsplit(torch.from_numpy(x), k, world, rank, None, coarse_split, search_assigned, pack, merge_packed)
     if rank == 0:
-        np.savez(out, D=Dm.numpy(), I=Im.numpy(), Dfull=Dfull, Ifull=Ifull, key=state["key"], keyfull=keyfull)
+        np.savez(out, D=Dm.numpy(), I=Im.numpy(), Dfull=Dfull, Ifull=Ifull, key=state["key"], keyfull=keyfull,
+                 Dq=Dq.numpy(), Iq=Iq.numpy(), keyq=qstate["key"], xrq=qstate["xr"], xr=xr)
     dist.destroy_process_group()
 
 
@@ -123,6 +160,9 @@ def test_gloo_world2_two_exchange_protocol(tmp_path, oracle):
     g = np.load(out)
     assert np.array_equal(g["key"], g["keyfull"])                       # sharded coarse quantizer == unsharded probe selection
     assert_topk_equal(g["D"], g["I"], g["Dfull"], g["Ifull"], "two-exchange sharded search vs unsharded")
+    # query-split protocol (7 queries over 2 ranks: slices of 4 and 3 + one padded row)
+    assert np.array_equal(g["keyq"], g["keyfull"]) and np.array_equal(g["xrq"].view(np.int32), g["xr"].view(np.int32))
+    assert_topk_equal(g["Dq"], g["Iq"], g["Dfull"], g["Ifull"], "query-split sharded search vs unsharded")
 
 
 def _worker(rank, world, port, out):

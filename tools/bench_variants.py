@@ -1,7 +1,7 @@
 """A/B timing of bit-identical kernel variants on hardware (dph_set_tuning):  python tools/bench_variants.py [sgemm] [c2] [shard]
   sgemm : tile shapes of the sequential-k SGEMM at the OPQ-rotation / coarse shapes
   c2    : BASELINE.json configs[1] (100 M phrases, IVF4096, batch 64, nprobe 256) -- quad-scan IMAD levels; results must not change
-  shard : one rank of C4 (shard 0 of 8; batch 1024) at nprobe 256 and 32 -- IMAD levels and the two PQ-table kernels"""
+  shard : one rank of C4 (shard 0 of 8; batch 1024) at nprobe 256 and 32 -- list-split vs query-split coarse quantizer"""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -84,15 +84,22 @@ if "shard" in what:
             fkey = torch.where(bits >= 0x80000000, (~bits) & 0xFFFFFFFF, bits | 0x80000000)
             kg = torch.zeros((WORLD, B, nprobe), dtype=torch.int64, device="cuda"); kg[0] = (fkey << 32) | (0xFFFFFFFF - pr)
             keys_all.append(kg)
+        # records of the query-split protocol: every "rank" assigns its slice of 128 queries over all lists (here: this GPU, 8 times)
+        per = B // WORLD
+        recs = [torch.cat([ix.coarse_split(x[r * per:(r + 1) * per].contiguous()) for r in range(WORLD)]).contiguous() for x in X]
         base = None
-        combos = [(0, 1), (1, 1), (2, 1), (1, 2), (2, 2)] if nprobe == 256 else [(1, 1), (1, 2)]
-        for lvl, lv in combos:
-            tune(0, lvl); tune(2, lv)
-            fn = lambda i: (ix.coarse_local(X[i % 6]), ix.search_preassigned(keys_all[i % 6], K))
+        for proto in ("list-split", "query-split"):
+            if proto == "list-split":
+                fn = lambda i: (ix.coarse_local(X[i % 6]), ix.search_preassigned(keys_all[i % 6], K))
+                pre = lambda i: ix.coarse_local(X[i % 6])
+            else:
+                fn = lambda i: (ix.coarse_split(X[i % 6][:per]), ix.search_assigned(recs[i % 6], K))
+                pre = lambda i: ix.coarse_split(X[i % 6][:per])
+            ms_pre = timeit(pre, 12, warm=3)
             ms = timeit(fn, 12, warm=3)
             scan = np.mean(ix.profile_scan_ms()[-12:])
             _, (D, I, G) = fn(0)
             if base is None: base = (D.clone(), I.clone())
             same = bool((D == base[0]).all() and (I == base[1]).all())
-            print(f"C4 shard nprobe {nprobe}: imad {lvl} lut kernel {lv}: rank step {ms:.3f} ms -> {B / ms * 1000:.0f} QPS on 8 GPUs, scan {scan:.3f} ms, same results {same}", flush=True)
-    tune(0, 1); tune(2, 0)
+            print(f"C4 shard nprobe {nprobe} {proto}: rank step {ms:.3f} ms (before the exchange {ms_pre:.3f}) -> {B / ms * 1000:.0f} QPS on 8 GPUs, "
+                  f"scan {scan:.3f} ms, same results {same}", flush=True)
