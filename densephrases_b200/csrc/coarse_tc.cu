@@ -21,13 +21,22 @@ __device__ __forceinline__ float thread_exact_dot(const float* __restrict__ C, c
     if (li < 0) return 0.0f;
     const float4* row = reinterpret_cast<const float4*>(C + li * DPH_D);
     float acc = 0.0f;
-#pragma unroll 8
-    for (int t4 = 0; t4 < DPH_D / 4; t4++) {
-        const float4 c = __ldg(row + t4);
-        acc = fmaf(xq[4 * t4 + 0], c.x, acc);
-        acc = fmaf(xq[4 * t4 + 1], c.y, acc);
-        acc = fmaf(xq[4 * t4 + 2], c.z, acc);
-        acc = fmaf(xq[4 * t4 + 3], c.w, acc);
+    // explicit batches of 16 row loads in flight per thread (with one CTA per query and 64 ... 375 busy threads the kernel is L2-latency
+    // bound); the FMA chain itself stays t-ascending
+#pragma unroll 1
+    for (int t0 = 0; t0 < DPH_D / 4; t0 += 16) {
+        float4 c[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++)        // volatile asm: the optimiser otherwise sinks every load next to its use (two in flight)
+            asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(c[e].x), "=f"(c[e].y), "=f"(c[e].z), "=f"(c[e].w) : "l"(row + t0 + e));
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const int t4 = t0 + e;
+            acc = fmaf(xq[4 * t4 + 0], c[e].x, acc);
+            acc = fmaf(xq[4 * t4 + 1], c[e].y, acc);
+            acc = fmaf(xq[4 * t4 + 2], c[e].z, acc);
+            acc = fmaf(xq[4 * t4 + 3], c[e].w, acc);
+        }
     }
     return acc;
 }
@@ -41,7 +50,7 @@ struct CoarseTcArgs {
 };
 
 // one CTA per query: exact re-score of the candidates, final selection, proof.
-__global__ void __launch_bounds__(256) coarse_tc_finish_kernel(CoarseTcArgs a) {
+__global__ void __launch_bounds__(256, 3) coarse_tc_finish_kernel(CoarseTcArgs a) {     // <= 85 registers: room for 16 row loads in flight
     __shared__ float xq[DPH_D];
     __shared__ unsigned long long sel[DPH_MAX_NPROBE];
     __shared__ float red[8];
@@ -96,7 +105,7 @@ __global__ void __launch_bounds__(256) coarse_tc_finish_kernel(CoarseTcArgs a) {
 }
 
 // flagged queries only: exact scores for every list of the shard (same chain as sgemm_nt_seq), written to S_exact[q].
-__global__ void __launch_bounds__(256) coarse_tc_repair_kernel(CoarseTcArgs a) {
+__global__ void __launch_bounds__(256, 3) coarse_tc_repair_kernel(CoarseTcArgs a) {
     const long long q = blockIdx.x;
     if (a.flags[q] == 0) return;
     __shared__ float xq[DPH_D];

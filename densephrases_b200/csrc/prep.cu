@@ -535,35 +535,36 @@ int dph_launch_coarse_select(const float* S, int64_t n, int64_t nlist, int nprob
 // A CTA handles one 32-sub-quantizer segment for LQ = 4 queries: every codebook entry it fetches (2 float4 per thread and
 // sub-quantizer, from L2) is used for four queries, so the L2 -> SM stream is n/4 x 786 KB instead of n x 786 KB (at 1024 queries per
 // batch that stream -- 805 MB -- was what the kernel's 128 us were spent on, not the 100 MB of table writes).
-#define LQ 4
 #define LUT_TILE_LD 257                                  // [query][sub-quantizer][code] tile, code rows padded: conflict-free both ways
+// LQ queries x MS sub-quantizers per CTA (MS = 32 or 16; grid.y = 96 / MS).  <4, 32> reads n/4 x 786 KB of codebook; <8, 16> has the same
+// 131 KB tile and half that stream (every codebook entry serves eight queries), its table rows are written as 64-byte runs.
+template <int LQ, int MS>
 __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ xr, const float* __restrict__ pq, long long n,
                                                    float* __restrict__ lut_canon,
                                                    float* __restrict__ lutmax, float* __restrict__ lutmin, float* __restrict__ lutmaxv) {
     extern __shared__ __align__(16) float lut_sm[];
-    float* __restrict__ tile = lut_sm;                    // [LQ][32][LUT_TILE_LD]
-    __shared__ __align__(16) float xs[LQ * 256];          // a separate object: stores to `tile` cannot alias it, loads can be hoisted
+    float* __restrict__ tile = lut_sm;                    // [LQ][MS][LUT_TILE_LD]
+    __shared__ __align__(16) float xs[LQ * MS * 8];       // a separate object: stores to `tile` cannot alias it, loads can be hoisted
     const long long q0 = (long long)blockIdx.x * LQ;
-    const int seg = blockIdx.y, j = threadIdx.x, lane = j & 31, warp = j >> 5;
+    const int m0 = blockIdx.y * MS, j = threadIdx.x, lane = j & 31, warp = j >> 5;
     const int nq = (int)((n - q0) < LQ ? (n - q0) : LQ);
-#pragma unroll
-    for (int qi = 0; qi < LQ; qi++) xs[qi * 256 + j] = qi < nq ? xr[(q0 + qi) * DPH_D + seg * 256 + j] : 0.0f;
+    for (int i = j; i < LQ * MS * 8; i += 256) { const int qi = i / (MS * 8); xs[i] = qi < nq ? xr[(q0 + qi) * DPH_D + m0 * 8 + (i % (MS * 8))] : 0.0f; }
     __syncthreads();
     // software pipeline over batches of 8 sub-quantizers: the 16 codebook loads of batch b + 1 are issued before batch b is consumed
-    // (loop-carried, so the scheduler cannot sink them next to their uses); the loop is otherwise L2-latency bound (one CTA per SM)
+    // (loop-carried, so the scheduler cannot sink them next to their uses)
     float4 c0[8], c1[8];
 #pragma unroll
     for (int u = 0; u < 8; u++) {
-        const float4* cb = reinterpret_cast<const float4*>(pq + ((size_t)(seg * 32 + u) * 256 + j) * 8);
+        const float4* cb = reinterpret_cast<const float4*>(pq + ((size_t)(m0 + u) * 256 + j) * 8);
         c0[u] = __ldg(cb); c1[u] = __ldg(cb + 1);
     }
 #pragma unroll 1
-    for (int ml0 = 0; ml0 < 32; ml0 += 8) {
+    for (int ml0 = 0; ml0 < MS; ml0 += 8) {
         float4 n0[8], n1[8];
-        if (ml0 + 8 < 32) {
+        if (ml0 + 8 < MS) {
 #pragma unroll
             for (int u = 0; u < 8; u++) {
-                const float4* cb = reinterpret_cast<const float4*>(pq + ((size_t)(seg * 32 + ml0 + 8 + u) * 256 + j) * 8);
+                const float4* cb = reinterpret_cast<const float4*>(pq + ((size_t)(m0 + ml0 + 8 + u) * 256 + j) * 8);
                 n0[u] = __ldg(cb); n1[u] = __ldg(cb + 1);
             }
         }
@@ -572,12 +573,12 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ xr, 
             const int ml = ml0 + u;
 #pragma unroll
             for (int qi = 0; qi < LQ; qi++) {
-                const float4 x0 = *reinterpret_cast<const float4*>(xs + qi * 256 + ml * 8);
-                const float4 x1 = *reinterpret_cast<const float4*>(xs + qi * 256 + ml * 8 + 4);
+                const float4 x0 = *reinterpret_cast<const float4*>(xs + (qi * MS + ml) * 8);
+                const float4 x1 = *reinterpret_cast<const float4*>(xs + (qi * MS + ml) * 8 + 4);
                 float acc = 0.0f;                        // one sequential FMA chain over the 8 sub-dimensions (compute_inner_prod_table)
                 acc = fmaf(x0.x, c0[u].x, acc); acc = fmaf(x0.y, c0[u].y, acc); acc = fmaf(x0.z, c0[u].z, acc); acc = fmaf(x0.w, c0[u].w, acc);
                 acc = fmaf(x1.x, c1[u].x, acc); acc = fmaf(x1.y, c1[u].y, acc); acc = fmaf(x1.z, c1[u].z, acc); acc = fmaf(x1.w, c1[u].w, acc);
-                tile[(qi * 32 + ml) * LUT_TILE_LD + j] = acc;
+                tile[(qi * MS + ml) * LUT_TILE_LD + j] = acc;
             }
         }
 #pragma unroll
@@ -585,7 +586,7 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ xr, 
     }
     __syncthreads();
     // per (query, sub-quantizer): max |entry|, min, max over the 256 codes -- one warp per pair, 8 entries per lane
-    for (int p = warp; p < nq * 32; p += 8) {
+    for (int p = warp; p < nq * MS; p += 8) {
         const float* row = tile + p * LUT_TILE_LD;
         float a = 0.0f, lo = row[lane], hi = lo;
 #pragma unroll
@@ -597,15 +598,16 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ xr, 
             hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
         }
         if (lane == 0) {
-            const long long o = (q0 + (p >> 5)) * DPH_M + seg * 32 + (p & 31);
+            const long long o = (q0 + p / MS) * DPH_M + m0 + (p % MS);
             lutmax[o] = a; lutmin[o] = lo; lutmaxv[o] = hi;
         }
     }
-    // canonical table rows [code][m % 32]: consecutive threads -> consecutive m (coalesced stores, conflict-free tile reads)
+    // canonical table rows [code][m % 32]: consecutive threads -> consecutive m (runs of MS floats; the tile is read column-wise)
+    const int seg = m0 >> 5, mo = m0 & 31;
     for (int qi = 0; qi < nq; qi++) {
-        float* dst = lut_canon + (size_t)(q0 + qi) * DPH_LUT_CANON_FLOATS + (size_t)seg * (256 * 32);
-        const float* t = tile + qi * 32 * LUT_TILE_LD;
-        for (int idx = j; idx < 256 * 32; idx += 256) dst[idx] = t[(idx & 31) * LUT_TILE_LD + (idx >> 5)];
+        float* dst = lut_canon + (size_t)(q0 + qi) * DPH_LUT_CANON_FLOATS + (size_t)seg * (256 * 32) + mo;
+        const float* t = tile + qi * MS * LUT_TILE_LD;
+        for (int idx = j; idx < 256 * MS; idx += 256) dst[(idx / MS) * 32 + (idx % MS)] = t[(idx % MS) * LUT_TILE_LD + (idx / MS)];
     }
 }
 
@@ -649,10 +651,18 @@ __global__ void __launch_bounds__(256) lutq_kernel(const float* __restrict__ lut
 int dph_launch_lut(const float* xr, int64_t n, const float* pq, float* lut_canon, float* lutmax, float* lutmin, float* lutmaxv,
                    void* lutq, float2* qparams, cudaStream_t st, int group) {
     if (n == 0) return 0;
-    const size_t lut_smem = (size_t)(LQ * 32 * LUT_TILE_LD) * 4;
     static DphPerDeviceOnce lut_once;
-    if (lut_once.first()) { DPH_CUDA(cudaFuncSetAttribute(lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_smem)); }
-    lut_kernel<<<dim3((unsigned)((n + LQ - 1) / LQ), 3), 256, lut_smem, st>>>(xr, pq, n, lut_canon, lutmax, lutmin, lutmaxv);
+    constexpr int lut_smem = 4 * 32 * LUT_TILE_LD * 4;        // both shapes: 128 (query, sub-quantizer) rows
+    if (lut_once.first()) {
+        DPH_CUDA(cudaFuncSetAttribute(lut_kernel<4, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, lut_smem));
+        DPH_CUDA(cudaFuncSetAttribute(lut_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, lut_smem));
+    }
+    // knob 2 of dph_set_tuning: 2 selects <8, 16>.  Measured on one shard of C4 (1024 queries, tools/bench_variants.py shard,
+    // profiles/r2p_variants.txt): no faster than <4, 32> (rank step 4.499 vs 4.500 ms at nprobe 256, 1.500 vs 1.479 ms at nprobe 32) -- the
+    // kernel is bound by its per-CTA latency chain, not by the codebook stream -- so <4, 32> stays the default.
+    const int lv = g_dph_tune[2];
+    if (lv == 2) lut_kernel<8, 16><<<dim3((unsigned)((n + 7) / 8), 6), 256, lut_smem, st>>>(xr, pq, n, lut_canon, lutmax, lutmin, lutmaxv);
+    else lut_kernel<4, 32><<<dim3((unsigned)((n + 3) / 4), 3), 256, lut_smem, st>>>(xr, pq, n, lut_canon, lutmax, lutmin, lutmaxv);
     DPH_CUDA(cudaGetLastError());
     if (lutq) {
         if (group == 4) lutq_kernel<unsigned char, DPH_QMAX8><<<dim3((unsigned)n, 3), 256, 0, st>>>(lut_canon, lutmin, lutmaxv, (unsigned char*)lutq, qparams);

@@ -834,15 +834,18 @@ struct MergeArgs {
     float* D; long long* I; unsigned* G; int* flags; const int* only_flagged;
 };
 
-__device__ __forceinline__ int find_seg(const DphSeg* segs, int nprobe, unsigned gidx) {
-    int lo = 0, hi = nprobe;   // last r with gstart <= gidx
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (segs[mid].gstart <= gidx) lo = mid; else hi = mid; }
+// last segment r with gstart[r] <= gidx; gstart = the query's segment starts, staged in shared memory by the caller (a binary search
+// over the descriptors in global memory is a chain of ~8 dependent L2 round trips per survivor)
+__device__ __forceinline__ int find_seg(const unsigned* gstart, int nsg, unsigned gidx) {
+    int lo = 0, hi = nsg;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (gstart[mid] <= gidx) lo = mid; else hi = mid; }
     return lo;
 }
 
 __global__ void __launch_bounds__(256) merge_kernel(MergeArgs a) {
     __shared__ SelectScratch sc;
     __shared__ unsigned long long surv[DPH_SURV_CAP];
+    __shared__ unsigned sgs[DPH_MAX_NPROBE];
     __shared__ int scnt, sflag;
     const long long q = blockIdx.x;
     const int tid = threadIdx.x;
@@ -856,6 +859,7 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeArgs a) {
     const int nsg = a.nseg[q];
     const int k = a.k;
     if (tid == 0) { scnt = 0; sflag = 0; }
+    for (int i = tid; i < nsg; i += blockDim.x) sgs[i] = segs[i].gstart;
     __syncthreads();
     auto get = [&](int i) { return E[i]; };
     unsigned long long pivot = 0ull;   // gather keys >= pivot
@@ -887,7 +891,7 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeArgs a) {
         const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
         for (int i = warp; i < ns; i += nwarps) {
             const unsigned gidx = dph_ckey_gidx(surv[i]);
-            const DphSeg s = segs[find_seg(segs, nsg, gidx)];
+            const DphSeg s = segs[find_seg(sgs, nsg, gidx)];
             const unsigned j = gidx - s.gstart;
             const uint8_t* blk = a.codes + (s.blk + (long long)(j >> 5)) * DPH_BLK_BYTES;
             const int ln = (int)(j & 31u);
@@ -915,7 +919,7 @@ __global__ void __launch_bounds__(256) merge_kernel(MergeArgs a) {
         if (i < ns) {
             const unsigned long long e = surv[i];
             gi = dph_ckey_gidx(e); d = dph_ckey_score(e);
-            const DphSeg s = segs[find_seg(segs, nsg, gi)];
+            const DphSeg s = segs[find_seg(sgs, nsg, gi)];
             const unsigned j = gi - s.gstart;
             id = a.ids ? a.ids[s.blk * 32 + j] : a.list_start[s.list] + (long long)j;
         }

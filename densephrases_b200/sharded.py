@@ -60,7 +60,18 @@ def sharded_search(x, k, world, group, coarse_local, search_preassigned, pack, m
     return merge_packed(Pg.view(world, n, k, 2), k)
 
 
-def sharded_search_qsplit(x, k, world, rank, group, coarse_split, search_assigned, pack, merge_packed):
+def query_slice(x, rank, world):
+    """Rows [r P, (r+1) P) of the batch, P = ceil(n / W), zero rows padding the last slice (x: torch tensor on any device)."""
+    n = x.shape[0]
+    per = (n + world - 1) // world
+    lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+    xl = x[lo:hi]
+    if hi - lo < per:
+        xl = torch.cat([xl, torch.zeros((per - (hi - lo), x.shape[1]), dtype=x.dtype, device=x.device)])
+    return xl.contiguous()
+
+
+def sharded_search_qsplit(x, k, world, rank, group, coarse_split, search_assigned, pack, merge_packed, x_local=None, n=None):
     """The query-split protocol (large batches): the coarse quantizer is replicated, so rank r rotates and assigns queries
     [r P, (r+1) P) of the batch (P = ceil(n / W), zero rows pad the last slice) over ALL lists and the ranks exchange the results:
         rec    = coarse_split(x[r P : (r+1) P])      [P, 768 + 2 nprobe]  rotated query | probed lists | coarse scores
@@ -68,16 +79,15 @@ def sharded_search_qsplit(x, k, world, rank, group, coarse_split, search_assigne
         D,I,G  = search_assigned(rec_g, k)           per-shard partial top-k over the global probe set
         P_g    = all_gather(pack(D, I, G))           [W, n, k, 2]         exchange 2
         return merge_packed(P_g, k)
-    Same probes, same scores as sharded_search; the per-query work before the scan is done once instead of once per rank."""
+    Same probes, same scores as sharded_search; the per-query work before the scan is done once instead of once per rank.
+    A caller that holds the batch on the host passes only its slice (x_local = query_slice(x_host, rank, world) on the device, n =
+    the batch size): then a rank's host-to-device copy is n / W rows instead of n."""
     import torch.distributed as dist
-    n = x.shape[0]
-    per = (n + world - 1) // world
-    lo, hi = min(rank * per, n), min((rank + 1) * per, n)
-    xl = x[lo:hi]
-    if hi - lo < per:
-        xl = torch.cat([xl, torch.zeros((per - (hi - lo), x.shape[1]), dtype=x.dtype, device=x.device)])
-    rec = coarse_split(xl.contiguous())
-    rec_g = torch.empty((world * per, rec.shape[1]), dtype=rec.dtype, device=rec.device)
+    if x_local is None:
+        n = x.shape[0]
+        x_local = query_slice(x, rank, world)
+    rec = coarse_split(x_local)
+    rec_g = torch.empty((world * x_local.shape[0], rec.shape[1]), dtype=rec.dtype, device=rec.device)
     dist.all_gather_into_tensor(rec_g, rec.contiguous(), group=group)
     D, I, G = search_assigned(rec_g[:n], k)
     P = pack(D, I, G)
@@ -176,6 +186,9 @@ class ShardedIvfPq:
     def nprobe(self, v):
         self.local.nprobe = v
 
+    def _qsplit(self, n):
+        return self.world > 1 and (self.query_split is True or (self.query_split is None and use_query_split(n, self.world, self.local.nlist)))
+
     def search_device(self, x, k):
         """x torch cuda [n,d] (same on every rank) -> (D, I) torch cuda [n,k] (same on every rank)."""
         if self.world == 1:
@@ -184,7 +197,7 @@ class ShardedIvfPq:
         if n > 4096:        # one chunk per collective round
             parts = [self.search_device(x[i:i + 4096], k) for i in range(0, n, 4096)]
             return torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
-        if self.query_split is True or (self.query_split is None and use_query_split(n, self.world, self.local.nlist)):
+        if self._qsplit(n):
             return sharded_search_qsplit(x, k, self.world, self.rank, self.group, self.local.coarse_split, self.local.search_assigned, pack_topk,
                                          merge_shards_packed)
         return sharded_search(x, k, self.world, self.group, self.local.coarse_local, self.local.search_preassigned, pack_topk, merge_shards_packed)
@@ -196,8 +209,12 @@ class ShardedIvfPq:
         xt = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)) if isinstance(x, np.ndarray) else x
         n = xt.shape[0]
         dev = torch.device("cuda", self.device)
-        xd = xt.to(dev, non_blocking=True)
-        D, I = self.search_device(xd, k)
+        if n <= 4096 and self._qsplit(n):        # query-split: only this rank's slice of the batch crosses PCIe
+            xl = query_slice(xt, self.rank, self.world).to(dev, non_blocking=True)
+            D, I = sharded_search_qsplit(None, k, self.world, self.rank, self.group, self.local.coarse_split, self.local.search_assigned, pack_topk,
+                                         merge_shards_packed, x_local=xl, n=n)
+        else:
+            D, I = self.search_device(xt.to(dev, non_blocking=True), k)
         if self._pinned_out is None or self._pinned_out[0].shape != (n, k):
             self._pinned_out = (torch.empty((n, k), dtype=torch.float32).pin_memory(), torch.empty((n, k), dtype=torch.int64).pin_memory())
         Dh, Ih = self._pinned_out

@@ -182,7 +182,8 @@ int dph_gemm_tf32_nt(const float* A, const float* W, const float* bias, const fl
 int dph_gemm_tf32_set_mode(int mode);
 /* Measurement hook (process-wide): choose between kernel variants that compute bit-identical results, for A/B timing on hardware
  * (tools/bench_variants.py).  knob 0: additions of the quad scan issued on the FMA pipe (0 none .. 3 all; default 1);
- * knob 1: tile shape of the sequential-k SGEMM (0 auto, 1: 128x128, 2: 64x64, 3: 32x64, 4: 16x64). */
+ * knob 1: tile shape of the sequential-k SGEMM (0 auto, 1: 128x128, 2: 64x64, 3: 32x64, 4: 16x64);
+ * knob 2: shape of the PQ-table kernel (default: 4 queries x 32 sub-quantizers per CTA; 2: 8 x 16). */
 int dph_set_tuning(int knob, int value);
 
 #ifdef __cplusplus

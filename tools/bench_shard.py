@@ -1,14 +1,16 @@
 """One rank of BASELINE.json configs[3] (C4): 1B phrases, IVF65536,PQ96, 8 list-range shards, batch 1024 -- measured on ONE B200
-by building shard 0 only (125M phrases, 12 GB) and timing the rank-local work of a sharded search:
-    coarse_local (this shard's 8192 centroids)  +  search_preassigned (LUT, plan, scan of this shard's probed lists, merge)
-(the two NCCL all-gathers, ~2 x 20 us, are not included).  Projected 8-GPU QPS = 1024 / rank step time.
+by building shard 0 only (125M phrases, 12 GB) and timing the rank-local work of a sharded search with the protocol the product
+picks for the shape (densephrases_b200.sharded.use_query_split):
+    query-split (C4):  coarse_split (this rank's 128 queries over all 65536 centroids)  +  search_assigned (LUT, plan, scan, merge)
+    list-split  (C5):  coarse_local (all queries over this shard's centroids)           +  search_preassigned
+(the two NCCL all-gathers, ~2 x 20 us, are not included).  Projected 8-GPU QPS = batch / rank step time.
 python tools/bench_shard.py [c4|c5] [auto|single|pair|quad] [nprobe ...]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
 from densephrases_b200 import IvfPqIndex
-from densephrases_b200.sharded import shard_ranges
+from densephrases_b200.sharded import shard_ranges, use_query_split
 
 CONFIGS = {"c4": (1_000_000_000, 65536, 8, 1024, 10),       # BASELINE.json configs[3]
            "c5": (580_000_000, 1_048_576, 8, 128, 10)}       # configs[4]: multi_wiki-scale dump, IVF1048576, eval batch 64 questions = 128 vectors
@@ -34,6 +36,9 @@ ix.set_scan_mode(MODES[mode])
 for nprobe in [int(a) for a in sys.argv[1:]] or [256, 32]:
     ix.nprobe = nprobe
     res = {}
+    qsplit = use_query_split(B, WORLD, NLIST)
+    per = (B + WORLD - 1) // WORLD
+    recs = [torch.cat([ix.coarse_split(x[r * per:(r + 1) * per].contiguous()) for r in range(WORLD)]).contiguous() for x in X] if qsplit else None
     for name in ("coarse_local", "preassigned"):
         keys_all = []
         for x in X:      # global probes of each batch via the replicated path, re-expressed as gathered keys in slot 0
@@ -45,7 +50,10 @@ for nprobe in [int(a) for a in sys.argv[1:]] or [256, 32]:
             key = (fkey << 32) | (0xFFFFFFFF - pr)
             kg = torch.zeros((WORLD, B, nprobe), dtype=torch.int64, device="cuda"); kg[0] = key
             keys_all.append(kg)
-        fn = (lambda i: ix.coarse_local(X[i])) if name == "coarse_local" else (lambda i: (ix.coarse_local(X[i]), ix.search_preassigned(keys_all[i], K)))
+        if qsplit:
+            fn = (lambda i: ix.coarse_split(X[i][:per])) if name == "coarse_local" else (lambda i: (ix.coarse_split(X[i][:per]), ix.search_assigned(recs[i], K)))
+        else:
+            fn = (lambda i: ix.coarse_local(X[i])) if name == "coarse_local" else (lambda i: (ix.coarse_local(X[i]), ix.search_preassigned(keys_all[i], K)))
         for i in range(3): fn(i)
         torch.cuda.synchronize(); e0.record()
         for i in range(3, 6): fn(i)
@@ -55,6 +63,6 @@ for nprobe in [int(a) for a in sys.argv[1:]] or [256, 32]:
     pr = ix.last_probes(B).astype(np.int64); m = (pr >= lo) & (pr < hi)
     gb = float(lens[pr[m]].sum()) * 96 / 1e9
     step = res["preassigned"]
-    print(f"nprobe={nprobe} mode={mode}: rank step {step:.3f} ms (coarse_local {res['coarse_local']:.3f} ms), queries/gather={ix.last_group_size()}, "
+    print(f"nprobe={nprobe} mode={mode} {'query-split' if qsplit else 'list-split'}: rank step {step:.3f} ms (before the exchange {res['coarse_local']:.3f} ms), queries/gather={ix.last_group_size()}, "
           f"algorithmic {gb:.2f} GB/rank/step = {gb/step*1000:.0f} GB/s; projected 8-GPU {B/step*1000:.0f} QPS "
           f"(HBM roofline {8*6590.9/(gb*8/B):.0f} QPS)", flush=True)

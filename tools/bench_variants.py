@@ -88,7 +88,8 @@ if "shard" in what:
         per = B // WORLD
         recs = [torch.cat([ix.coarse_split(x[r * per:(r + 1) * per].contiguous()) for r in range(WORLD)]).contiguous() for x in X]
         base = None
-        for proto in ("list-split", "query-split"):
+        for proto in ("list-split", "query-split", "query-split lut<8,16>"):
+            tune(2, 2 if proto.endswith("16>") else 1)
             if proto == "list-split":
                 fn = lambda i: (ix.coarse_local(X[i % 6]), ix.search_preassigned(keys_all[i % 6], K))
                 pre = lambda i: ix.coarse_local(X[i % 6])
@@ -103,3 +104,4 @@ if "shard" in what:
             same = bool((D == base[0]).all() and (I == base[1]).all())
             print(f"C4 shard nprobe {nprobe} {proto}: rank step {ms:.3f} ms (before the exchange {ms_pre:.3f}) -> {B / ms * 1000:.0f} QPS on 8 GPUs, "
                   f"scan {scan:.3f} ms, same results {same}", flush=True)
+        tune(2, 0)
