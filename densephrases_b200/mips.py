@@ -225,8 +225,17 @@ class MIPS(object):
         `nprobe` is accepted and ignored, like the reference (its assignment is commented out at index.py:191)."""
         B = query.shape[0]
         tic = time()
-        halves = np.split(query.astype(np.float32), 2, axis=1)
-        scores, labels = self.index.search(np.concatenate(halves, axis=0), top_k)
+        if isinstance(query, torch.Tensor) and query.is_cuda and hasattr(self.index, 'search_device'):
+            # device-resident queries (DensePhrases.search hands over the encoder's output): no host round trip before the index
+            d = query.shape[1] // 2
+            x = torch.cat([query[:, :d], query[:, d:]], 0).float().contiguous()
+            Dd, Id = self.index.search_device(x, top_k)
+            scores, labels = Dd.cpu().numpy(), Id.cpu().numpy()
+        else:
+            if isinstance(query, torch.Tensor):
+                query = query.detach().cpu().numpy()
+            halves = np.split(query.astype(np.float32), 2, axis=1)
+            scores, labels = self.index.search(np.concatenate(halves, axis=0), top_k)
         self.stage_seconds['mips'] += time() - tic
         self.stage_seconds['batches'] += 1
         logger.debug(f'1) {time()-tic:.3f}s: MIPS')
@@ -388,6 +397,8 @@ class MIPS(object):
         tic = time()
         dense = self.search_dense(query, q_texts=q_texts, nprobe=nprobe, top_k=top_k)
         s_doc, s_word, s_lab, e_doc, e_word, e_lab, s_sc, e_sc = dense
+        if isinstance(query, torch.Tensor):          # the phrase stage and the result dicts work on host arrays
+            query = query.detach().cpu().numpy()
         logger.debug(f'Top-{top_k} MIPS: {time()-tic:.3f}s')
         tic = time()
         outs = self.search_phrase(query, s_doc, s_word, s_lab, e_doc, e_word, e_lab, s_sc, e_sc, top_k=top_k,

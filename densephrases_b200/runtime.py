@@ -157,17 +157,34 @@ def load_phrase_index(args, ignore_logging=False):
 
 
 def get_query2vec(query_encoder, tokenizer, args, batch_size=64):
-    """-> query2vec(list[str]) -> list of (start_vec [1][768] list, end_vec [1][768] list, tokens) like open_utils.py:85-100."""
-    def query2vec(queries):
-        outs = []
+    """-> query2vec(list[str]) -> list of (start_vec [1][768] list, end_vec [1][768] list, tokens) like open_utils.py:85-100.
+    The returned function also carries `query2vec.tensors(list[str]) -> (start [n,768], end [n,768] torch tensors on the encoder's
+    device, tokens)`: the same vectors without the per-question Python lists of the reference's contract (768 floats -> list -> back
+    to an array costs more than the encoder forward); DensePhrases.search and embed_all_query use it (SURVEY.md 8f #3)."""
+    def encode(queries):
         for i in range(0, len(queries), batch_size):
             feats = [tokenizer.encode_question(q, args.max_query_length) for q in queries[i:i + batch_size]]
             ids, mask, tt = (torch.tensor([f[j] for f in feats], dtype=torch.int64) for j in range(3))
             with torch.no_grad():
                 start, end = query_encoder(input_ids_=ids, attention_mask_=mask, token_type_ids_=tt, return_query=True)
+            yield start, end, feats
+
+    def query2vec(queries):
+        outs = []
+        for start, end, feats in encode(queries):
             start, end = start.cpu().numpy(), end.cpu().numpy()       # one device->host copy per batch (reference: one per row)
             outs += [(start[j].tolist(), end[j].tolist(), feats[j][3]) for j in range(len(feats))]
         return outs
+
+    def tensors(queries):
+        starts, ends, toks = [], [], []
+        for start, end, feats in encode(queries):
+            starts.append(start[:, 0]); ends.append(end[:, 0]); toks += [f[3] for f in feats]
+        if not starts:
+            z = torch.zeros((0, 768), dtype=torch.float32)
+            return z, z, toks
+        return torch.cat(starts, 0), torch.cat(ends, 0), toks
+    query2vec.tensors = tensors
     return query2vec
 
 
@@ -211,12 +228,10 @@ def load_qa_pairs(data_path, args, q_idx=None, draft_num_examples=100, shuffle=F
 # ---- eval_phrase_retrieval ---------------------------------------------------------------------------------------
 def embed_all_query(questions, args, query_encoder, tokenizer, batch_size=64):
     query2vec = get_query2vec(query_encoder=query_encoder, tokenizer=tokenizer, args=args, batch_size=batch_size)
-    outs = []
-    for i in range(0, len(questions), batch_size):
-        outs += query2vec(questions[i:i + batch_size])
-    start = np.concatenate([o[0] for o in outs], 0)
-    end = np.concatenate([o[1] for o in outs], 0)
-    return np.concatenate([start, end], 1)
+    # open_utils.py:103-117 concatenates the per-question lists; the same array (float64 like an array built from Python floats, same
+    # values) comes from one device->host copy per batch
+    start, end, _ = query2vec.tensors(questions)
+    return np.concatenate([start.cpu().numpy(), end.cpu().numpy()], 1).astype(np.float64)
 
 
 def evaluate(args, mips=None, query_encoder=None, tokenizer=None, q_idx=None):
@@ -297,8 +312,12 @@ class DensePhrases(object):
             # never reaches the encoder or the result dicts.  Reproduced as is (same results on the same inputs); the evaluation
             # path (load_qa_pairs, open_utils.py:147-154) does use the truecased questions.
             query = truecase_questions(self.truecase, batch_query)
-        outs = self.query2vec(batch_query)
-        query_vec = np.concatenate([np.concatenate([o[0] for o in outs], 0), np.concatenate([o[1] for o in outs], 0)], 1)
+        if hasattr(self.query2vec, 'tensors'):        # encoder output stays a tensor on its device until the index has searched it
+            start, end, _ = self.query2vec.tensors(batch_query)
+            query_vec = torch.cat([start, end], 1)
+        else:                                         # a caller-supplied query2vec with the reference's list contract (model.py:69-73)
+            outs = self.query2vec(batch_query)
+            query_vec = np.concatenate([np.concatenate([o[0] for o in outs], 0), np.concatenate([o[1] for o in outs], 0)], 1)
         search_top_k = top_k * 2 if retrieval_unit in ('sentence', 'paragraph', 'document') else top_k
         rets = self.mips.search(query_vec, q_texts=batch_query, nprobe=256, top_k=search_top_k, max_answer_length=10, return_idxs=False,
                                 aggregate=True, agg_strat=self._AGG[retrieval_unit], return_sent=retrieval_unit == 'sentence')
