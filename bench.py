@@ -244,14 +244,55 @@ def run_reference(args):
               f", OpenMP over queries on {cores} threads")
     # C1 (BASELINE.json configs[0]): the reference's own CPU-runnable case
     c1 = c1_cpu(oracle, cores)
+    # C3 (configs[2]) on the host, N = 1 only (the GPU arm reports it in `encoder.c3`)
+    c3 = c3_cpu(oracle, cores, wl, ref) if args.gpus == 1 else None
     line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
             "steps": K, "warmup": W, "ms_per_step": 1000.0 * t / K, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(wl, args.gpus), "where": "host cpu",
             "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
             "step_ms_min_max": [1000.0 * min(times[W:]), 1000.0 * max(times[W:])], "c1": c1}
+    if c3 is not None:
+        line["c3"] = c3
     emit(line)
     return 0
+
+
+def c3_cpu(oracle, cores, wl, ref):
+    """C3 on the host: 64 questions (the GPU arm's token ids and weights: same seeds) -> both towers under torch on the CPU cores
+    (oracle/encoder_ref.py, the restatement pinned to the reference Encoder: the reference's own path is torch eager fp32,
+    single_utils.py:116) -> ONE stacked 128-vector search of the C2 index by the FAISS-equivalent restatement."""
+    import torch
+    from densephrases_b200.encoder import BertGeometry, random_state_dict, synthetic_query_batch      # seeded data generators only
+    from oracle import encoder_ref
+    geo = BertGeometry()
+    sd = random_state_dict(geo, 1)
+    ids, mask, tt = synthetic_query_batch(64, 64, geo.vocab_size, 2)
+    best = None
+    for threads in sorted({max(1, min(cores, 32)), max(1, cores)}):       # MKL does not always scale to every core: keep the better setting
+        torch.set_num_threads(threads)
+        encoder_ref.embed_query(sd, ids[:4], mask[:4], tt[:4])
+        t0 = time.perf_counter()
+        s, e = encoder_ref.embed_query(sd, ids, mask, tt)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, threads)
+    t_enc, enc_threads = best
+    x = torch.cat([s[:, 0], e[:, 0]], 0).numpy()
+    xr = ref.rotate(x)
+    _, key = ref.coarse(xr, wl["nprobe"])
+    lists = np.unique(key[key >= 0])
+    need_gb = float(ref.list_len[lists].sum()) * 96 / 1e9
+    rr = ref.with_resident_lists(lists) if need_gb <= 64.0 else ref
+    t0 = time.perf_counter()
+    xr = rr.rotate(x)
+    _, key = rr.coarse(xr, wl["nprobe"])
+    rr.search_preassigned(xr, key, wl["k"])
+    t_search = time.perf_counter() - t0
+    return {"questions_per_s": 64.0 / (t_enc + t_search), "ms_per_64_questions": 1000.0 * (t_enc + t_search),
+            "encoder_ms": 1000.0 * t_enc, "encoder_threads": enc_threads, "search_ms": 1000.0 * t_search, "search_threads": cores, "kind": "port",
+            "what": "64 questions: both towers under torch fp32 on the host cores + one stacked 128-vector search on the C2 index "
+                    f"({need_gb:.1f} GB of probed lists resident in RAM)"}
 
 
 def c1_cpu(oracle, cores, x=None):
@@ -360,7 +401,16 @@ def measure_search(cx, ix, wl, Q, Qh, nprobe, sample_clocks=False):
     # step-level fraction of the HBM roofline: all ranks' algorithmic bytes / (step time x N x peak)
     tot_bytes = cx.sum_over_ranks(mean_bytes)
     step_frac = tot_bytes / (ms_dev / K / 1000.0) / 1e9 / (cx.world * pk["hbm_gbs"])
-    launches = (18 if pair_mode else 12) + (3 if cx.world > 1 else 0)
+    # kernels of this repo launched per search step (counted from the per-launch lists in profiles/: r2q_launches_c2.csv,
+    # r2q_launches_shard_c4_np*.csv): one GPU: rotation, coarse quantizer, tables, plan, scan, merge, 4 early-exit fallback launches;
+    # sharded: + record pack / unpack (query-split) or coarse merge (list-split), + top-k pack and merge
+    from densephrases_b200.sharded import use_query_split
+    if cx.world == 1:
+        launches = 18 if pair_mode else 12
+    elif use_query_split(B, cx.world, wl["nlist"]):
+        launches = 26 if pair_mode else 21
+    else:
+        launches = 21 if pair_mode else 15
     return {"nprobe": nprobe, "value": B * K / (ms_dev / 1000.0), "ms_per_step": ms_dev / K,
             "e2e": {"value": B * K / (ms_e2e / 1000.0), "unit": "queries/s", "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * k * 12,
                     "ms_per_step": ms_e2e / K},
