@@ -1,6 +1,8 @@
 """ShardedIvfPq: the phrase index sharded by inverted-list range over the ranks of one torch.distributed job
 (SURVEY.md 8e): every rank holds lists [lo, hi), replicated coarse quantizer / OPQ / PQ codebooks; a search is
-  per-rank partial top-k  ->  ONE all-gather of (score, label, scan position) per shard  ->  identical k-way merge.
+  coarse step (exchange 1: query-split records or list-split candidate keys, see sharded_search_qsplit / sharded_search)
+  ->  per-rank partial top-k over the global probe set  ->  exchange 2: ONE all-gather of the packed (candidate key, label) pairs
+  ->  identical k-way merge on every rank.
 With world_size 1 it degenerates to IvfPqIndex.  This is the call a user (MIPS.search_dense) makes."""
 import numpy as np
 import torch

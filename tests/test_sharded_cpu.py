@@ -26,6 +26,22 @@ def test_shard_ranges_balance_by_bytes():
     assert a0 == 0 and a1 == b0 and b1 == 4 and 1 <= a1 <= 3
 
 
+def test_query_slice_and_protocol_choice():
+    """Slices of the query-split protocol: contiguous, P = ceil(n / W) rows each, zero rows pad the tail; their concatenation cut to
+    n rows is the batch.  use_query_split: large batches over a moderate number of lists only."""
+    from densephrases_b200.sharded import query_slice, use_query_split
+    x = torch.arange(7 * 3, dtype=torch.float32).reshape(7, 3) + 1
+    for world in (1, 2, 3, 8):
+        parts = [query_slice(x, r, world) for r in range(world)]
+        per = (7 + world - 1) // world
+        assert all(p.shape == (per, 3) and p.is_contiguous() for p in parts)
+        cat = torch.cat(parts)
+        assert torch.equal(cat[:7], x) and not cat[7:].any()
+    assert use_query_split(1024, 8, 65536) and use_query_split(1024, 2, 65536)          # C4
+    assert not use_query_split(128, 8, 1048576) and not use_query_split(64, 8, 4096)     # C5 (few queries, 1M lists); small batches
+    assert not use_query_split(1024, 1, 65536)
+
+
 def numpy_merge(Dg, Ig, Gg, k):
     Dg, Ig, Gg = Dg.numpy(), Ig.numpy(), Gg.numpy().astype(np.int64) & 0xFFFFFFFF
     nsh, n, _ = Dg.shape
