@@ -263,11 +263,27 @@ REF_API void ref_search_preassigned(const ref_index* ix, const float* xr, int64_
                 centroid_row(ix, l, cen);
                 float dis0 = dot_seq(q, cen, ix->d);                       /* set_list: fvec_inner_product(qi, centroid) */
                 const uint8_t* codes = list_codes(ix, l, &scratch, &cap);
-                for (int64_t j = 0; j < len; j++) {                         /* scan_list_with_table */
-                    const uint8_t* c = codes + j * ix->code_size;
+                /* scan_list_with_table.  Four code rows are summed side by side (four independent chains, each still
+                 * dis = dis0; for m asc: dis += LUT[m][c[m]] -- the values are those of the one-row loop bit for bit) so that
+                 * the 96-long dependent add chain of one row overlaps the next rows' on any core; the heap sees the rows in
+                 * storage order. */
+                const int64_t cs = ix->code_size; const int M = ix->M, ksub = ix->ksub;
+                int64_t j = 0;
+                for (; j + 4 <= len; j += 4) {
+                    const uint8_t* c0 = codes + j * cs; const uint8_t* c1 = c0 + cs; const uint8_t* c2 = c1 + cs; const uint8_t* c3 = c2 + cs;
+                    const float* tab = lut;
+                    float d0 = dis0, d1 = dis0, d2 = dis0, d3 = dis0;
+                    for (int m = 0; m < M; m++) { d0 += tab[c0[m]]; d1 += tab[c1[m]]; d2 += tab[c2[m]]; d3 += tab[c3[m]]; tab += ksub; }
+                    if (simi[0] < d0) { heap_pop(k, simi, idxi); heap_push(k, simi, idxi, d0, list_id(ix, l, j)); }
+                    if (simi[0] < d1) { heap_pop(k, simi, idxi); heap_push(k, simi, idxi, d1, list_id(ix, l, j + 1)); }
+                    if (simi[0] < d2) { heap_pop(k, simi, idxi); heap_push(k, simi, idxi, d2, list_id(ix, l, j + 2)); }
+                    if (simi[0] < d3) { heap_pop(k, simi, idxi); heap_push(k, simi, idxi, d3, list_id(ix, l, j + 3)); }
+                }
+                for (; j < len; j++) {
+                    const uint8_t* c = codes + j * cs;
                     const float* tab = lut;
                     float dis = dis0;
-                    for (int m = 0; m < ix->M; m++) { dis += tab[c[m]]; tab += ix->ksub; }
+                    for (int m = 0; m < M; m++) { dis += tab[c[m]]; tab += ksub; }
                     if (simi[0] < dis) { heap_pop(k, simi, idxi); heap_push(k, simi, idxi, dis, list_id(ix, l, j)); }
                 }
                 total += len;
