@@ -514,6 +514,70 @@ class _H5:
                 raise ValueError('new-style (link message) groups are not supported')
         return None
 
+    # -- attributes (object-header attribute messages; h5py's default for small attributes) ---------------------------------
+    @property
+    def root_addr(self):
+        return self.root_header
+
+    def _global_heap_object(self, coll_addr, index):
+        a = self.base + coll_addr
+        if bytes(self.buf[a:a + 4]) != b'GCOL':
+            raise ValueError('bad global heap collection signature')
+        size = struct.unpack_from('<Q', self.buf, a + 8)[0]
+        pos, end = a + 16, a + size
+        while pos + 16 <= end:
+            idx, _, _, osize = struct.unpack_from('<HHIQ', self.buf, pos)
+            if idx == 0:
+                break
+            if idx == index:
+                return bytes(self.buf[pos + 16:pos + 16 + osize])
+            pos += 16 + ((osize + 7) // 8) * 8
+        raise ValueError(f'global heap object {index} not found')
+
+    def _attr_value(self, dt_at, ds_at, data_at):
+        cls_ver, b0, b1, _, size = struct.unpack_from('<BBBBI', self.buf, dt_at)
+        cls = cls_ver & 0x0F
+        sver, rank = struct.unpack_from('<BB', self.buf, ds_at)
+        dims = struct.unpack_from(f'<{rank}Q', self.buf, ds_at + (8 if sver == 1 else 4)) if rank else ()
+        count = int(np.prod(dims)) if rank else 1
+        if cls == 3:                                            # fixed-length string (null-terminated / null- or space-padded)
+            vals = [bytes(self.buf[data_at + i * size:data_at + (i + 1) * size]).split(b'\0')[0].decode('utf-8') for i in range(count)]
+        elif cls == 9 and (b0 & 0x0F) == 1:                     # variable-length string: (length, global heap collection, index)
+            vals = []
+            for i in range(count):
+                n, coll, idx = struct.unpack_from('<IQI', self.buf, data_at + 16 * i)
+                vals.append(self._global_heap_object(coll, idx)[:n].decode('utf-8') if n else '')
+        elif cls in (0, 1):
+            vals = np.frombuffer(self.buf, self._dtype(dt_at), count, data_at).copy()
+            return vals.reshape(dims) if rank else vals[0]
+        else:
+            raise ValueError(f'attribute datatype class {cls} is not supported')
+        return vals[0] if not rank else vals
+
+    def attributes(self, addr):
+        """object header address -> {attribute name: str | number | ndarray} (attribute message versions 1-3)."""
+        out = {}
+        for mtype, _, data, msize in self.messages(addr):
+            if mtype != 0x000C:
+                continue
+            ver = self.buf[data]
+            name_sz, dt_sz, ds_sz = struct.unpack_from('<HHH', self.buf, data + 2)
+            if ver == 1:
+                pad = lambda n: (n + 7) // 8 * 8
+                pos = data + 8
+            elif ver in (2, 3):
+                if self.buf[data + 1] & 0x03:
+                    raise ValueError('shared attribute datatypes / dataspaces are not supported')
+                pad = lambda n: n
+                pos = data + (9 if ver == 3 else 8)
+            else:
+                raise ValueError(f'attribute message version {ver} not supported')
+            name = bytes(self.buf[pos:pos + name_sz]).split(b'\0')[0].decode('utf-8')
+            dt_at = pos + pad(name_sz)
+            ds_at = dt_at + pad(dt_sz)
+            out[name] = self._attr_value(dt_at, ds_at, ds_at + pad(ds_sz))
+        return out
+
     # -- datasets -------------------------------------------------------------------------------------------------------
     def _dtype(self, data):
         cls_ver, b0, _, _, size = struct.unpack_from('<BBBBI', self.buf, data)
@@ -629,6 +693,13 @@ def read_hdf5(path, max_depth=8):
         raise ValueError(f'corrupt or unsupported HDF5 file {path}: {type(e).__name__}: {e}') from e
 
 
+def open_hdf5(path):
+    """-> the lazy reader (`children(addr)`, `dataset(addr)`, `attributes(addr)`, `root_addr`) over a memory map of the file."""
+    with open(path, 'rb') as f:
+        buf = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+    return _H5(buf)
+
+
 def read_idx2id(path):
     """idx2id.hdf5 -> {offset_key: {'doc': ints, 'word': ints}} (MIPS.load_idx_f, index.py:78-88)."""
     tree = read_hdf5(path)
@@ -717,7 +788,39 @@ class _H5Writer:
         msgs.append(self._msg(0x0008, layout))
         return self._header(msgs)
 
-    def group(self, links):
+    def _attr_msgs(self, attrs):
+        """{name: str (variable-length UTF-8 string in a global heap collection, what h5py writes for `g.attrs[k] = "text"`) |
+        bytes (fixed-length string)} -> version-1 attribute messages."""
+        if not attrs:
+            return []
+        vlen = [(k, v.encode('utf-8')) for k, v in attrs.items() if isinstance(v, str)]
+        objs, coll_at = {}, 0
+        if vlen:
+            body = bytearray()
+            for i, (k, raw) in enumerate(vlen, 1):
+                objs[k] = (i, len(raw))
+                body += struct.pack('<HHIQ', i, 1, 0, len(raw)) + raw + b'\0' * (-len(raw) % 8)
+            total = max(4096, 16 + len(body) + 16)
+            free = total - 16 - len(body)
+            body += struct.pack('<HHIQ', 0, 0, 0, free) + b'\0' * (free - 16)
+            coll_at = self.alloc(b'GCOL' + struct.pack('<BBBBQ', 1, 0, 0, 0, total) + bytes(body))
+        msgs = []
+        space = struct.pack('<BBBBI', 1, 0, 0, 0, 0)                                       # scalar dataspace
+        for k, v in attrs.items():
+            name = k.encode('utf-8') + b'\0'
+            if isinstance(v, str):
+                dt = struct.pack('<BBBBI', 0x19, 0x01, 0x01, 0, 16) + struct.pack('<BBBBI', 0x13, 0x10, 0, 0, 1)   # vlen string of UTF-8 chars
+                idx, n = objs[k]
+                data = struct.pack('<IQI', n, coll_at, idx)
+            else:
+                raw = bytes(v) + b'\0'
+                dt = struct.pack('<BBBBI', 0x13, 0x00, 0, 0, len(raw))                      # null-terminated ASCII string
+                data = raw
+            p8 = lambda b: b + b'\0' * (-len(b) % 8)
+            msgs.append(self._msg(0x000C, struct.pack('<BBHHH', 1, 0, len(name), len(dt), len(space)) + p8(name) + p8(dt) + p8(space) + data))
+        return msgs
+
+    def group(self, links, attrs=None):
         """links {name: object header address} -> (header address, btree address, heap address)"""
         names = sorted(links)                                  # the B-tree orders links by name
         if len(names) > 2 * self.LEAF_K * 2 * self.INTERNAL_K:
@@ -743,7 +846,7 @@ class _H5Writer:
             node += struct.pack('<QQ', s, k)
         node += b'\0' * (24 + 8 * (2 * self.INTERNAL_K + 1) + 8 * 2 * self.INTERNAL_K - len(node))
         tree_at = self.alloc(node)
-        return self._header([self._msg(0x0011, struct.pack('<QQ', tree_at, heap_at))]), tree_at, heap_at
+        return self._header([self._msg(0x0011, struct.pack('<QQ', tree_at, heap_at))] + self._attr_msgs(attrs)), tree_at, heap_at
 
     def finish(self, root):
         header, tree, heap = root
@@ -755,15 +858,18 @@ class _H5Writer:
         return bytes(self.b)
 
 
-def write_hdf5(path, tree, chunks=None):
+def write_hdf5(path, tree, chunks=None, attrs=None):
     """tree: nested dict {name: dict | ndarray} -> HDF5 file in the subset read_hdf5 understands.
-    chunks {dataset name: chunk shape}: store those datasets chunked with shuffle + deflate instead of contiguous."""
+    chunks {dataset name: chunk shape}: store those datasets chunked with shuffle + deflate instead of contiguous.
+    attrs {group name: {attribute: str | bytes}}: string attributes of the groups with that name (phrase dumps: context / title)."""
     w = _H5Writer()
     chunks = chunks or {}
+    attrs = attrs or {}
 
     def emit(node, name=None):
         if isinstance(node, dict):
-            return w.group({k: (emit(child, k)[0] if isinstance(child, dict) else emit(child, k)) for k, child in node.items()})
+            return w.group({k: (emit(child, k)[0] if isinstance(child, dict) else emit(child, k)) for k, child in node.items()},
+                           attrs.get(name))
         return w.dataset_chunked(node, chunks[name]) if name in chunks else w.dataset(node)
 
     data = w.finish(emit(tree))

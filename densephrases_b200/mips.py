@@ -17,7 +17,8 @@ On-disk artefacts: `MIPS(...)` takes the reference's paths.  It prefers this rep
 (`index.dph.npz`, `idx2id.npz`, `meta_dph.pkl`) and otherwise parses the reference's own files -- `index.faiss` (+ the
 `.ivfdata` payload of a merged index), `idx2id.hdf5`, `meta_compressed.pkl` with its blosc blobs -- with the pure-Python
 readers of densephrases_b200/artifacts.py (no faiss / h5py / blosc; see that module's STATUS note).
-`MIPS.from_components` wraps in-memory objects.
+`MIPS.from_components` wraps in-memory objects.  Without in-RAM metadata the phrase stage falls back to the phrase dump
+(phrase_dump.py: metadata and int8 token vectors per document, index.py:246-273) -- functional, not accelerated.
 """
 import json
 import logging
@@ -136,15 +137,20 @@ class MIPS(object):
                         break
         self.phrase_dump_dir = phrase_dump_dir
         self._attach(index, self.load_idx_f(idx2id_path), doc_groups, index_path, cuda, logging_level)
+        if doc_groups is None:                     # index.py:75-76: "Will read metadata directly from hdf5 files"
+            from .phrase_dump import PhraseDump
+            logger.info('Will read metadata and token vectors directly from the phrase dump (not accelerated)')
+            self.phrase_dump = PhraseDump(phrase_dump_dir)
 
     @classmethod
-    def from_components(cls, index, idx_f, doc_groups, index_path='synthetic_PQ', cuda=True, logging_level=logging.INFO):
+    def from_components(cls, index, idx_f, doc_groups, index_path='synthetic_PQ', cuda=True, logging_level=logging.INFO, phrase_dump=None):
         """index: IvfPqIndex-like (search / reconstruct_batch / opq_matrix / ntotal / d / nprobe);
         idx_f: {str(offset): {'doc','word'}} (idx2id.hdf5 layout, build_phrase_index.py:268-276);
         doc_groups: {str(doc_idx): {'word2char_start','word2char_end','f2o_start','context','title'}} (meta_compressed.pkl)."""
         self = cls.__new__(cls)
         self.phrase_dump_dir = None
         self._attach(index, idx_f, doc_groups, index_path, cuda, logging_level)
+        self.phrase_dump = phrase_dump            # object with .get(doc_idx) -> record (phrase_dump.py); used when doc_groups is None
         return self
 
     def _attach(self, index, idx_f, doc_groups, index_path, cuda, logging_level):
@@ -163,6 +169,7 @@ class MIPS(object):
         self.stage_seconds = {'mips': 0.0, 'get_idxs': 0.0, 'phrase_vectors': 0.0, 'phrase_select': 0.0, 'metadata': 0.0, 'batches': 0}
         self.sentencizer = RuleSentencizer()
         self.offset = self.scale = None
+        self.phrase_dump = None
         logger.info(f'index ntotal: {self.index.ntotal} | PQ: {self.is_pq} | nprobe: {self.index.nprobe}')
 
     # ---- loading helpers -------------------------------------------------------------------------------
@@ -255,36 +262,80 @@ class MIPS(object):
             q = torch.from_numpy(np.ascontiguousarray(qvec, dtype=np.float32)).to(self.device)
             return (q.unsqueeze(1) * w).sum(2).cpu().numpy(), w.cpu().numpy()
 
+    def _windows_from_dump(self, docs, s_doc, s_word, e_doc, e_word, L):
+        """The phrase-dump branch of the reference (index.py:246-273,330-336,356-361): metadata straight from the dump's document
+        groups; for a start hit the int8 rows [start, min(start + L, T)) of the document's `start` dataset, left-aligned in an L-row
+        window, for an end hit the rows [max(0, end - L + 1), end], right-aligned; filled rows are dequantised x / 20 - 2, padding
+        rows stay 0.  Also returns the RAW first / last rows: the reference hands those, not the dequantised ones, to the
+        `return_idxs` vectors (index.py:381-389)."""
+        recs = {d: self.phrase_dump.get(d) for d in docs}
+        meta = {d: {'word2char_start': np.asarray(r['word2char_start']), 'word2char_end': np.asarray(r['word2char_end']),
+                    'f2o_start': np.asarray(r['f2o_start']), 'context': r['context'], 'title': r['title'], 'offset': -2, 'scale': 20}
+                for d, r in recs.items()}
+        H, dim = len(s_doc), self.index.d
+        raw_f, raw_b = np.zeros((H, L, dim), dtype=np.float32), np.zeros((H, L, dim), dtype=np.float32)
+        fwd, bwd = np.zeros((H, L, dim), dtype=np.float32), np.zeros((H, L, dim), dtype=np.float32)
+
+        def dequant(rows):                                   # int8_to_float(num, offset=-2, factor=20) = num / factor + offset
+            return np.asarray(rows).astype(np.float64) / 20.0 + (-2.0)
+        for h in range(H):
+            if s_doc[h] in recs:
+                vec = recs[s_doc[h]]['start']
+                a = int(s_word[h])
+                rows = np.asarray(vec[a:min(a + L, len(vec))]) if a >= 0 else np.zeros((0, dim))
+                n = len(rows)
+                if n:
+                    raw_f[h, :n], fwd[h, :n] = rows, dequant(rows)
+            if e_doc[h] in recs:
+                vec = recs[e_doc[h]]['start']
+                b = int(e_word[h])
+                rows = np.asarray(vec[max(0, b - L + 1):b + 1]) if b >= 0 else np.zeros((0, dim))
+                n = len(rows)
+                if n:
+                    raw_b[h, L - n:], bwd[h, L - n:] = rows, dequant(rows)
+        return meta, fwd, bwd, raw_f[:, 0], raw_b[:, -1]
+
     def search_phrase(self, query, start_doc_idxs, start_idxs, orig_start_idxs, end_doc_idxs, end_idxs, orig_end_idxs,
                       start_scores, end_scores, top_k=10, max_answer_length=10, return_idxs=False, return_sent=False):
-        """For every start hit pick the best end within L tokens and vice versa (index.py:220-422), PQ + in-RAM metadata."""
-        if self.doc_groups is None or orig_start_idxs is None:
-            raise NotImplementedError('reading token vectors from the HDF5 phrase dump (index.py:246-273) needs h5py; '
-                                      'use a PQ index with meta_dph.pkl')
+        """For every start hit pick the best end within L tokens and vice versa (index.py:220-422).  Token vectors come from the
+        index (`reconstruct`, PQ + in-RAM metadata: the accelerated branch) or -- when there is no `meta_compressed.pkl` -- from the
+        int8 `start` rows of the phrase dump together with the dump's own metadata (index.py:246-273; functional, not accelerated)."""
+        from_dump = self.doc_groups is None or orig_start_idxs is None
+        if from_dump and self.phrase_dump is None:
+            raise NotImplementedError('no in-RAM metadata (meta_compressed.pkl / meta_dph.pkl) and no phrase dump to read token vectors '
+                                      'and metadata from (index.py:246-273)')
         L, B = max_answer_length, query.shape[0]
         q_rep = np.repeat(query, top_k, axis=0)                         # row h = hit h of query h // top_k
         q_start, q_end = np.split(q_rep, 2, axis=1)
         owner = np.repeat(np.arange(B), 2 * top_k)
-        s_doc, s_word, s_lab, s_sc = (np.reshape(a, [-1]) for a in (start_doc_idxs, start_idxs, orig_start_idxs, start_scores))
-        e_doc, e_word, e_lab, e_sc = (np.reshape(a, [-1]) for a in (end_doc_idxs, end_idxs, orig_end_idxs, end_scores))
+        s_doc, s_word, s_sc = (np.reshape(a, [-1]) for a in (start_doc_idxs, start_idxs, start_scores))
+        e_doc, e_word, e_sc = (np.reshape(a, [-1]) for a in (end_doc_idxs, end_idxs, end_scores))
         assert len(s_doc) == len(s_word) == len(e_word) == len(s_sc)
         H = len(s_doc)
 
         tic = time()
         docs = [d for d in dict.fromkeys(s_doc.tolist() + e_doc.tolist()) if d >= 0]
-        meta = {d: self.decompress_meta(str(d)) for d in docs}
-        packed = _PackedDocs(meta)
         span = np.arange(L, dtype=np.int64)
-        fwd_labels = s_lab.astype(np.int64)[:, None] + span              # [start, start+L)        (index.py:284)
-        bwd_labels = e_lab.astype(np.int64)[:, None] - (L - 1) + span    # (end-L, end]            (index.py:294)
-        fused = (not return_idxs) and hasattr(self.index, 'window_scores')
-        if fused:   # one CUDA call per direction: reconstruct + un-rotate + dot fused (libdph_b200: dph_index_window_scores)
+        if from_dump:
+            meta, fwd, bwd, fwd_first, bwd_last = self._windows_from_dump(docs, s_doc, s_word, e_doc, e_word, L)
+            fused = False
+        else:
+            meta = {d: self.decompress_meta(str(d)) for d in docs}
+            s_lab, e_lab = np.reshape(orig_start_idxs, [-1]), np.reshape(orig_end_idxs, [-1])
+            fwd_labels = s_lab.astype(np.int64)[:, None] + span              # [start, start+L)        (index.py:284)
+            bwd_labels = e_lab.astype(np.int64)[:, None] - (L - 1) + span    # (end-L, end]            (index.py:294)
+            fused = (not return_idxs) and hasattr(self.index, 'window_scores')
+        packed = _PackedDocs(meta)
+        if from_dump:
+            pass
+        elif fused:   # one CUDA call per direction: reconstruct + un-rotate + dot fused (libdph_b200: dph_index_window_scores)
             end_sc = self.index.window_scores(q_end, fwd_labels[:, 0], L)
             start_sc = self.index.window_scores(q_start, bwd_labels[:, 0], L)
         else:
             vecs, _ = self.reconst_batch(np.concatenate([fwd_labels.ravel(), bwd_labels.ravel()]))   # missing label -> zeros
             vecs = np.asarray(vecs, dtype=np.float32)
             fwd, bwd = vecs[:H * L].reshape(H, L, -1), vecs[H * L:].reshape(H, L, -1)
+            fwd_first, bwd_last = fwd[:, 0], bwd[:, -1]
         self.stage_seconds['phrase_vectors'] += time() - tic
         logger.debug(f'1) {time()-tic:.3f}s: reconstruct vecs')
 
@@ -318,8 +369,8 @@ class MIPS(object):
         score = np.stack([score_se.max(1), score_es.max(1)], 1).ravel()
         if return_idxs:   # un-rotated start/end vectors for query-side fine-tuning (index.py:381-389): R is applied once more
             R = self.R.cpu().numpy()
-            svec = np.stack([fwd[:, 0], bwd_unrot[np.arange(H), pick_s]], 1).reshape(2 * H, -1).dot(R)
-            evec = np.stack([fwd_unrot[np.arange(H), pick_e], bwd[:, -1]], 1).reshape(2 * H, -1).dot(R)
+            svec = np.stack([fwd_first, bwd_unrot[np.arange(H), pick_s]], 1).reshape(2 * H, -1).dot(R)
+            evec = np.stack([fwd_unrot[np.arange(H), pick_e], bwd_last], 1).reshape(2 * H, -1).dot(R)
 
         results = [[] for _ in range(B)]
         for h, (d, a, b, sc) in enumerate(zip(doc_of.tolist(), first.tolist(), last.tolist(), score.tolist())):

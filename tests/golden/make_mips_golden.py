@@ -92,6 +92,39 @@ def main():
     json.dump(out, open(path, "w"), ensure_ascii=True)
     print(path, os.path.getsize(path), [len(r) for r in out["configs"][0]["results"]])
 
+    # ---- the phrase-dump branch (index.py:246-273): no in-RAM metadata -> h5py groups serve metadata AND int8 token vectors ----
+    recs = test_mips.dump_records(doc_groups)
+
+    class Group(dict):                                      # h5py.Group stand-in: datasets by name (numpy arrays), .attrs
+        def __init__(self, rec):
+            super().__init__({f: rec[f] for f in ("start", "word2char_start", "word2char_end", "f2o_start")})
+            self.attrs = {"context": rec["context"], "title": rec["title"]}
+
+    class File(dict):                                       # h5py.File stand-in
+        def __init__(self, path, mode):
+            super().__init__({k: Group(r) for k, r in recs.items()})
+
+        def close(self):
+            pass
+    sys.modules["h5py"].File = File
+
+    def fresh_dump():
+        m = fresh()
+        m.doc_groups, m.phrase_dump_dir = None, "/nonexistent/phrase.hdf5"      # not a directory: one dump file (index.py:98-99)
+        return m
+    out2 = {"nprobe": 8, "top_k": 5, "configs": []}
+    for aggregate, agg, ridx in [(False, "opt1", True), (True, "opt1", False), (True, "opt2", True), (True, "opt4", False)]:
+        res = fresh_dump().search(query, q_texts=["q"] * len(query), nprobe=8, top_k=5, aggregate=aggregate, agg_strat=agg, return_idxs=ridx)
+        rows = [[dict({"context": r["context"], "title": r["title"], "doc_idx": int(r["doc_idx"]), "start_pos": int(r["start_pos"]),
+                       "end_pos": int(r["end_pos"]), "start_idx": int(r["start_idx"]), "end_idx": int(r["end_idx"]), "score": float(r["score"]),
+                       "answer": r["answer"]},
+                      **({"start_vec_sum": float(np.sum(r["start_vec"])), "end_vec_sum": float(np.sum(r["end_vec"]))} if ridx else {}))
+                 for r in rs] for rs in res]
+        out2["configs"].append({"aggregate": aggregate, "agg_strat": agg, "return_idxs": ridx, "results": rows})
+    path = os.path.join(ROOT, "tests", "golden", "mips_search_hdf5.json")
+    json.dump(out2, open(path, "w"), ensure_ascii=True)
+    print(path, os.path.getsize(path), [len(r) for r in out2["configs"][0]["results"]])
+
 
 if __name__ == "__main__":
     main()

@@ -192,6 +192,52 @@ def test_faiss_reader_and_search_oracle_against_real_faiss(tmp_path):
     assert np.array_equal(If, Ir) and np.abs(Df - Dr).max() < 1e-3
 
 
+def test_hdf5_groups_datasets_and_string_attributes_round_trip(tmp_path):
+    """The phrase-dump subset (one group per document, int8 / int datasets, `context` / `title` string attributes:
+    embed_utils.py:233-246) written by this module's writer -- variable-length UTF-8 strings in a global heap collection like h5py's
+    `g.attrs[k] = "text"`, and fixed-length strings -- and read back lazily."""
+    rng = np.random.default_rng(5)
+    tree = {str(d): {"start": rng.integers(-128, 128, (T, 16), dtype=np.int8), "f2o_start": np.arange(T, dtype=np.int64)} for d, T in ((3, 5), (40, 1), (41, 0))}
+    attrs = {"3": {"context": "Paris is the capital. [PAR] caf\u00e9 \u2713 " * 200, "title": "Paris"}, "40": {"context": "", "title": b"fixed"},
+             "41": {"context": "x", "title": "T"}}
+    p = str(tmp_path / "0-1.hdf5")
+    A.write_hdf5(p, tree, attrs=attrs)
+    h = A.open_hdf5(p)
+    root = h.children(h.root_addr)
+    assert sorted(root) == sorted(tree)
+    for k, addr in root.items():
+        got, members = h.attributes(addr), h.children(addr)
+        assert got["context"] == attrs[k]["context"]
+        assert got["title"] == (attrs[k]["title"].decode() if isinstance(attrs[k]["title"], bytes) else attrs[k]["title"])
+        assert np.array_equal(h.dataset(members["start"]), tree[k]["start"]) and h.dataset(members["start"]).dtype == np.int8
+    assert h.attributes(h.root_addr) == {}
+    assert np.array_equal(A.read_hdf5(p)["3"]["f2o_start"], tree["3"]["f2o_start"])      # attributes do not disturb the eager reader
+
+
+def test_phrase_dump_reader_against_h5py(tmp_path):
+    """Auto-enabled where h5py exists: a phrase-dump-like file written by h5py itself, read by the native reader (PhraseDump)."""
+    h5py = pytest.importorskip("h5py")
+    from densephrases_b200.phrase_dump import _NativeFile
+    rng = np.random.default_rng(1)
+    p = str(tmp_path / "0-1.hdf5")
+    want = {}
+    with h5py.File(p, "w") as f:
+        for d in (0, 17):
+            g = f.create_group(str(d))
+            want[str(d)] = {"start": rng.integers(-128, 128, (9, 768), dtype=np.int8), "f2o_start": np.arange(9), "word2char_start": np.arange(9) * 3,
+                            "word2char_end": np.arange(9) * 3 + 2, "context": "some context caf\u00e9 " * 30, "title": f"title {d}"}
+            for name in ("start", "f2o_start", "word2char_start", "word2char_end"):
+                g.create_dataset(name, data=want[str(d)][name])
+            g.attrs["context"], g.attrs["title"] = want[str(d)]["context"], want[str(d)]["title"]
+    nf = _NativeFile(p)
+    for k, w in want.items():
+        assert nf.has(k)
+        rec = nf.group(k)
+        assert rec["context"] == w["context"] and rec["title"] == w["title"]
+        for name in ("start", "f2o_start", "word2char_start", "word2char_end"):
+            assert np.array_equal(np.asarray(rec[name]), w[name])
+
+
 def test_hdf5_reader_against_h5py(tmp_path):
     h5py = pytest.importorskip("h5py")
     rng = np.random.default_rng(0)

@@ -39,6 +39,19 @@ def build(oracle, n_docs=12):
     return doc_groups, idx_f, (A, pq, Cm, list_len, codes, ids), ref, query
 
 
+def dump_records(doc_groups, seed=21):
+    """The synthetic corpus in the phrase-dump form (one record per document: int8 token vectors `start`, the maps, context / title),
+    shared by the golden generator (served to the UNMODIFIED reference through a stand-in h5py) and the tests."""
+    rng = np.random.default_rng(seed)
+    recs = {}
+    for k, g in doc_groups.items():
+        T = len(g['f2o_start'])
+        recs[str(k)] = {'start': rng.integers(-128, 128, (T, 768), dtype=np.int8), 'word2char_start': np.asarray(g['word2char_start']),
+                        'word2char_end': np.asarray(g['word2char_end']), 'f2o_start': np.asarray(g['f2o_start']),
+                        'context': g['context'], 'title': g['title']}
+    return recs
+
+
 def compare(outs, refs, vec_tol=None):
     assert len(outs) == len(refs)
     for got, want in zip(outs, refs):
@@ -64,6 +77,32 @@ def test_mips_host_logic_matches_reference_restatement_cpu(oracle, aggregate, ag
                       normalize_answer=normalize_answer)
     compare(outs, refs, vec_tol=1e-3)
     assert len(mips.num_docs_list) == 1
+
+
+def test_fused_window_score_branch_on_cpu(oracle):
+    """The branch MIPS takes on the GPU (index.window_scores: reconstruct + un-rotate + dot fused in one call, return_idxs=False),
+    driven on the CPU by an adapter that computes the same window scores from the oracle: same results as the reference restatement."""
+    from densephrases_b200.mips import MIPS, normalize_answer
+    from oracle.mips_ref import ref_search
+
+    class Fused(OracleIndexAdapter):
+        calls = 0
+
+        def window_scores(self, q, first_ids, L):
+            Fused.calls += 1
+            xq = self.ref.rotate(np.ascontiguousarray(q, dtype=np.float32))          # <q, A^T v> == <A q, v>
+            out = np.zeros((len(first_ids), L), dtype=np.float32)
+            for j in range(L):
+                v, _ = self.ref.reconstruct(np.asarray(first_ids, dtype=np.int64) + j)     # missing label -> zero row
+                out[:, j] = (xq * v).sum(1)
+            return out
+    doc_groups, idx_f, _, ref, query = build(oracle)
+    mips = MIPS.from_components(Fused(ref), idx_f, doc_groups, cuda=False)
+    mips.index.nprobe = 8
+    outs = mips.search(query, q_texts=['q'] * len(query), top_k=5, aggregate=True, agg_strat='opt1', return_idxs=False)
+    assert Fused.calls == 2                                                          # one fused call per direction
+    refs = ref_search(ref, idx_f, doc_groups, query, top_k=5, nprobe=8, aggregate=True, agg_strat='opt1', normalize_answer=normalize_answer)
+    compare(outs, refs)
 
 
 def test_get_idxs_clips_out_of_range(oracle):
@@ -163,6 +202,47 @@ def test_phrase_stage_matches_reference_golden(oracle, which):
                     assert g[key] == w[key], (cfg["agg_strat"], key, g[key], w[key])
                 assert abs(g["score"] - w["score"]) <= 1e-3 * max(1.0, abs(w["score"]))
                 assert abs(float(np.sum(g["start_vec"])) - w["start_vec_sum"]) < 5e-2 and abs(float(np.sum(g["end_vec"])) - w["end_vec_sum"]) < 5e-2
+
+
+@pytest.mark.parametrize("source", ["mapping", "native_hdf5_file"])
+def test_phrase_dump_branch_matches_reference_golden(oracle, source, tmp_path):
+    """Without in-RAM metadata the reference reads token vectors (int8 `start` rows, dequantised x / 20 - 2) and metadata from the phrase
+    dump (index.py:246-273).  tests/golden/mips_search_hdf5.json holds what the UNMODIFIED reference `MIPS.search` returned on that
+    branch (generator: make_mips_golden.py, a stand-in h5py serving these records); our MIPS reproduces it from an in-memory mapping
+    and from an HDF5 file written and read back by this repo's native subset writer / reader (groups, int8 datasets, string attributes)."""
+    import json
+    import os
+    from densephrases_b200 import artifacts
+    from densephrases_b200.mips import MIPS
+    from densephrases_b200.phrase_dump import DictPhraseDump, PhraseDump
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "mips_search_hdf5.json")))
+    doc_groups, idx_f, _, ref, query = build(oracle)
+    recs = dump_records(doc_groups)
+    if source == "mapping":
+        dump = DictPhraseDump(recs)
+    else:
+        path = str(tmp_path / "phrase" / "0-1.hdf5")
+        os.makedirs(os.path.dirname(path))
+        artifacts.write_hdf5(path, {k: {f: r[f] for f in ("start", "word2char_start", "word2char_end", "f2o_start")} for k, r in recs.items()},
+                             attrs={k: {"context": r["context"], "title": r["title"]} for k, r in recs.items()})
+        dump = PhraseDump(os.path.dirname(path))
+    for cfg in gold["configs"]:
+        mips = MIPS.from_components(OracleIndexAdapter(ref), idx_f, None, cuda=False, phrase_dump=dump)
+        mips.index.nprobe = gold["nprobe"]
+        outs = mips.search(query, q_texts=["q"] * len(query), top_k=gold["top_k"], aggregate=cfg["aggregate"], agg_strat=cfg["agg_strat"],
+                           return_idxs=cfg["return_idxs"])
+        assert len(outs) == len(cfg["results"])
+        for got, want in zip(outs, cfg["results"]):
+            assert len(got) == len(want), (cfg, len(got), len(want))
+            for g, w in zip(got, want):
+                for key in ("context", "title", "doc_idx", "start_pos", "end_pos", "start_idx", "end_idx", "answer"):
+                    assert g[key] == w[key], (cfg["agg_strat"], key, g[key], w[key])
+                assert abs(g["score"] - w["score"]) <= 1e-3 * max(1.0, abs(w["score"]))
+                if cfg["return_idxs"]:
+                    assert abs(float(np.sum(g["start_vec"])) - w["start_vec_sum"]) <= 2e-3 * max(1.0, abs(w["start_vec_sum"]))
+                    assert abs(float(np.sum(g["end_vec"])) - w["end_vec_sum"]) <= 2e-3 * max(1.0, abs(w["end_vec_sum"]))
+    with pytest.raises(NotImplementedError):                   # neither in-RAM metadata nor a dump
+        MIPS.from_components(OracleIndexAdapter(ref), idx_f, None, cuda=False).search(query, q_texts=["q"] * len(query), top_k=3)
 
 
 @pytest.mark.gpu
