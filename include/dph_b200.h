@@ -103,7 +103,9 @@ int dph_index_search_preassigned(dph_index* ix, const uint64_t* keys_gathered_de
  * rec [n_local, dph_index_record_floats()] = [768 f32 rotated query | nprobe i32 list numbers | nprobe f32 coarse scores].  After an
  * all-gather of the records, search_assigned (rec [n, ...], all queries in batch order) runs the rest of the search on this shard's
  * lists.  Same probes and scores as the unsharded search; the rotation and the exact re-rank of the tensor-core coarse quantizer are
- * done once per query instead of once per query and shard. */
+ * done once per query instead of once per query and shard.  Records and candidate keys are an exchange format between ranks running
+ * THIS library on replicas of the same coarse quantizer: list numbers inside them are trusted, not validated (a caller that
+ * fabricates them must keep them in [-1, nlist)). */
 int dph_index_record_floats(const dph_index* ix);
 int dph_index_coarse_split(dph_index* ix, const float* x_dev, int64_t n_local, float* rec_dev);
 int dph_index_search_assigned(dph_index* ix, const float* rec_dev, int64_t n, int k, float* D_dev, int64_t* I_dev, uint32_t* G_dev);
